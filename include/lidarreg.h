@@ -1,0 +1,150 @@
+/*
+ * lidarreg.h -- C ABI of the B200-native robust-registration hot path.
+ *
+ * Drop-in boundary for AmnonDrory/LidarRegistration's
+ *   Experiments/test.py --algo RANSAC --mode {MNN|MMN|no_filter}
+ * i.e. the work below Experiments/algorithms/FR.py:16 (citations relative to
+ * the reference tree).  Each entry point names the reference interface it
+ * replaces.  All array arguments are DEVICE pointers owned by the caller
+ * unless marked [host]; `stream` is a cudaStream_t passed as void*.  Every
+ * function returns 0 on success and a non-zero LrStatus otherwise, with a
+ * message available from lr_last_error(); nothing throws across the boundary.
+ * There is no CPU fallback: without a CUDA device every compute entry fails
+ * with LR_ERR_CUDA.
+ *
+ * Transforms are 4x4 row-major doubles in the column-vector convention
+ * (q ~ T[:3,:3] p + T[:3,3]), i.e. what FR() returns (FR.py:119) -- the
+ * transpose of pygcransac's row-vector pose (GC_RANSAC.py:55).
+ */
+#ifndef LIDARREG_H
+#define LIDARREG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum LrStatus {
+    LR_OK = 0,
+    LR_ERR_ARG = 1,   /* bad argument (null pointer, unsupported D / sample size, ...) */
+    LR_ERR_CUDA = 2,  /* CUDA runtime error, or no device */
+    LR_ERR_ALLOC = 3  /* workspace allocation failed */
+} LrStatus;
+
+/* sampler ids follow gcransac_python.cpp:462-465 (0 uniform, 1 PROSAC) and add
+ * Open3D's with-replacement draw */
+enum { LR_SAMPLER_UNIFORM = 0, LR_SAMPLER_PROSAC = 1, LR_SAMPLER_REPLACE = 2 };
+
+/* Parameters of one RANSAC run.  Mirrors the kwargs of
+ * pygcransac.findRigidTransform (GC_RANSAC.py:12-22) and of Open3D's
+ * registration_ransac_based_on_correspondence (FR.py:128-137). */
+typedef struct LrRansacParams {
+    double threshold;     /* inlier distance, metres (FR.py:85,95: 2*voxel = 0.6) */
+    double confidence;    /* stopping confidence; >= 1 disables the early exit (fixed budget) */
+    double elc_ratio;     /* edge-length similarity (preemption_edge_length.h:82: 0.9) */
+    int64_t max_iters;    /* hypothesis budget (--iters) */
+    uint64_t seed;        /* hypothesis h is a pure function of (seed, h) */
+    int32_t sample_size;  /* 3 (GC minimal sample) or 4 (FR.py:134 ransac_n) */
+    int32_t sampler;      /* LR_SAMPLER_* */
+    int32_t use_elc;      /* edge-length pre-rejection on/off (--fast_rejection ELC|NONE) */
+    int32_t round_size;   /* hypotheses per round; the confidence exit is evaluated at round ends */
+    int32_t refit;        /* also return the least-squares refit over the selected model's inliers */
+    int32_t reserved;
+} LrRansacParams;
+
+typedef struct LrRansacStats {
+    int64_t iters_run;    /* hypotheses generated (multiple of round_size unless capped by max_iters) */
+    int64_t n_scored;     /* hypotheses that passed ELC and were scored against all correspondences */
+    int64_t n_rechecked;  /* scored hypotheses whose fp32 count was ambiguous and was redone in fp64 */
+    int64_t best_id;      /* selected hypothesis (-1: none) */
+    int64_t best_count;   /* its inlier count (exact, fp64 semantics) */
+    int64_t refit_count;  /* inliers used by the refit */
+} LrRansacStats;
+
+/* ---- library ---------------------------------------------------------- */
+const char *lr_last_error(void);
+int lr_version(void);
+/* [host] outputs; number of SMs and compute capability of the current device */
+int lr_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* release every device workspace held by the library */
+int lr_shutdown(void);
+
+/* ---- correspondence search (Experiments/algorithms/matching.py) ------- */
+
+/* find_nn (matching.py:22-65).  f0[N,D], f1[M,D] fp32 row-major; D multiple of
+ * 8, D <= 128.  idx1[N] = argmin_j sqrt(max(|f0_i|^2+|f1_j|^2-2 f0_i.f1_j,1e-30)),
+ * lowest j on ties; idx1_2nd[N] (nullable) = same with column idx1[i] masked
+ * (matching.py:36-37).  Indices are int64 like the reference's. */
+int lr_match_nn(const float *f0, int64_t N, const float *f1, int64_t M, int D, int64_t *idx1,
+                int64_t *idx1_2nd, void *stream);
+
+/* nn_to_mutual (matching.py:222-239) incl. torch_intersect (:67-87): keeps
+ * (i, idx1[i]) iff i is the nearest neighbour of idx1[i] in f0.  out_i/out_j
+ * have room for N entries and come out sorted by i; *K [device] = count. */
+int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64_t M, int D, const int64_t *idx1,
+                    int64_t *out_i, int64_t *out_j, int64_t *K, void *stream);
+
+/* calc_distance_ratio_in_feature_space (matching.py:89-98): out[k] =
+ * |f0[i0[k]]-f1[i1[k]]| / (|f0[i0[k]]-f1[i2[k]]| + 1e-6), fp32. */
+int lr_match_ratio(const float *f0, const float *f1, int D, int64_t K, const int64_t *i0, const int64_t *i1,
+                   const int64_t *i2, float *out, void *stream);
+
+/* xyz[idx] gather that builds the correspondence arrays (FR.py:72-73):
+ * out[k,:] = xyz[idx[k],:], fp32 [.,3]. */
+int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, void *stream);
+
+/* ---- RANSAC rigid motion ---------------------------------------------- */
+
+/* Replaces pygcransac.findRigidTransform (GC_RANSAC.py:46-49,
+ * gcransac_python.cpp:404-624) and Open3D's
+ * registration_ransac_based_on_correspondence (FR.py:128-137): src[n,3],
+ * tgt[n,3] fp32 correspondences.  T_out[16] [host] = selected model (identity
+ * if none); T_refit[16] [host, nullable] = Kabsch over its inliers
+ * (FR.py:99-111); mask[n] (device, nullable) = inlier mask of the selected
+ * model; stats [host, nullable].  Synchronises `stream` before returning. */
+int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
+                    double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
+
+/* Fed-sample parity hook (BASELINE.json: "same fed hypothesis triplets").
+ * samples[H,m] int32 (m = 3 or 4).  counts[H] = exact inlier count of each
+ * sample's Kabsch model, -1 where ELC rejects it; models[H,12] (nullable) =
+ * the fp64 [R|t] rows; *best [host] = argmax count, lowest h on ties (-1 if
+ * every sample is rejected).  Synchronises `stream`. */
+int lr_ransac_score_samples(const float *src, const float *tgt, int64_t n, const int32_t *samples, int64_t H,
+                            int m, double threshold, int use_elc, double elc_ratio, int32_t *counts,
+                            double *models, int64_t *best, void *stream);
+
+/* Multi-GPU hypothesis sharding: score hypotheses [id_lo, id_hi)
+ * of the run described by `params` and max-merge the packed result
+ *   key = (count + 1) << 32 | (0xFFFFFFFF - id)
+ * into *key [device, uint64].  Asynchronous on `stream`.  The caller
+ * all-reduces (MAX) the keys across ranks between rounds. */
+int lr_ransac_shard(const float *src, const float *tgt, int64_t n, const LrRansacParams *params, int64_t id_lo,
+                    int64_t id_hi, uint64_t *key, void *stream);
+
+/* Turn a (reduced) key back into the model: regenerates hypothesis id from
+ * (seed, id), returns T_out / T_refit / mask / stats as lr_ransac_rigid does.
+ * `key` [host].  Synchronises `stream`. */
+int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, const LrRansacParams *params, uint64_t key,
+                       double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
+
+/* Confidence stopping rule shared by every rank: hypotheses needed once the
+ * best inlier count is c (Open3D: log(1-conf)/log(1-(c/n)^m)). */
+int64_t lr_ransac_conf_iters(int64_t c, int64_t n, int m, double confidence, int64_t max_iters);
+
+/* The hypothesis sampler itself, for parity tests: ids[H] int64 (device) ->
+ * samples[H,m] int32 (device). */
+int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t id_lo, int64_t H, int32_t *samples,
+                     void *stream);
+
+/* Refit over an indexed correspondence set (FR.py:99-111): inliers of
+ * (xyz0[i0[k]], xyz1[i1[k]]) under T_in [host] at `threshold`, then Kabsch.
+ * T_out[16] [host]; *count [host, nullable].  Synchronises `stream`. */
+int lr_refit_indexed(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1, int64_t K,
+                     const double *T_in, double threshold, double *T_out, int64_t *count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDARREG_H */

@@ -1,0 +1,140 @@
+"""Drop-in for Experiments/algorithms/FR.py (reference :16-139): the algorithm interface.
+
+FR(A, B, A_feat, B_feat, args, T_gt) keeps the reference's signature, the
+8-tuple it returns (FR.py:119), the mode / codebase switches and their
+assertion behaviour, and the timing bookkeeping (filter + algorithm + the
+extra cost of the 2nd nearest neighbour, FR.py:116-117).  `--mode MMN`
+(README.md:55 of the reference, a typo its own code rejects) is accepted as an
+alias of `MNN`.  All arithmetic runs in liblidarreg.so.
+"""
+from copy import deepcopy
+from time import time
+
+import numpy as np
+import torch
+
+from .. import engine
+from .GC_RANSAC import GC_RANSAC
+from .matching import (Grid_Prioritized_Filter, calc_distance_ratio_in_feature_space, find_2nn,
+                       measure_inlier_ratio, nn_to_mutual)
+
+__doc__ = (__doc__ or "") + "\nFast RANSAC algorithms\n"
+
+VOXEL_SIZE = 0.3  # FR.py:18
+
+
+class PointCloud:
+    """Minimal stand-in for o3d.geometry.PointCloud: what the path itself touches
+    (`.points`, `.transform(T)`, deepcopy; matching.py:244-247, FR.py:102-104).  When
+    open3d is importable the real class is returned instead, so the caller's ICP step
+    (Experiments/test.py:185-187) keeps working."""
+
+    def __init__(self, xyz=None):
+        self.points = np.zeros((0, 3)) if xyz is None else np.asarray(xyz, dtype=np.float64)
+
+    def transform(self, T):
+        T = np.asarray(T, dtype=np.float64)
+        self.points = self.points @ T[:3, :3].T + T[:3, 3]
+        return self
+
+    def __deepcopy__(self, memo):
+        return PointCloud(self.points.copy())
+
+
+def make_point_cloud(xyz):
+    try:
+        import open3d as o3d  # noqa: F401  (optional: absent in the build image)
+        pcd = o3d.geometry.PointCloud()
+        pcd.points = o3d.utility.Vector3dVector(xyz)
+        return pcd
+    except Exception:
+        return PointCloud(xyz)
+
+
+def FR(A, B, A_feat, B_feat, args, T_gt):
+    voxel_size = VOXEL_SIZE
+    xyz0, xyz1 = A, B
+    xyz0_np = xyz0.detach().cpu().numpy().astype(np.float64)
+    xyz1_np = xyz1.detach().cpu().numpy().astype(np.float64)
+    pcd0 = make_point_cloud(xyz0_np)
+    pcd1 = make_point_cloud(xyz1_np)
+
+    fcgf_feats0 = engine.to_dev_f32(A_feat)  # FR.py:32-34 [H->D]
+    fcgf_feats1 = engine.to_dev_f32(B_feat)
+    mode = "MNN" if args.mode == "MMN" else args.mode
+
+    with torch.no_grad():
+        # 1. Coarse correspondences
+        corres_idx0, corres_idx1, idx1_2nd, additional_time_for_finding_2nd_closest = find_2nn(fcgf_feats0,
+                                                                                              fcgf_feats1)
+        num_pairs_init = len(corres_idx0)
+        inlier_ratio_init = measure_inlier_ratio(corres_idx0, corres_idx1, pcd0, pcd1, T_gt, voxel_size)
+
+        torch.cuda.synchronize()
+        start_time = time()
+        # 2. Filter correspondences
+        norm_feat_dist = None
+        if mode == "MNN":
+            corres_idx0_orig, corres_idx1_orig = corres_idx0, corres_idx1
+            corres_idx0, corres_idx1, idx1_2nd = nn_to_mutual(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
+                                                              idx1_2nd, force_return_2nd=True)
+        elif mode == "GPF":
+            corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, _, norm_feat_dist = \
+                Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args)
+        elif mode == "no_filter":
+            corres_idx0_orig, corres_idx1_orig = corres_idx0, corres_idx1
+        else:
+            assert False, "unknown mode"
+        torch.cuda.synchronize()
+        filter_time = time() - start_time
+
+        num_pairs_filtered = len(corres_idx0)
+        inlier_ratio_filtered = measure_inlier_ratio(corres_idx0, corres_idx1, pcd0, pcd1, T_gt, voxel_size)
+
+    start_time = time()
+    ransac_iters = 500 * 10 ** 3  # FR.py:65
+    if args.iters is not None:
+        ransac_iters = args.iters
+
+    # 3. Perform RANSAC
+    if args.codebase == "GC":
+        A_ = xyz0_np[corres_idx0, :].astype(np.float32)
+        B_ = xyz1_np[corres_idx1, :].astype(np.float32)
+        if args.prosac:
+            if mode == 'GPF':
+                feat_dist = norm_feat_dist.detach().cpu().numpy()
+            else:
+                feat_dist = calc_distance_ratio_in_feature_space(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
+                                                                 idx1_2nd).detach().cpu().numpy()
+            match_quality = -feat_dist
+        else:
+            match_quality = None
+        T, _ = GC_RANSAC(A_, B_, distance_threshold=2 * voxel_size, num_iterations=ransac_iters, args=args,
+                         match_quality=match_quality)
+
+    elif args.codebase == "open3D":
+        T = RANSAC_registration(pcd0, pcd1, corres_idx0, corres_idx1, 2 * voxel_size, num_iterations=ransac_iters,
+                                args=args)
+        # estimate motion using all inlier pairs of the ORIGINAL (unfiltered) NN set (FR.py:99-111)
+        T, _ = engine.refit_indexed(xyz0.detach().float(), xyz1.detach().float(), corres_idx0_orig,
+                                    corres_idx1_orig, T, 2 * voxel_size)
+    else:
+        assert False, "unknown codebase"
+
+    torch.cuda.synchronize()
+    algo_time = time() - start_time
+    elapsed_time = filter_time + algo_time + additional_time_for_finding_2nd_closest
+    return T, elapsed_time, pcd0, pcd1, num_pairs_init, inlier_ratio_init, num_pairs_filtered, inlier_ratio_filtered
+
+
+def RANSAC_registration(pcd0, pcd1, idx0, idx1, distance_threshold, num_iterations, args):
+    """FR.py:122-139: Open3D registration_ransac_based_on_correspondence with ransac_n=4,
+    CorrespondenceCheckerBasedOnEdgeLength (0.9), confidence 0.9995, no refit inside."""
+    xyz0 = torch.from_numpy(np.asarray(pcd0.points)).float()
+    xyz1 = torch.from_numpy(np.asarray(pcd1.points)).float()
+    src = engine.gather_xyz(xyz0, idx0)
+    tgt = engine.gather_xyz(xyz1, idx1)
+    params = engine.make_params(threshold=distance_threshold, confidence=0.9995, max_iters=num_iterations,
+                                seed=getattr(args, "seed", 51), sample_size=4, sampler=engine.SAMPLER_REPLACE,
+                                use_elc=True, elc_ratio=0.9, refit=False)
+    return engine.ransac_rigid(src, tgt, params)["T"]

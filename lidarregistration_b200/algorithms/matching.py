@@ -1,0 +1,182 @@
+"""Drop-in for Experiments/algorithms/matching.py of AmnonDrory/LidarRegistration.
+
+Same function names, arguments, return types (int64 CPU index tensors, pairs
+sorted by idx0, lowest index on ties) and error behaviour as the reference
+file (citations: /root/reference/Experiments/algorithms/matching.py); the
+arithmetic runs in liblidarreg.so on the GPU.  The `*_dev` variants keep
+everything in HBM for the fused FR() path.
+"""
+from copy import deepcopy
+from time import time
+
+import numpy as np
+import torch
+
+from .. import engine
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+def find_nn(F0, F1, return_2nd=False):
+    """matching.py:22-65 -> (corres_idx0 = arange(N), corres_idx1, idx1_2nd | None), int64 CPU."""
+    idx1, idx2 = engine.match_nn(F0, F1, want_2nd=return_2nd)
+    N = idx1.shape[0]
+    corres_idx0 = torch.arange(N).long().squeeze()
+    corres_idx1 = idx1.long().squeeze().cpu()
+    if return_2nd:
+        return corres_idx0, corres_idx1, idx2.long().squeeze().cpu()
+    return corres_idx0, corres_idx1, None
+
+
+def find_2nn(fcgf_feats0, fcgf_feats1):
+    """matching.py:6-19: NN + 2nd NN and the *extra* seconds the 2nd NN costs.
+
+    The reference times find_nn twice and reports the difference; the same
+    bookkeeping is kept (both sweeps are timed on the device) so that
+    `model_time` keeps its meaning (FR.py:117).
+    """
+    f0, f1 = engine.to_dev_f32(fcgf_feats0), engine.to_dev_f32(fcgf_feats1)
+    _sync()
+    t0 = time()
+    engine.match_nn(f0, f1, want_2nd=False)
+    _sync()
+    simple = time() - t0
+    t0 = time()
+    idx1, idx2 = engine.match_nn(f0, f1, want_2nd=True)
+    _sync()
+    extra = (time() - t0) - simple
+    N = idx1.shape[0]
+    return torch.arange(N).long().squeeze(), idx1.cpu(), idx2.cpu(), extra
+
+
+def torch_intersect(Na, Nb, i_ab, j_ab, i_ba, j_ba):
+    """matching.py:67-87: edges present in both lists, sorted by (i, j)."""
+    dev = i_ab.device
+    ka = i_ab.long() * Nb + j_ab.long()
+    kb = i_ba.long().to(dev) * Nb + j_ba.long().to(dev)
+    ka_u, kb_u = torch.unique(ka), torch.unique(kb)
+    both = ka_u[torch.isin(ka_u, kb_u)]
+    return both // Nb, both % Nb
+
+
+def nn_to_mutual(feats0, feats1, corres_idx0, corres_idx1, idx1_2nd=None, force_return_2nd=False):
+    """matching.py:222-239: keep (i, j) iff j = NN_1(i) and i = NN_0(j); sorted by i."""
+    assert len(corres_idx0) == len(feats0), "nn_to_mutual relies on corres_idx0 being the full range (matching.py:234)"
+    out_i, out_j = engine.match_mutual(feats0, feats1, corres_idx1)
+    final_corres_idx0, final_corres_idx1 = out_i.cpu(), out_j.cpu()
+    if idx1_2nd is not None:
+        idx1_2nd = idx1_2nd[final_corres_idx0]
+        return final_corres_idx0, final_corres_idx1, idx1_2nd
+    elif force_return_2nd:
+        return final_corres_idx0, final_corres_idx1, None
+    else:
+        return final_corres_idx0, final_corres_idx1
+
+
+def calc_distance_ratio_in_feature_space(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd):
+    """matching.py:89-98: d(f0_i, f1_nn) / (d(f0_i, f1_2nd) + 1e-6), fp32 (on the features' device)."""
+    out = engine.match_ratio(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd)
+    return out if getattr(fcgf_feats0, "is_cuda", False) else out.cpu()
+
+
+def mark_best_buddies(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1):
+    """matching.py:207-220: which NN pairs are mutual."""
+    bb_idx0, bb_idx1 = nn_to_mutual(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1)
+    corres_idx0_np = corres_idx0.detach().cpu().numpy()
+    corres_idx1_np = corres_idx1.detach().cpu().numpy()
+    P = 1 + np.max(corres_idx0_np)
+    bb_idx_flat = P * bb_idx1.numpy() + bb_idx0.numpy()
+    corres_idx_flat = P * corres_idx1_np + corres_idx0_np
+    is_bb = np.isin(corres_idx_flat, bb_idx_flat)
+    return is_bb, is_bb.sum()
+
+
+def Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args,
+                            BB_first=False):
+    """matching.py:100-205 (--mode GPF): best-buddy marking, 10x10 xy grid, water-filling quota,
+    per-cell selection by normalised ratio.  Host-side bookkeeping on top of the CUDA
+    mutual / ratio kernels."""
+    corres_idx0_orig = deepcopy(corres_idx0)
+    corres_idx1_orig = deepcopy(corres_idx1)
+    idx1_2nd_orig = deepcopy(idx1_2nd)
+    GRID_WID = args.GPF_grid_wid
+
+    if BB_first:
+        TOTAL_NUM = args.GPF_max_matches
+        corres_idx0, corres_idx1, idx1_2nd = nn_to_mutual(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
+                                                          idx1_2nd, force_return_2nd=True)
+        if TOTAL_NUM >= corres_idx0.shape[0]:
+            return corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, idx1_2nd_orig, None
+    else:
+        is_bb, num_bb = mark_best_buddies(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1)
+        TOTAL_NUM = args.GPF_factor * num_bb
+
+    feat_dist = calc_distance_ratio_in_feature_space(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
+                                                     idx1_2nd).cpu()
+    m, M = torch.min(feat_dist), torch.max(feat_dist)
+    norm_feat_dist = (feat_dist - m) / (M - m)
+    if not BB_first:
+        norm_feat_dist[torch.from_numpy(is_bb)] -= 1  # best buddies sort first (matching.py:126-134)
+
+    def to_quads(X):
+        EPS = 10 ** -3
+        lo, hi = torch.min(X), torch.max(X)
+        return torch.floor(GRID_WID * ((X - lo) / (hi - lo + EPS)))
+
+    xyz0_c = xyz0.detach().cpu() if torch.is_tensor(xyz0) else torch.from_numpy(np.asarray(xyz0))
+    quadrant_i = to_quads(xyz0_c[corres_idx0, 0]).numpy()
+    quadrant_j = to_quads(xyz0_c[corres_idx0, 1]).numpy()
+    cell = (quadrant_i * GRID_WID + quadrant_j).astype(np.int64)
+    max_per_quad = np.bincount(cell, minlength=GRID_WID * GRID_WID).astype(np.float64).reshape(GRID_WID, GRID_WID)
+
+    def apply_height(height):
+        is_dwarf = max_per_quad < height
+        return is_dwarf * max_per_quad + (~is_dwarf) * height
+
+    max_height, min_height = TOTAL_NUM, 0
+    curr_height = (max_height + min_height) / 2
+    while np.abs(max_height - min_height) > 2:
+        cur_total = apply_height(curr_height).sum()
+        if cur_total == TOTAL_NUM:
+            break
+        elif cur_total < TOTAL_NUM:
+            min_height = curr_height
+        else:
+            max_height = curr_height
+        curr_height = (max_height + min_height) / 2
+    per_quad = apply_height(np.round(curr_height))
+
+    keep = np.zeros(len(norm_feat_dist), dtype=bool)
+    nfd = norm_feat_dist.numpy()
+    for qi in range(GRID_WID):
+        for qj in range(GRID_WID):
+            quota = int(per_quad[qi, qj])
+            if quota <= 0:
+                continue
+            cand = np.nonzero(cell == qi * GRID_WID + qj)[0]
+            if per_quad[qi, qj] == max_per_quad[qi, qj]:
+                keep[cand] = True
+            else:
+                order = torch.argsort(norm_feat_dist[cand]).numpy()  # same sort as matching.py:192
+                keep[cand[order[:quota]]] = True
+    del nfd
+
+    corres_idx0 = corres_idx0[keep]
+    corres_idx1 = corres_idx1[keep]
+    norm_feat_dist = norm_feat_dist[keep]
+    idx1_2nd = idx1_2nd[keep] if idx1_2nd is not None else None
+    return corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, idx1_2nd_orig, norm_feat_dist
+
+
+def measure_inlier_ratio(corres_idx0, corres_idx1, pcd0, pcd1, T_gt, voxel_size):
+    """matching.py:241-249 (ground-truth statistic only; numpy fp64 like the reference)."""
+    corres_idx0_ = corres_idx0.detach().cpu().numpy()
+    corres_idx1_ = corres_idx1.detach().cpu().numpy()
+    pcd0_trans = deepcopy(pcd0)
+    pcd0_trans.transform(T_gt)
+    dist2 = np.sum((np.array(pcd0_trans.points)[corres_idx0_, :] - np.array(pcd1.points)[corres_idx1_, :]) ** 2,
+                   axis=1)
+    is_close = dist2 < (2 * voxel_size) ** 2
+    return float(is_close.sum()) / len(is_close)

@@ -1,0 +1,70 @@
+// lr_common.cuh -- shared host/device plumbing of liblidarreg (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/lidarreg.h"
+
+#define LR_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace lr {
+
+// thread-local error text returned by lr_last_error()
+void set_error(const char *fmt, ...);
+
+#define LR_CUDA_TRY(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            lr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));   \
+            return LR_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define LR_REQUIRE(cond, msg)                                        \
+    do {                                                             \
+        if (!(cond)) {                                               \
+            lr::set_error("%s:%d: %s", __FILE__, __LINE__, msg);     \
+            return LR_ERR_ARG;                                       \
+        }                                                            \
+    } while (0)
+
+// Grow-only device scratch, one arena per (device, slot).  The library owns
+// nothing else on the device.  Not shared between concurrent calls: every entry
+// point takes the arena lock for its duration (the reference path is called
+// from one Python thread per process, Experiments/test.py:108-167).
+enum Slot { SLOT_RANSAC = 0, SLOT_MATCH = 1, SLOT_MISC = 2, SLOT_COUNT = 3 };
+
+struct Arena {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+// returns nullptr (and sets the error) on failure
+void *arena_get(int slot, size_t bytes);
+void arena_release_all();
+int sm_count();
+
+struct Lock {
+    Lock();
+    ~Lock();
+};
+
+// carve 256-byte aligned pieces out of one arena block
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *p) : base(reinterpret_cast<char *>(p)) {}
+    template <class T>
+    T *take(size_t count)
+    {
+        T *r = reinterpret_cast<T *>(base + off);
+        off += (count * sizeof(T) + 255) & ~size_t(255);
+        return r;
+    }
+};
+inline size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+
+}  // namespace lr

@@ -1,0 +1,104 @@
+// lr_core.cu -- error text, device scratch arenas, library-level entry points.
+#include <mutex>
+#include <stdarg.h>
+
+#include "lr_common.cuh"
+
+namespace lr {
+
+static thread_local char g_err[512] = "";
+static std::recursive_mutex g_mu;
+static const int kMaxDev = 64;
+static Arena g_arena[kMaxDev][SLOT_COUNT];
+static int g_sms[kMaxDev];
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+Lock::Lock() { g_mu.lock(); }
+Lock::~Lock() { g_mu.unlock(); }
+
+void *arena_get(int slot, size_t bytes)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
+        set_error("no CUDA device (cudaGetDevice failed)");
+        return nullptr;
+    }
+    Arena &a = g_arena[dev][slot];
+    if (a.cap < bytes) {
+        if (a.ptr) {
+            cudaDeviceSynchronize();  // nobody may still be reading the old block
+            cudaFree(a.ptr);
+            a.ptr = nullptr;
+            a.cap = 0;
+        }
+        size_t want = bytes + bytes / 4 + (size_t(1) << 20);
+        cudaError_t e = cudaMalloc(&a.ptr, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            a.ptr = nullptr;
+            return nullptr;
+        }
+        a.cap = want;
+    }
+    return a.ptr;
+}
+
+void arena_release_all()
+{
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return;
+    for (int d = 0; d < kMaxDev; ++d)
+        for (int s = 0; s < SLOT_COUNT; ++s)
+            if (g_arena[d][s].ptr) {
+                cudaSetDevice(d);
+                cudaFree(g_arena[d][s].ptr);
+                g_arena[d][s] = Arena();
+            }
+    cudaSetDevice(cur);
+}
+
+int sm_count()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 148;
+    if (g_sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        g_sms[dev] = v;
+    }
+    return g_sms[dev];
+}
+
+}  // namespace lr
+
+LR_EXPORT const char *lr_last_error(void) { return lr::g_err; }
+
+LR_EXPORT int lr_version(void) { return 100; }
+
+LR_EXPORT int lr_device_info(int *sms, int *major, int *minor)
+{
+    int dev = 0;
+    LR_CUDA_TRY(cudaGetDevice(&dev));
+    int a = 0, b = 0, c = 0;
+    LR_CUDA_TRY(cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev));
+    LR_CUDA_TRY(cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev));
+    LR_CUDA_TRY(cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev));
+    if (sms) *sms = a;
+    if (major) *major = b;
+    if (minor) *minor = c;
+    return LR_OK;
+}
+
+LR_EXPORT int lr_shutdown(void)
+{
+    lr::Lock lock;
+    lr::arena_release_all();
+    return LR_OK;
+}

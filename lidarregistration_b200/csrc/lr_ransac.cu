@@ -1,0 +1,1079 @@
+// lr_ransac.cu -- batched RANSAC rigid-motion estimation for sm_100a.
+//
+// Replaces (reference tree citations):
+//   pygcransac.findRigidTransform        Experiments/algorithms/GC_RANSAC.py:46-49,
+//                                        GC-RANSAC/src/pygcransac/src/gcransac_python.cpp:404-624
+//   o3d registration_ransac_based_on_correspondence   Experiments/algorithms/FR.py:122-139
+//   EdgeLenPreemptiveVerification::verifyModel
+//                                        GC-RANSAC/src/pygcransac/include/preemption/preemption_edge_length.h:71-128
+//   inlier refit                         Experiments/algorithms/FR.py:99-111
+//
+// Structure of one round of R hypotheses (DESIGN.md "RANSAC kernels"):
+//   k_gen    one thread per hypothesis id: counter-based sample, ELC in fp64,
+//            fixed-sweep Jacobi Kabsch in fp64 registers; survivors are
+//            compacted (warp-aggregated) with an fp32 copy of [R|t] and the
+//            rigorous fp32 error band of the inlier test
+//   k_score  thread-owns-hypothesis sweep over all correspondences staged
+//            through shared memory with cp.async (float4 + float2 per point,
+//            broadcast reads); two counters bracket the exact count
+//   k_recount  the few hypotheses whose bracket is open are recounted in the
+//            canonical fp64 arithmetic, one warp each
+//   k_round_end  packed (count, id) arg-max merge, confidence exit flag
+// fp64 arithmetic follows oracle/lr_oracle.c operation for operation (this
+// file is compiled with -fmad=false; FMAs are written explicitly where wanted).
+#include <math.h>
+
+#include <vector>
+
+#include "lr_common.cuh"
+
+namespace {
+
+constexpr int kScoreThreads = 128;  // hypotheses per score item (one per thread)
+constexpr int kChunk = 1024;        // correspondences per shared-memory stage
+constexpr int kGenThreads = 128;
+
+struct Ctl {
+    unsigned long long best_key;   // over finished rounds
+    unsigned long long round_key;  // current round
+    int n_surv;                    // survivors of the current round (compacted slots)
+    int n_flag;                    // slots whose fp32 bracket is open
+    int done;                      // confidence exit reached
+    int pad0;
+    long long iters_run, n_scored, n_rechecked;
+    unsigned int p1max_bits, qmax_bits;  // max |p|_1, max |q|_inf as float bits
+    long long refit_count;
+    double T[12], Tref[12];
+    double csum[6];
+    double H[9];
+};
+
+struct Ws {
+    Ctl *ctl;
+    float4 *P4;       // (px, py, pz, qx)
+    float2 *Q2;       // (qy, qz)
+    uint32_t *slot_id;
+    float4 *m32;      // 4 x float4 per slot: R rows + t, then (lo, hi, -, -)
+    double *m64;      // 12 per slot
+    int *flagged;
+    int *need;        // per round: inlier count that triggers the confidence exit
+    double *scratchT; // 16 doubles of staging
+    int64_t n_pad;
+};
+
+// ------------------------------------------------------------------------
+// canonical fp64 device arithmetic (mirrors oracle/lr_oracle.c)
+// ------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint32_t draw(uint64_t seed, uint64_t id, uint32_t d, uint32_t m)
+{
+    uint64_t r = mix64(mix64(seed ^ (id * 0xD1342543DE82EF95ULL)) + (uint64_t)d * 0x9E3779B97F4A7C15ULL);
+    return (uint32_t)(((r >> 32) * (uint64_t)m) >> 32);
+}
+
+template <int M>
+__device__ __forceinline__ void sample_ids(uint64_t seed, uint64_t id, int sampler, int64_t n, int32_t (&out)[M])
+{
+    if (sampler == LR_SAMPLER_REPLACE) {
+#pragma unroll
+        for (int d = 0; d < M; ++d) out[d] = (int32_t)draw(seed, id, d, (uint32_t)n);
+        return;
+    }
+    int32_t taken[M];
+#pragma unroll
+    for (int d = 0; d < M; ++d) {
+        int32_t r = (int32_t)draw(seed, id, d, (uint32_t)(n - d));
+#pragma unroll
+        for (int e = 0; e < M; ++e)
+            if (e < d && r >= taken[e]) ++r;
+        out[d] = r;
+        // sorted insert (fully unrolled bubble from the back)
+        taken[d] = r;
+#pragma unroll
+        for (int e = M - 1; e > 0; --e)
+            if (e <= d && taken[e - 1] > taken[e]) {
+                int32_t tmp = taken[e];
+                taken[e] = taken[e - 1];
+                taken[e - 1] = tmp;
+            }
+    }
+}
+
+__device__ __forceinline__ double len3(const double *a, const double *b)
+{
+    double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+    return sqrt((dx * dx + dy * dy) + dz * dz);
+}
+
+template <int M>
+__device__ __forceinline__ bool elc_pass(const double (&P)[M][3], const double (&Q)[M][3], double ratio)
+{
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = i + 1; j < M; ++j) {
+            double ds = len3(P[i], P[j]);
+            double dt = len3(Q[i], Q[j]);
+            if ((ds < dt * ratio) || (dt < ds * ratio)) ok = false;
+        }
+    return ok;
+}
+
+__device__ __forceinline__ double coldot(const double (&H)[3][3], int p, int q)
+{
+    return (H[0][p] * H[0][q] + H[1][p] * H[1][q]) + H[2][p] * H[2][q];
+}
+
+__device__ __forceinline__ void colswap(double (&A)[3][3], int p, int q)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double t = A[k][p];
+        A[k][p] = A[k][q];
+        A[k][q] = t;
+    }
+}
+
+// H = sum (q - cq)(p - cp)^T  ->  proper rotation (see oracle lro_rot_from_H)
+__device__ void rot_from_H(const double (&Hin)[3][3], double (&R)[3][3])
+{
+    double H[3][3], V[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            H[r][c] = Hin[r][c];
+            V[r][c] = (r == c) ? 1.0 : 0.0;
+        }
+#pragma unroll 1
+    for (int sweep = 0; sweep < 6; ++sweep) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int p = (r == 2) ? 1 : 0;
+            const int q = (r == 0) ? 1 : 2;
+            double alpha = coldot(H, p, p);
+            double beta = coldot(H, q, q);
+            double gamma = coldot(H, p, q);
+            double c = 1.0, s = 0.0;
+            if (gamma != 0.0) {
+                double zeta = (beta - alpha) / (2.0 * gamma);
+                double az = fabs(zeta);
+                double tt = 1.0 / (az + sqrt(1.0 + zeta * zeta));
+                if (zeta < 0.0) tt = -tt;
+                c = 1.0 / sqrt(1.0 + tt * tt);
+                s = c * tt;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double hp = H[k][p], hq = H[k][q];
+                H[k][p] = c * hp - s * hq;
+                H[k][q] = s * hp + c * hq;
+                double vp = V[k][p], vq = V[k][q];
+                V[k][p] = c * vp - s * vq;
+                V[k][q] = s * vp + c * vq;
+            }
+        }
+    }
+    double s0 = coldot(H, 0, 0), s1 = coldot(H, 1, 1), s2 = coldot(H, 2, 2);
+    // stable descending sort of the three columns (== oracle's first-argmax picks)
+    if (s1 > s0) { colswap(H, 0, 1); colswap(V, 0, 1); double t = s0; s0 = s1; s1 = t; }
+    if (s2 > s1) { colswap(H, 1, 2); colswap(V, 1, 2); double t = s1; s1 = s2; s2 = t; }
+    if (s1 > s0) { colswap(H, 0, 1); colswap(V, 0, 1); double t = s0; s0 = s1; s1 = t; }
+    if (!(s0 > 0.0)) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[r][c] = (r == c) ? 1.0 : 0.0;
+        return;
+    }
+    double u1[3], u2[3], u3[3], v1[3], v2[3], v3[3];
+    double sa = sqrt(s0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        u1[k] = H[k][0] / sa;
+        v1[k] = V[k][0];
+        v2[k] = V[k][1];
+    }
+    if (s1 > s0 * 1e-30) {
+        double sb = sqrt(s1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) u2[k] = H[k][1] / sb;
+    } else {
+        int e = 0;
+        double m = fabs(u1[0]);
+        if (fabs(u1[1]) < m) { e = 1; m = fabs(u1[1]); }
+        if (fabs(u1[2]) < m) { e = 2; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) u2[k] = (k == e) ? 1.0 : 0.0;
+    }
+    double g = (u1[0] * u2[0] + u1[1] * u2[1]) + u1[2] * u2[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u2[k] = u2[k] - g * u1[k];
+    double nu = sqrt((u2[0] * u2[0] + u2[1] * u2[1]) + u2[2] * u2[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u2[k] = u2[k] / nu;
+    u3[0] = u1[1] * u2[2] - u1[2] * u2[1];
+    u3[1] = u1[2] * u2[0] - u1[0] * u2[2];
+    u3[2] = u1[0] * u2[1] - u1[1] * u2[0];
+    v3[0] = v1[1] * v2[2] - v1[2] * v2[1];
+    v3[1] = v1[2] * v2[0] - v1[0] * v2[2];
+    v3[2] = v1[0] * v2[1] - v1[1] * v2[0];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r][c] = (u1[r] * v1[c] + u2[r] * v2[c]) + u3[r] * v3[c];
+}
+
+__device__ __forceinline__ void finish_T(const double (&R)[3][3], const double (&cp)[3], const double (&cq)[3],
+                                         double (&T)[12])
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        T[4 * r + 0] = R[r][0];
+        T[4 * r + 1] = R[r][1];
+        T[4 * r + 2] = R[r][2];
+        T[4 * r + 3] = cq[r] - ((R[r][0] * cp[0] + R[r][1] * cp[1]) + R[r][2] * cp[2]);
+    }
+}
+
+template <int M>
+__device__ void kabsch_small(const double (&P)[M][3], const double (&Q)[M][3], double (&T)[12])
+{
+    double cp[3] = {0, 0, 0}, cq[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cp[c] = cp[c] + P[i][c];
+            cq[c] = cq[c] + Q[i][c];
+        }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        cp[c] = cp[c] / (double)M;
+        cq[c] = cq[c] / (double)M;
+    }
+    double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        double dp[3], dq[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            dp[c] = P[i][c] - cp[c];
+            dq[c] = Q[i][c] - cq[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) H[r][c] = H[r][c] + dq[r] * dp[c];
+    }
+    double R[3][3];
+    rot_from_H(H, R);
+    finish_T(R, cp, cq, T);
+}
+
+__device__ __forceinline__ double res2_f64(const double *T, double px, double py, double pz, double qx, double qy,
+                                           double qz)
+{
+    double d0 = (((T[0] * px + T[1] * py) + T[2] * pz) + T[3]) - qx;
+    double d1 = (((T[4] * px + T[5] * py) + T[6] * pz) + T[7]) - qy;
+    double d2 = (((T[8] * px + T[9] * py) + T[10] * pz) + T[11]) - qz;
+    return (d0 * d0 + d1 * d1) + d2 * d2;
+}
+
+__device__ __forceinline__ unsigned long long make_key(int count, uint32_t id)
+{
+    return ((unsigned long long)(uint32_t)(count + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - id);
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------
+
+// AoS [n,3] x2  ->  (px,py,pz,qx) + (qy,qz), padded to a multiple of kChunk with
+// far-away points that can never be inliers; also the coordinate bounds that
+// enter the fp32 error band.
+__global__ void k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, int64_t n_pad,
+                       float4 *__restrict__ P4, float2 *__restrict__ Q2, Ctl *ctl)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float p1 = 0.f, qm = 0.f;
+    if (i < n) {
+        float px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
+        float qx = tgt[3 * i], qy = tgt[3 * i + 1], qz = tgt[3 * i + 2];
+        P4[i] = make_float4(px, py, pz, qx);
+        Q2[i] = make_float2(qy, qz);
+        p1 = fabsf(px) + fabsf(py) + fabsf(pz);
+        qm = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
+    } else if (i < n_pad) {
+        P4[i] = make_float4(0.f, 0.f, 0.f, 1e18f);
+        Q2[i] = make_float2(1e18f, 1e18f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        p1 = fmaxf(p1, __shfl_xor_sync(0xffffffffu, p1, o));
+        qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // round p1 up a little: the fp32 sum above is itself rounded
+        atomicMax(&ctl->p1max_bits, __float_as_uint(p1 * 1.000001f));
+        atomicMax(&ctl->qmax_bits, __float_as_uint(qm));
+    }
+}
+
+__global__ void k_ctl_reset(Ctl *ctl)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctl->best_key = 0ULL;
+        ctl->round_key = 0ULL;
+        ctl->n_surv = 0;
+        ctl->n_flag = 0;
+        ctl->done = 0;
+        ctl->iters_run = 0;
+        ctl->n_scored = 0;
+        ctl->n_rechecked = 0;
+        ctl->p1max_bits = 0u;
+        ctl->qmax_bits = 0u;
+        ctl->refit_count = 0;
+    }
+}
+
+// one thread per hypothesis: sample -> ELC -> Kabsch -> compacted slot
+template <int M>
+__global__ void __launch_bounds__(kGenThreads)
+k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, uint64_t seed, int sampler,
+      int use_elc, double elc_ratio, double thr2, int64_t id_lo, int64_t id_hi,
+      const int32_t *__restrict__ fed, Ctl *ctl, uint32_t *__restrict__ slot_id, float4 *__restrict__ m32,
+      double *__restrict__ m64)
+{
+    if (ctl->done) return;
+    int64_t id = id_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool ok = id < id_hi;
+    double T[12];
+    if (ok) {
+        int32_t s[M];
+        if (fed) {
+#pragma unroll
+            for (int d = 0; d < M; ++d) s[d] = fed[(id - id_lo) * M + d];
+        } else {
+            sample_ids<M>(seed, (uint64_t)id, sampler, n, s);
+        }
+        double P[M][3], Q[M][3];
+#pragma unroll
+        for (int d = 0; d < M; ++d)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                P[d][c] = (double)src[3 * (int64_t)s[d] + c];
+                Q[d][c] = (double)tgt[3 * (int64_t)s[d] + c];
+            }
+        if (use_elc) ok = elc_pass<M>(P, Q, elc_ratio);
+        if (ok) kabsch_small<M>(P, Q, T);
+    }
+    // warp-aggregated compaction
+    unsigned ballot = __ballot_sync(0xffffffffu, ok);
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(&ctl->n_surv, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!ok) return;
+    int slot = base + __popc(ballot & ((1u << lane) - 1u));
+    slot_id[slot] = (uint32_t)id;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m64[(size_t)slot * 12 + k] = T[k];
+    // fp32 copy + error band of the inlier test (DESIGN.md "fp32 bracket")
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    double tinf = fmax(fabs(T[3]), fmax(fabs(T[7]), fabs(T[11])));
+    double E = 8.0 * u * ((double)__uint_as_float(ctl->p1max_bits) + (double)__uint_as_float(ctl->qmax_bits) + tinf);
+    double thr = sqrt(thr2);
+    double delta = 4.0 * E * thr + 4.0 * E * E + 8.0 * u * thr2 + 1e-9;
+    float lo = __double2float_rd(thr2 - delta);
+    float hi = __double2float_ru(thr2 + delta);
+    m32[(size_t)slot * 4 + 0] = make_float4((float)T[0], (float)T[1], (float)T[2], (float)T[3]);
+    m32[(size_t)slot * 4 + 1] = make_float4((float)T[4], (float)T[5], (float)T[6], (float)T[7]);
+    m32[(size_t)slot * 4 + 2] = make_float4((float)T[8], (float)T[9], (float)T[10], (float)T[11]);
+    m32[(size_t)slot * 4 + 3] = make_float4(lo, hi, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Inlier sweep.  Each thread owns one surviving hypothesis ([R|t] in fp32
+// registers) and walks every correspondence; correspondences are staged
+// through shared memory in double-buffered chunks with cp.async and read as
+// warp-wide broadcasts (LDS.128 + LDS.64 per point per warp).  Per pair:
+// 12 FFMA/FADD for R p + t - q, 3 for |.|^2, two compare+add for the bracket.
+__global__ void __launch_bounds__(kScoreThreads)
+k_score(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n_pad, Ctl *ctl,
+        const uint32_t *__restrict__ slot_id, const float4 *__restrict__ m32, int *__restrict__ flagged,
+        int32_t *__restrict__ counts_out, int64_t id_base)
+{
+    if (ctl->done) return;
+    __shared__ __align__(16) float4 sP[2][kChunk];
+    __shared__ __align__(16) float2 sQ[2][kChunk];
+    const int tid = threadIdx.x;
+    const int nsurv = ctl->n_surv;
+    const int nitems = (nsurv + kScoreThreads - 1) / kScoreThreads;
+    const int nchunks = (int)(n_pad / kChunk);
+
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int slot = item * kScoreThreads + tid;
+        const bool valid = slot < nsurv;
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, bw = make_float4(-1.f, -1.f, 0, 0);
+        if (valid) {
+            r0 = m32[(size_t)slot * 4 + 0];
+            r1 = m32[(size_t)slot * 4 + 1];
+            r2 = m32[(size_t)slot * 4 + 2];
+            bw = m32[(size_t)slot * 4 + 3];
+        }
+        const float lo = bw.x, hi = bw.y;
+        int cnt_lo = 0, cnt_hi = 0;
+
+        auto stage = [&](int c, int buf) {
+            const float4 *gp = P4 + (size_t)c * kChunk;
+            const float4 *gq = reinterpret_cast<const float4 *>(Q2 + (size_t)c * kChunk);
+            float4 *sq = reinterpret_cast<float4 *>(&sQ[buf][0]);
+#pragma unroll
+            for (int k = 0; k < kChunk / kScoreThreads; ++k) cp_async16(&sP[buf][tid + k * kScoreThreads], gp + tid + k * kScoreThreads);
+#pragma unroll
+            for (int k = 0; k < kChunk / 2 / kScoreThreads; ++k) cp_async16(sq + tid + k * kScoreThreads, gq + tid + k * kScoreThreads);
+            cp_async_commit();
+        };
+
+        stage(0, 0);
+        for (int c = 0; c < nchunks; ++c) {
+            const int buf = c & 1;
+            if (c + 1 < nchunks) {
+                stage(c + 1, buf ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int i = 0; i < kChunk; ++i) {
+                const float4 a = sP[buf][i];
+                const float2 b = sQ[buf][i];
+                float d0 = fmaf(r0.x, a.x, fmaf(r0.y, a.y, fmaf(r0.z, a.z, r0.w))) - a.w;
+                float d1 = fmaf(r1.x, a.x, fmaf(r1.y, a.y, fmaf(r1.z, a.z, r1.w))) - b.x;
+                float d2 = fmaf(r2.x, a.x, fmaf(r2.y, a.y, fmaf(r2.z, a.z, r2.w))) - b.y;
+                float rr = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+                cnt_lo += (rr < lo) ? 1 : 0;
+                cnt_hi += (rr < hi) ? 1 : 0;
+            }
+            __syncthreads();
+        }
+
+        unsigned long long key = 0ULL;
+        if (valid) {
+            if (cnt_lo == cnt_hi) {
+                const uint32_t id = slot_id[slot];
+                key = make_key(cnt_lo, id);
+                if (counts_out) counts_out[(int64_t)id - id_base] = cnt_lo;
+            } else {
+                flagged[atomicAdd(&ctl->n_flag, 1)] = slot;
+            }
+        }
+        key = warp_max_u64(key);
+        if ((tid & 31) == 0 && key) atomicMax(&ctl->round_key, key);
+    }
+}
+
+// exact fp64 recount of the hypotheses whose fp32 bracket stayed open
+__global__ void __launch_bounds__(256)
+k_recount(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n, Ctl *ctl,
+          const uint32_t *__restrict__ slot_id, const double *__restrict__ m64, const int *__restrict__ flagged,
+          double thr2, int32_t *__restrict__ counts_out, int64_t id_base)
+{
+    if (ctl->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nflag = ctl->n_flag;
+    for (int f = warp; f < nflag; f += nwarps) {
+        const int slot = flagged[f];
+        double T[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) T[k] = m64[(size_t)slot * 12 + k];
+        int cnt = 0;
+        for (int64_t i = lane; i < n; i += 32) {
+            const float4 a = P4[i];
+            const float2 b = Q2[i];
+            cnt += res2_f64(T, a.x, a.y, a.z, a.w, b.x, b.y) < thr2 ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) {
+            const uint32_t id = slot_id[slot];
+            atomicMax(&ctl->round_key, make_key(cnt, id));
+            if (counts_out) counts_out[(int64_t)id - id_base] = cnt;
+        }
+    }
+}
+
+__global__ void k_round_end(Ctl *ctl, int64_t round_len, const int *__restrict__ need, int round_idx,
+                            unsigned long long *user_key)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (ctl->done) return;
+    if (ctl->round_key > ctl->best_key) ctl->best_key = ctl->round_key;
+    if (user_key && ctl->round_key > *user_key) *user_key = ctl->round_key;
+    ctl->iters_run += round_len;
+    ctl->n_scored += ctl->n_surv;
+    ctl->n_rechecked += ctl->n_flag;
+    ctl->round_key = 0ULL;
+    ctl->n_surv = 0;
+    ctl->n_flag = 0;
+    if (need) {
+        long long cnt = (long long)(ctl->best_key >> 32) - 1;
+        if (ctl->best_key != 0ULL && cnt >= (long long)need[round_idx]) ctl->done = 1;
+    }
+}
+
+// key -> model of the selected hypothesis (identity when none / zero inliers)
+template <int M>
+__global__ void k_model_from_key(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n,
+                                 uint64_t seed, int sampler, unsigned long long key_in, int use_ctl_key, Ctl *ctl)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long key = use_ctl_key ? ctl->best_key : key_in;
+    if (!use_ctl_key) ctl->best_key = key;
+    double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    long long cnt = (long long)(key >> 32) - 1;
+    if (key != 0ULL && cnt > 0) {
+        uint64_t id = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFULL));
+        int32_t s[M];
+        sample_ids<M>(seed, id, sampler, n, s);
+        double P[M][3], Q[M][3];
+#pragma unroll
+        for (int d = 0; d < M; ++d)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                P[d][c] = (double)src[3 * (int64_t)s[d] + c];
+                Q[d][c] = (double)tgt[3 * (int64_t)s[d] + c];
+            }
+        kabsch_small<M>(P, Q, T);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) ctl->T[k] = T[k];
+    ctl->refit_count = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ctl->csum[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) ctl->H[k] = 0.0;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;  // valid in thread 0
+}
+
+// fetch one correspondence either directly ([n,3] arrays) or through index lists
+__device__ __forceinline__ void fetch_pair(const float *a, const float *b, const int64_t *ia, const int64_t *ib,
+                                           int64_t i, double (&p)[3], double (&q)[3])
+{
+    const int64_t ka = ia ? ia[i] : i, kb = ib ? ib[i] : i;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        p[c] = (double)a[3 * ka + c];
+        q[c] = (double)b[3 * kb + c];
+    }
+}
+
+// pass 1 of the refit: exact inlier mask of ctl->T, count, coordinate sums
+__global__ void __launch_bounds__(256)
+k_mask_sums(const float *__restrict__ a, const float *__restrict__ b, const int64_t *__restrict__ ia,
+            const int64_t *__restrict__ ib, int64_t n, double thr2, Ctl *ctl, uint8_t *__restrict__ mask)
+{
+    __shared__ double sh[8];
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = ctl->T[k];
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double p[3], q[3];
+        fetch_pair(a, b, ia, ib, i, p, q);
+        bool in = res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]) < thr2;
+        if (mask) mask[i] = in ? 1 : 0;
+        if (in) {
+            ++cnt;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                s[c] += p[c];
+                s[3 + c] += q[c];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double r = block_sum(s[k], sh);
+        if (threadIdx.x == 0 && r != 0.0) atomicAdd(&ctl->csum[k], r);
+    }
+    double c = block_sum((double)cnt, sh);
+    if (threadIdx.x == 0 && c != 0.0) atomicAdd((unsigned long long *)&ctl->refit_count, (unsigned long long)c);
+}
+
+// pass 2: centred cross-covariance over the inliers
+__global__ void __launch_bounds__(256)
+k_refit_H(const float *__restrict__ a, const float *__restrict__ b, const int64_t *__restrict__ ia,
+          const int64_t *__restrict__ ib, int64_t n, double thr2, Ctl *ctl)
+{
+    __shared__ double sh[8];
+    const long long k = ctl->refit_count;
+    if (k <= 0) return;
+    double T[12], cp[3], cq[3];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) T[j] = ctl->T[j];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        cp[c] = ctl->csum[c] / (double)k;
+        cq[c] = ctl->csum[3 + c] / (double)k;
+    }
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double p[3], q[3];
+        fetch_pair(a, b, ia, ib, i, p, q);
+        if (res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]) < thr2) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) H[3 * r + c] += (q[r] - cq[r]) * (p[c] - cp[c]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        double r = block_sum(H[j], sh);
+        if (threadIdx.x == 0 && r != 0.0) atomicAdd(&ctl->H[j], r);
+    }
+}
+
+__global__ void k_refit_solve(Ctl *ctl)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const long long k = ctl->refit_count;
+    double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    if (k > 0) {
+        double H[3][3], R[3][3], cp[3], cq[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) H[r][c] = ctl->H[3 * r + c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cp[c] = ctl->csum[c] / (double)k;
+            cq[c] = ctl->csum[3 + c] / (double)k;
+        }
+        rot_from_H(H, R);
+        finish_T(R, cp, cq, T);
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) ctl->Tref[j] = T[j];
+}
+
+__global__ void k_set_T(Ctl *ctl, const double *T12)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < 12; ++k) ctl->T[k] = T12[k];
+    ctl->refit_count = 0;
+    for (int k = 0; k < 6; ++k) ctl->csum[k] = 0.0;
+    for (int k = 0; k < 9; ++k) ctl->H[k] = 0.0;
+}
+
+template <int M>
+__global__ void k_sample_only(uint64_t seed, int sampler, int64_t n, int64_t id_lo, int64_t H, int32_t *out)
+{
+    int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    int32_t s[M];
+    sample_ids<M>(seed, (uint64_t)(id_lo + h), sampler, n, s);
+#pragma unroll
+    for (int d = 0; d < M; ++d) out[h * M + d] = s[d];
+}
+
+// compacted fp64 models -> sample order (fed-sample hook only)
+__global__ void k_scatter_models(const Ctl *ctl, const uint32_t *slot_id, const double *m64, double *models)
+{
+    int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= ctl->n_surv) return;
+    const size_t h = slot_id[slot];
+    for (int k = 0; k < 12; ++k) models[h * 12 + k] = m64[(size_t)slot * 12 + k];
+}
+
+// ------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------
+
+int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
+{
+    ws.n_pad = ((n + kChunk - 1) / kChunk) * kChunk;
+    if (ws.n_pad == 0) ws.n_pad = kChunk;
+    size_t bytes = lr::padded(sizeof(Ctl)) + lr::padded(sizeof(float4) * ws.n_pad) + lr::padded(sizeof(float2) * ws.n_pad) +
+                   lr::padded(sizeof(uint32_t) * round) + lr::padded(sizeof(float4) * 4 * round) +
+                   lr::padded(sizeof(double) * 12 * round) + lr::padded(sizeof(int) * round) +
+                   lr::padded(sizeof(int) * (nrounds + 1)) + lr::padded(sizeof(double) * 16);
+    void *base = lr::arena_get(lr::SLOT_RANSAC, bytes);
+    if (!base) return LR_ERR_ALLOC;
+    lr::Carver cv(base);
+    ws.ctl = cv.take<Ctl>(1);
+    ws.P4 = cv.take<float4>(ws.n_pad);
+    ws.Q2 = cv.take<float2>(ws.n_pad);
+    ws.slot_id = cv.take<uint32_t>(round);
+    ws.m32 = cv.take<float4>(4 * round);
+    ws.m64 = cv.take<double>(12 * round);
+    ws.flagged = cv.take<int>(round);
+    ws.need = cv.take<int>(nrounds + 1);
+    ws.scratchT = cv.take<double>(16);
+    return LR_OK;
+}
+
+int check_params(const LrRansacParams *p, int64_t n)
+{
+    LR_REQUIRE(p != nullptr, "params is null");
+    LR_REQUIRE(p->sample_size == 3 || p->sample_size == 4, "sample_size must be 3 or 4");
+    LR_REQUIRE(p->sampler == LR_SAMPLER_UNIFORM || p->sampler == LR_SAMPLER_REPLACE,
+               "sampler must be LR_SAMPLER_UNIFORM or LR_SAMPLER_REPLACE (PROSAC: not implemented)");
+    LR_REQUIRE(p->threshold > 0.0, "threshold must be positive");
+    LR_REQUIRE(p->max_iters >= 0 && p->max_iters < (int64_t)0xFFFFFFFFLL, "max_iters out of range");
+    LR_REQUIRE(p->round_size > 0 && p->round_size <= (1 << 22), "round_size out of range");
+    LR_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "n out of range");
+    return LR_OK;
+}
+
+int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cudaStream_t st)
+{
+    k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
+    int blocks = (int)((ws.n_pad + 255) / 256);
+    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P4, ws.Q2, ws.ctl);
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+// one round: ids [lo, hi) (or H fed samples), leaves the result in ctl->round_key
+int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int64_t lo,
+                 int64_t hi, const int32_t *fed, int32_t *counts_out, cudaStream_t st)
+{
+    const int64_t len = hi - lo;
+    if (len <= 0) return LR_OK;
+    const double thr2 = p.threshold * p.threshold;
+    int gblocks = (int)((len + kGenThreads - 1) / kGenThreads);
+    if (p.sample_size == 3)
+        k_gen<3><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, thr2, lo, hi,
+                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64);
+    else
+        k_gen<4><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, thr2, lo, hi,
+                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64);
+    int items = (int)((len + kScoreThreads - 1) / kScoreThreads);
+    int sblocks = lr::sm_count() * 4;
+    if (sblocks > items) sblocks = items;
+    k_score<<<sblocks, kScoreThreads, 0, st>>>(ws.P4, ws.Q2, ws.n_pad, ws.ctl, ws.slot_id, ws.m32, ws.flagged,
+                                               counts_out, lo);
+    k_recount<<<lr::sm_count() * 2, 256, 0, st>>>(ws.P4, ws.Q2, n, ws.ctl, ws.slot_id, ws.m64, ws.flagged, thr2,
+                                                  counts_out, lo);
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+void T12_to_16(const double *T12, double *T16)
+{
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) T16[4 * r + c] = T12[4 * r + c];
+    T16[12] = T16[13] = T16[14] = 0.0;
+    T16[15] = 1.0;
+}
+
+void identity16(double *T)
+{
+    for (int k = 0; k < 16; ++k) T[k] = (k % 5 == 0) ? 1.0 : 0.0;
+}
+
+// model from key + mask + refit + D2H
+int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
+           uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st)
+{
+    const double thr2 = p.threshold * p.threshold;
+    if (p.sample_size == 3)
+        k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, key, use_ctl_key, ws.ctl);
+    else
+        k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, key, use_ctl_key, ws.ctl);
+    const bool want_refit = (T_refit != nullptr) && p.refit;
+    if (want_refit || mask || stats) {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
+        if (blocks < 1) blocks = 1;
+        k_mask_sums<<<blocks, 256, 0, st>>>(src, tgt, nullptr, nullptr, n, thr2, ws.ctl, mask);
+        if (want_refit) {
+            k_refit_H<<<blocks, 256, 0, st>>>(src, tgt, nullptr, nullptr, n, thr2, ws.ctl);
+            k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
+        }
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    Ctl h;
+    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    if (T_out) T12_to_16(h.T, T_out);
+    if (T_refit) {
+        if (want_refit) T12_to_16(h.Tref, T_refit);
+        else identity16(T_refit);
+    }
+    if (stats) {
+        stats->iters_run = h.iters_run;
+        stats->n_scored = h.n_scored;
+        stats->n_rechecked = h.n_rechecked;
+        long long cnt = (long long)(h.best_key >> 32) - 1;
+        if (h.best_key != 0ULL) {
+            stats->best_id = (int64_t)(0xFFFFFFFFu - (uint32_t)(h.best_key & 0xFFFFFFFFULL));
+            stats->best_count = cnt;
+        } else {
+            stats->best_id = -1;
+            stats->best_count = -1;
+        }
+        stats->refit_count = h.refit_count;
+    }
+    return LR_OK;
+}
+
+}  // namespace
+
+LR_EXPORT int64_t lr_ransac_conf_iters(int64_t c, int64_t n, int m, double conf, int64_t max_iters)
+{
+    // Open3D stopping rule; same expression as the oracle's lro_conf_iters
+    if (!(conf < 1.0) || c <= 0 || n <= 0) return max_iters;
+    double fitness = (double)c / (double)n;
+    double denom = log(1.0 - pow(fitness, (double)m));
+    if (!(denom < 0.0)) return max_iters;
+    double k = log(1.0 - conf) / denom;
+    if (!(k < (double)max_iters)) return max_iters;
+    int64_t ki = (int64_t)ceil(k);
+    return ki < 1 ? 1 : ki;
+}
+
+LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
+                              double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream)
+{
+    lr::Lock lock;
+    int rc = check_params(params, n);
+    if (rc) return rc;
+    LR_REQUIRE(T_out != nullptr, "T_out is null");
+    LR_REQUIRE(n == 0 || (src && tgt), "src/tgt is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LrRansacParams &p = *params;
+    if (n < p.sample_size) {  // Open3D: |corres| < ransac_n -> identity (App. B)
+        identity16(T_out);
+        if (T_refit) identity16(T_refit);
+        if (mask && n > 0) LR_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)n, st));
+        if (stats) *stats = LrRansacStats{0, 0, 0, -1, -1, 0};
+        LR_CUDA_TRY(cudaStreamSynchronize(st));
+        return LR_OK;
+    }
+    const int64_t R = p.round_size;
+    const int64_t nrounds = (p.max_iters + R - 1) / R;
+    Ws ws;
+    rc = ws_setup(n, R, nrounds, ws);
+    if (rc) return rc;
+    rc = launch_pack(src, tgt, n, ws, st);
+    if (rc) return rc;
+    // confidence exit: need[r] = smallest best-count that lets the loop stop
+    // after round r (conf_iters is non-increasing in the count)
+    const bool use_conf = p.confidence < 1.0 && nrounds > 0;
+    std::vector<int> need;
+    if (use_conf) {
+        need.resize(nrounds);
+        for (int64_t r = 0; r < nrounds; ++r) {
+            int64_t done = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
+            int64_t lo = 1, hi = n + 1;  // smallest c in [1, n] with conf_iters(c) <= done, else n + 1
+            while (lo < hi) {
+                int64_t mid = lo + (hi - lo) / 2;
+                if (lr_ransac_conf_iters(mid, n, p.sample_size, p.confidence, p.max_iters) <= done) hi = mid;
+                else lo = mid + 1;
+            }
+            need[r] = (int)lo;
+        }
+        LR_CUDA_TRY(cudaMemcpyAsync(ws.need, need.data(), sizeof(int) * nrounds, cudaMemcpyHostToDevice, st));
+    }
+    for (int64_t r = 0; r < nrounds; ++r) {
+        int64_t lo = r * R, hi = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
+        rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
+        if (rc) return rc;
+        k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, nullptr);
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    return finish(src, tgt, n, p, ws, 1, 0, T_out, T_refit, mask, stats, st);
+}
+
+LR_EXPORT int lr_ransac_score_samples(const float *src, const float *tgt, int64_t n, const int32_t *samples, int64_t H,
+                                      int m, double threshold, int use_elc, double elc_ratio, int32_t *counts,
+                                      double *models, int64_t *best, void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(m == 3 || m == 4, "m must be 3 or 4");
+    LR_REQUIRE(src && tgt && samples && counts, "null pointer");
+    LR_REQUIRE(n > 0 && n < (int64_t)1 << 31 && H > 0 && H < (int64_t)0xFFFFFFFFLL, "n/H out of range");
+    LR_REQUIRE(threshold > 0.0, "threshold must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    LrRansacParams p;
+    memset(&p, 0, sizeof(p));
+    p.threshold = threshold;
+    p.confidence = 1.0;
+    p.elc_ratio = elc_ratio;
+    p.max_iters = H;
+    p.sample_size = m;
+    p.sampler = LR_SAMPLER_UNIFORM;
+    p.use_elc = use_elc;
+    const int64_t R = H < 65536 ? H : 65536;
+    p.round_size = (int32_t)R;
+    Ws ws;
+    int rc = ws_setup(n, R, 1, ws);
+    if (rc) return rc;
+    rc = launch_pack(src, tgt, n, ws, st);
+    if (rc) return rc;
+    LR_CUDA_TRY(cudaMemsetAsync(counts, 0xFF, sizeof(int32_t) * H, st));  // -1 = rejected
+    if (models) LR_CUDA_TRY(cudaMemsetAsync(models, 0, sizeof(double) * 12 * H, st));
+    for (int64_t lo = 0; lo < H; lo += R) {
+        int64_t hi = lo + R < H ? lo + R : H;
+        rc = launch_round(src, tgt, n, p, ws, lo, hi, samples + lo * m, counts + lo, st);
+        if (rc) return rc;
+        if (models) {
+            // scatter the compacted fp64 models back to sample order before the slots are reused
+            k_scatter_models<<<(int)((hi - lo + 255) / 256), 256, 0, st>>>(ws.ctl, ws.slot_id, ws.m64, models);
+        }
+        k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, nullptr, 0, nullptr);
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    Ctl h;
+    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    if (best) *best = h.best_key ? (int64_t)(0xFFFFFFFFu - (uint32_t)(h.best_key & 0xFFFFFFFFULL)) : -1;
+    return LR_OK;
+}
+
+LR_EXPORT int lr_ransac_shard(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
+                              int64_t id_lo, int64_t id_hi, uint64_t *key, void *stream)
+{
+    lr::Lock lock;
+    int rc = check_params(params, n);
+    if (rc) return rc;
+    LR_REQUIRE(src && tgt && key, "null pointer");
+    LR_REQUIRE(n >= params->sample_size, "fewer correspondences than the sample size");
+    LR_REQUIRE(id_lo >= 0 && id_hi >= id_lo && id_hi < (int64_t)0xFFFFFFFFLL, "id range out of bounds");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LrRansacParams &p = *params;
+    const int64_t R = p.round_size;
+    Ws ws;
+    rc = ws_setup(n, R, 1, ws);
+    if (rc) return rc;
+    rc = launch_pack(src, tgt, n, ws, st);
+    if (rc) return rc;
+    for (int64_t lo = id_lo; lo < id_hi; lo += R) {
+        int64_t hi = lo + R < id_hi ? lo + R : id_hi;
+        rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
+        if (rc) return rc;
+        k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, nullptr, 0, (unsigned long long *)key);
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+LR_EXPORT int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
+                                 uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats,
+                                 void *stream)
+{
+    lr::Lock lock;
+    int rc = check_params(params, n);
+    if (rc) return rc;
+    LR_REQUIRE(src && tgt && T_out, "null pointer");
+    LR_REQUIRE(n >= params->sample_size, "fewer correspondences than the sample size");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws;
+    rc = ws_setup(n, params->round_size, 1, ws);
+    if (rc) return rc;
+    k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
+    return finish(src, tgt, n, *params, ws, 0, key, T_out, T_refit, mask, stats, st);
+}
+
+LR_EXPORT int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t id_lo, int64_t H, int32_t *samples,
+                               void *stream)
+{
+    int rc = check_params(params, n);
+    if (rc) return rc;
+    LR_REQUIRE(samples && H >= 0 && n >= params->sample_size, "bad arguments");
+    if (H == 0) return LR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int blocks = (int)((H + 255) / 256);
+    if (params->sample_size == 3)
+        k_sample_only<3><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, id_lo, H, samples);
+    else
+        k_sample_only<4><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, id_lo, H, samples);
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+LR_EXPORT int lr_refit_indexed(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1, int64_t K,
+                               const double *T_in, double threshold, double *T_out, int64_t *count, void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(xyz0 && xyz1 && T_in && T_out, "null pointer");
+    LR_REQUIRE(K >= 0 && threshold > 0.0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws;
+    int rc = ws_setup(1, 1, 1, ws);
+    if (rc) return rc;
+    double *dT = ws.scratchT;
+    double T12[12];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) T12[4 * r + c] = T_in[4 * r + c];
+    LR_CUDA_TRY(cudaMemcpyAsync(dT, T12, sizeof(T12), cudaMemcpyHostToDevice, st));
+    k_set_T<<<1, 32, 0, st>>>(ws.ctl, dT);
+    if (K > 0) {
+        int blocks = (int)((K + 255) / 256);
+        if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
+        const double thr2 = threshold * threshold;
+        k_mask_sums<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl, nullptr);
+        k_refit_H<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl);
+    }
+    k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
+    LR_CUDA_TRY(cudaGetLastError());
+    Ctl h;
+    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    T12_to_16(h.Tref, T_out);
+    if (count) *count = h.refit_count;
+    return LR_OK;
+}

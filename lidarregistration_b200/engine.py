@@ -1,0 +1,204 @@
+"""Device-resident front-end of the C ABI: CUDA tensors in, CUDA tensors out.
+
+One function per entry point of include/lidarreg.h.  PyTorch is used for
+device memory and streams only; every computation happens inside
+liblidarreg.so.  The reference-facing mirrors (same names and argument
+meaning as Experiments/algorithms/*.py) live in
+lidarregistration_b200.algorithms and call into this module.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LrRansacParams, LrRansacStats, SAMPLER_PROSAC, SAMPLER_REPLACE, SAMPLER_UNIFORM  # noqa: F401
+
+DEFAULT_ROUND = 65536
+
+
+def _dev():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_dev_f32(x):
+    """float32 contiguous CUDA tensor from a tensor / ndarray (no copy if already one)."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    x = x.detach()
+    if not x.is_cuda:
+        x = x.to(_dev(), non_blocking=True)
+    return x.to(torch.float32).contiguous()
+
+
+def to_dev_i64(x):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    x = x.detach()
+    if not x.is_cuda:
+        x = x.to(_dev(), non_blocking=True)
+    return x.to(torch.int64).contiguous()
+
+
+# ---------------------------------------------------------------- matching
+def match_nn(f0, f1, want_2nd=False):
+    """lr_match_nn: (idx1[N], idx1_2nd[N] | None), int64 CUDA tensors."""
+    f0, f1 = to_dev_f32(f0), to_dev_f32(f1)
+    N, D = f0.shape
+    M = f1.shape[0]
+    assert f1.shape[1] == D
+    idx1 = torch.empty(N, dtype=torch.int64, device=f0.device)
+    idx2 = torch.empty(N, dtype=torch.int64, device=f0.device) if want_2nd else None
+    if N == 0:
+        return idx1, idx2
+    rc = _lib.lib().lr_match_nn(_lib.ptr(f0), ctypes.c_int64(N), _lib.ptr(f1), ctypes.c_int64(M), int(D),
+                                _lib.ptr(idx1), _lib.ptr(idx2), _lib.stream_ptr())
+    _lib.check(rc, "lr_match_nn")
+    return idx1, idx2
+
+
+def match_mutual(f0, f1, idx1):
+    """lr_match_mutual: mutual pairs (i, j) sorted by i, int64 CUDA tensors."""
+    f0, f1, idx1 = to_dev_f32(f0), to_dev_f32(f1), to_dev_i64(idx1)
+    N, D = f0.shape
+    M = f1.shape[0]
+    out_i = torch.empty(N, dtype=torch.int64, device=f0.device)
+    out_j = torch.empty(N, dtype=torch.int64, device=f0.device)
+    K = torch.zeros(1, dtype=torch.int64, device=f0.device)
+    if N == 0:
+        return out_i, out_j
+    rc = _lib.lib().lr_match_mutual(_lib.ptr(f0), ctypes.c_int64(N), _lib.ptr(f1), ctypes.c_int64(M), int(D),
+                                    _lib.ptr(idx1), _lib.ptr(out_i), _lib.ptr(out_j), _lib.ptr(K),
+                                    _lib.stream_ptr())
+    _lib.check(rc, "lr_match_mutual")
+    k = int(K.item())
+    return out_i[:k], out_j[:k]
+
+
+def match_ratio(f0, f1, i0, i1, i2):
+    f0, f1 = to_dev_f32(f0), to_dev_f32(f1)
+    i0, i1, i2 = to_dev_i64(i0), to_dev_i64(i1), to_dev_i64(i2)
+    K = i0.shape[0]
+    out = torch.empty(K, dtype=torch.float32, device=f0.device)
+    rc = _lib.lib().lr_match_ratio(_lib.ptr(f0), _lib.ptr(f1), int(f0.shape[1]), ctypes.c_int64(K), _lib.ptr(i0),
+                                   _lib.ptr(i1), _lib.ptr(i2), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lr_match_ratio")
+    return out
+
+
+def gather_xyz(xyz, idx):
+    xyz, idx = to_dev_f32(xyz), to_dev_i64(idx)
+    K = idx.shape[0]
+    out = torch.empty((K, 3), dtype=torch.float32, device=xyz.device)
+    rc = _lib.lib().lr_gather_xyz(_lib.ptr(xyz), _lib.ptr(idx), ctypes.c_int64(K), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lr_gather_xyz")
+    return out
+
+
+# ------------------------------------------------------------------ RANSAC
+def make_params(threshold=0.6, confidence=1.0, max_iters=500000, seed=51, sample_size=3,
+                sampler=SAMPLER_UNIFORM, use_elc=True, elc_ratio=0.9, round_size=DEFAULT_ROUND, refit=True):
+    p = LrRansacParams()
+    p.threshold, p.confidence, p.elc_ratio = float(threshold), float(confidence), float(elc_ratio)
+    p.max_iters, p.seed = int(max_iters), int(seed)
+    p.sample_size, p.sampler, p.use_elc = int(sample_size), int(sampler), int(bool(use_elc))
+    p.round_size, p.refit, p.reserved = int(round_size), int(bool(refit)), 0
+    return p
+
+
+def ransac_rigid(src, tgt, params, want_mask=False):
+    """lr_ransac_rigid -> dict(T, T_refit, mask (CUDA bool) | None, + LrRansacStats fields)."""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    n = src.shape[0]
+    T = (ctypes.c_double * 16)()
+    Tr = (ctypes.c_double * 16)()
+    st = LrRansacStats()
+    mask = torch.empty(n, dtype=torch.uint8, device=src.device) if want_mask else None
+    rc = _lib.lib().lr_ransac_rigid(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), ctypes.byref(params), T, Tr,
+                                    _lib.ptr(mask), ctypes.byref(st), _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_rigid")
+    out = dict(T=_lib.T_from16(T), T_refit=_lib.T_from16(Tr), mask=mask.bool() if want_mask else None)
+    out.update(st.as_dict())
+    return out
+
+
+def ransac_score_samples(src, tgt, samples, threshold=0.6, use_elc=True, elc_ratio=0.9, want_models=False):
+    """Fed-sample parity hook -> (counts[H] int32 CUDA, best, models[H,12] | None)."""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    if isinstance(samples, np.ndarray):
+        samples = torch.from_numpy(np.ascontiguousarray(samples))
+    samples = samples.to(src.device).to(torch.int32).contiguous()
+    H, m = samples.shape
+    counts = torch.empty(H, dtype=torch.int32, device=src.device)
+    models = torch.empty((H, 12), dtype=torch.float64, device=src.device) if want_models else None
+    best = ctypes.c_int64(-1)
+    rc = _lib.lib().lr_ransac_score_samples(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(src.shape[0]),
+                                            _lib.ptr(samples), ctypes.c_int64(H), int(m), ctypes.c_double(threshold),
+                                            int(bool(use_elc)), ctypes.c_double(elc_ratio), _lib.ptr(counts),
+                                            _lib.ptr(models), ctypes.byref(best), _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_score_samples")
+    return counts, int(best.value), models
+
+
+def ransac_shard(src, tgt, params, id_lo, id_hi, key):
+    """lr_ransac_shard: asynchronously max-merge the packed best of ids [id_lo, id_hi) into key[0]."""
+    assert key.is_cuda and key.dtype == torch.int64 and key.numel() == 1
+    rc = _lib.lib().lr_ransac_shard(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(src.shape[0]), ctypes.byref(params),
+                                    ctypes.c_int64(id_lo), ctypes.c_int64(id_hi), _lib.ptr(key), _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_shard")
+
+
+def ransac_finalize(src, tgt, params, key, want_mask=False):
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    n = src.shape[0]
+    T = (ctypes.c_double * 16)()
+    Tr = (ctypes.c_double * 16)()
+    st = LrRansacStats()
+    mask = torch.empty(n, dtype=torch.uint8, device=src.device) if want_mask else None
+    rc = _lib.lib().lr_ransac_finalize(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), ctypes.byref(params),
+                                       ctypes.c_uint64(int(key) & 0xFFFFFFFFFFFFFFFF), T, Tr, _lib.ptr(mask),
+                                       ctypes.byref(st), _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_finalize")
+    out = dict(T=_lib.T_from16(T), T_refit=_lib.T_from16(Tr), mask=mask.bool() if want_mask else None)
+    out.update(st.as_dict())
+    return out
+
+
+def conf_iters(c, n, m, confidence, max_iters):
+    """Host-only stopping rule (needs no GPU)."""
+    return int(_lib.lib().lr_ransac_conf_iters(int(c), int(n), int(m), float(confidence), int(max_iters)))
+
+
+def ransac_sample(params, n, id_lo, H):
+    _lib.require_cuda()
+    out = torch.empty((H, params.sample_size), dtype=torch.int32, device=_dev())
+    rc = _lib.lib().lr_ransac_sample(ctypes.byref(params), ctypes.c_int64(n), ctypes.c_int64(id_lo),
+                                     ctypes.c_int64(H), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_sample")
+    return out
+
+
+def refit_indexed(xyz0, xyz1, i0, i1, T, threshold=0.6):
+    """lr_refit_indexed (FR.py:99-111) -> (T[4,4], inlier count)."""
+    xyz0, xyz1, i0, i1 = to_dev_f32(xyz0), to_dev_f32(xyz1), to_dev_i64(i0), to_dev_i64(i1)
+    Tin = (ctypes.c_double * 16)(*np.asarray(T, dtype=np.float64).reshape(-1))
+    Tout = (ctypes.c_double * 16)()
+    cnt = ctypes.c_int64(0)
+    rc = _lib.lib().lr_refit_indexed(_lib.ptr(xyz0), _lib.ptr(xyz1), _lib.ptr(i0), _lib.ptr(i1),
+                                     ctypes.c_int64(i0.shape[0]), Tin, ctypes.c_double(threshold), Tout,
+                                     ctypes.byref(cnt), _lib.stream_ptr())
+    _lib.check(rc, "lr_refit_indexed")
+    return _lib.T_from16(Tout), int(cnt.value)
+
+
+def key_unpack(key):
+    """packed (count + 1) << 32 | (0xFFFFFFFF - id)  ->  (count, id); (−1, −1) for the empty key"""
+    key = int(key) & 0xFFFFFFFFFFFFFFFF
+    if key == 0:
+        return -1, -1
+    return (key >> 32) - 1, 0xFFFFFFFF - (key & 0xFFFFFFFF)
+
+
+def key_pack(count, hid):
+    return ((int(count) + 1) << 32) | (0xFFFFFFFF - int(hid))

@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def matching_golden(golden_dir):
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "matching_ref.npz"))
+    cases = {}
+    for key in z.files:
+        case, field = key.split("/")
+        cases.setdefault(case, {})[field] = z[key]
+    return cases
+
+
+@pytest.fixture(scope="session")
+def kabsch_golden(golden_dir):
+    import numpy as np
+    return np.load(os.path.join(golden_dir, "kabsch_ref.npz"))

@@ -1,0 +1,99 @@
+"""Generate the golden fixtures of tests/golden/ by RUNNING THE REFERENCE.
+
+Run in the build container only (needs /root/reference, which does not exist
+on the GPU box):   python tests/golden/make_golden.py
+
+Imports, unmodified:
+  /root/reference/Experiments/algorithms/matching.py   (find_nn, nn_to_mutual, ratio)
+  /root/reference/Experiments/models/common.py         (rigid_transform_3d: Kabsch witness)
+on CPU torch and stores inputs + the reference's outputs as .npz.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference/Experiments"
+sys.path.insert(0, REF)
+from algorithms import matching as RM  # noqa: E402
+from models.common import rigid_transform_3d  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def unit(x):
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+def run_matching(f0, f1):
+    t0, t1 = torch.from_numpy(f0), torch.from_numpy(f1)
+    i0, i1, i2 = RM.find_nn(t0, t1, return_2nd=True)
+    _, i1_only, none = RM.find_nn(t0, t1, return_2nd=False)
+    assert none is None and torch.equal(i1, i1_only)
+    m0, m1, m2 = RM.nn_to_mutual(t0, t1, i0, i1, i2)
+    ratio = RM.calc_distance_ratio_in_feature_space(t0, t1, m0, m1, m2)
+    return dict(f0=f0, f1=f1, idx1=i1.numpy(), idx2=i2.numpy(), mut_i=m0.numpy(), mut_j=m1.numpy(),
+                mut_2nd=m2.numpy(), ratio=ratio.numpy())
+
+
+def matching_cases():
+    rng = np.random.default_rng(51)
+    cases = {}
+    # (a) FCGF-shaped: unit features, partial overlap, planted exact duplicates (ties)
+    N, M, D = 1500, 1700, 32
+    f0 = unit(rng.standard_normal((N, D)))
+    f1 = unit(rng.standard_normal((M, D)))
+    f1[:800] = unit(f0[:800] + 0.08 * rng.standard_normal((800, D)).astype(np.float32))
+    f1[1000] = f1[17]; f1[1001] = f1[17]; f0[5] = f1[17]          # three identical targets
+    f0[6] = f0[5]                                                  # two identical queries
+    f1[1200:1210] = f1[300:310]                                    # duplicate block
+    cases["fcgf"] = run_matching(f0, f1)
+    # (b) ragged sizes around the 128 / 250 tile edges, non-unit norms
+    for name, (n, m) in dict(r1=(2, 3), r2=(3, 2), r3=(129, 127), r4=(250, 251), r5=(257, 513), r6=(37, 1000)).items():
+        g0 = (rng.standard_normal((n, D)) * rng.uniform(0.2, 3.0, (n, 1))).astype(np.float32)
+        g1 = (rng.standard_normal((m, D)) * rng.uniform(0.2, 3.0, (m, 1))).astype(np.float32)
+        cases[name] = run_matching(g0, g1)
+    # (c) other feature widths the kernels instantiate
+    for d in (8, 16, 64):
+        g0 = unit(rng.standard_normal((300, d)))
+        g1 = unit(rng.standard_normal((280, d)))
+        cases[f"d{d}"] = run_matching(g0, g1)
+    # (d) all-identical rows: every distance ties, index 0 / 1 must win
+    g0 = np.tile(unit(rng.standard_normal((1, D))), (40, 1))
+    cases["allsame"] = run_matching(g0, g0.copy()[:33])
+    flat = {}
+    for k, v in cases.items():
+        for kk, vv in v.items():
+            flat[f"{k}/{kk}"] = vv
+    np.savez_compressed(os.path.join(OUT, "matching_ref.npz"), **flat)
+    print("matching_ref.npz:", {k: (v["f0"].shape, v["f1"].shape, len(v["mut_i"])) for k, v in cases.items()})
+
+
+def kabsch_cases():
+    rng = np.random.default_rng(52)
+    Ps, Qs, Ts, ks = [], [], [], []
+    for trial in range(200):
+        k = 3 if trial < 80 else (4 if trial < 120 else int(rng.integers(5, 400)))
+        P = rng.uniform(-10, 10, (k, 3))
+        ang = rng.uniform(-np.pi, np.pi)
+        ax = rng.standard_normal(3); ax /= np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        Q = P @ R.T + rng.uniform(-5, 5, 3) + rng.normal(0, 0.05, (k, 3))
+        if trial % 5 == 0:
+            Q = rng.uniform(-10, 10, (k, 3))  # unrelated clouds: exercises the reflection fix
+        # the witness only runs in fp32 (its `eye` is float32): modest coordinates keep it accurate
+        P, Q = P.astype(np.float32), Q.astype(np.float32)
+        T = rigid_transform_3d(torch.from_numpy(P)[None], torch.from_numpy(Q)[None])[0].numpy()
+        pad = 400 - k
+        Ps.append(np.pad(P, ((0, pad), (0, 0)))); Qs.append(np.pad(Q, ((0, pad), (0, 0)))); Ts.append(T); ks.append(k)
+    np.savez_compressed(os.path.join(OUT, "kabsch_ref.npz"), P=np.array(Ps), Q=np.array(Qs), T=np.array(Ts),
+                        k=np.array(ks))
+    print("kabsch_ref.npz:", len(ks), "cases")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    matching_cases()
+    kabsch_cases()
