@@ -9,9 +9,5 @@ pairs over GPUs.  There is no CPU implementation in this package.
 """
 __version__ = "0.1.0"
 
-from . import _lib, engine  # noqa: F401
+from . import _lib, build, engine  # noqa: F401
 
-
-def build(force=False, verbose=False):
-    from . import build as _b
-    return _b.build(force=force, verbose=verbose)

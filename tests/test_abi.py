@@ -1,0 +1,64 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/lidarreg.h declares."""
+import os
+import re
+
+import pytest
+
+from lidarregistration_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "lidarreg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    build.build()
+    L = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in lidarreg.h but not exported"
+    assert sorted(_lib.SYMBOLS) == syms
+    assert L.lr_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    import ctypes
+    assert ctypes.sizeof(_lib.LrRansacParams) == 3 * 8 + 2 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.LrRansacStats) == 6 * 8
+
+
+def test_host_only_entry_points():
+    from lidarregistration_b200 import engine
+    from oracle import lr_oracle as O
+    for c, n, m, conf in [(9000, 30000, 3, 0.9995), (1, 30000, 3, 0.999), (300, 30000, 4, 0.9995), (0, 10, 3, 0.5)]:
+        assert engine.conf_iters(c, n, m, conf, 10**6) == O.conf_iters(c, n, m, conf, 10**6)
+    assert engine.key_unpack(engine.key_pack(1234, 77)) == (1234, 77)
+    assert engine.key_unpack(0) == (-1, -1)
+    # ties: lower id wins under MAX
+    assert engine.key_pack(10, 3) > engine.key_pack(10, 4) > engine.key_pack(9, 0)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lidarregistration_b200 import engine
+    with pytest.raises(RuntimeError):
+        engine.match_nn(torch.zeros(4, 32), torch.zeros(4, 32))
+    with pytest.raises(RuntimeError):
+        engine.ransac_rigid(torch.zeros(4, 3), torch.zeros(4, 3), engine.make_params())
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lidarregistration_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "lr_oracle" not in txt.replace("oracle/lr_oracle.c", "") and "import oracle" not in txt \
+                    and "from oracle" not in txt, f

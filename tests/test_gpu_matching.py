@@ -1,0 +1,88 @@
+"""CUDA matching kernels vs the oracle / the reference's golden outputs, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from lidarregistration_b200 import engine, synthetic
+from lidarregistration_b200.algorithms import matching as GM
+from oracle import lr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_find_nn_and_mutual(matching_golden):
+    for name, c in matching_golden.items():
+        f0, f1 = torch.from_numpy(c["f0"]), torch.from_numpy(c["f1"])
+        i0, i1, i2 = GM.find_nn(f0, f1, return_2nd=True)
+        assert i1.dtype == torch.int64 and not i1.is_cuda
+        assert np.array_equal(i1.numpy(), c["idx1"]), name
+        assert np.array_equal(i2.numpy(), c["idx2"]), name
+        assert np.array_equal(i0.numpy(), np.arange(len(c["f0"])))
+        _, j1, none = GM.find_nn(f0, f1)
+        assert none is None and torch.equal(j1, i1)
+        m0, m1, m2 = GM.nn_to_mutual(f0, f1, i0, i1, i2)
+        assert np.array_equal(m0.numpy(), c["mut_i"]) and np.array_equal(m1.numpy(), c["mut_j"]), name
+        assert np.array_equal(m2.numpy(), c["mut_2nd"]), name
+        r = GM.calc_distance_ratio_in_feature_space(f0, f1, m0, m1, m2).numpy()
+        ok = np.isfinite(c["ratio"])
+        assert np.allclose(r[ok], c["ratio"][ok], rtol=3e-7, atol=0), name
+        ro = O.ratio(c["f0"], c["f1"], c["mut_i"], c["mut_j"], c["mut_2nd"])
+        assert np.array_equal(r[ok], ro[ok]), name  # bit-exact against the oracle
+
+
+@pytest.mark.parametrize("N,M,seed", [(5000, 6000, 1), (4097, 3001, 2), (20000, 20000, 3)])
+def test_find_nn_vs_oracle_synthetic(N, M, seed):
+    p = synthetic.make_pair(N, M, seed=seed, overlap=0.6)
+    i1, i2 = engine.match_nn(p["feat0"], p["feat1"], want_2nd=True)
+    _, o1, o2 = O.find_nn(p["feat0"], p["feat1"], return_2nd=True)
+    assert np.array_equal(i1.cpu().numpy(), o1)
+    assert np.array_equal(i2.cpu().numpy(), o2)
+    mi, mj = engine.match_mutual(p["feat0"], p["feat1"], i1)
+    oi, oj = O.nn_to_mutual(p["feat0"], p["feat1"], o1)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mj.cpu().numpy(), oj)
+
+
+def test_find_2nn_contract():
+    p = synthetic.make_pair(3000, seed=8)
+    i0, i1, i2, extra = GM.find_2nn(torch.from_numpy(p["feat0"]), torch.from_numpy(p["feat1"]))
+    assert isinstance(extra, float) and len(i0) == len(i1) == len(i2) == 3000
+    assert not torch.any(i1 == i2)
+
+
+def test_full_size_properties():
+    """cfg 2 of BASELINE.json (N = M = 50k x 32): size-independent properties instead of the oracle."""
+    N = M = 50000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f0 = torch.nn.functional.normalize(torch.randn(N, 32, device="cuda", generator=g), dim=1)
+    f1 = torch.nn.functional.normalize(torch.randn(M, 32, device="cuda", generator=g), dim=1)
+    f1[:20000] = torch.nn.functional.normalize(f0[:20000] + 0.05 * torch.randn(20000, 32, device="cuda", generator=g), dim=1)
+    i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+    assert int(i1.min()) >= 0 and int(i1.max()) < M and not torch.any(i1 == i2)
+    # planted neighbours are found
+    assert (i1[:20000] == torch.arange(20000, device="cuda")).float().mean() > 0.99
+    # d(i, nn) <= d(i, 2nd) <= d(i, random j)
+    d = lambda a, b: (a - b).norm(dim=1)
+    rnd = torch.randint(0, M, (N,), device="cuda")
+    assert torch.all(d(f0, f1[i1]) <= d(f0, f1[i2]) + 1e-6)
+    assert torch.all(d(f0, f1[i2]) <= d(f0, f1[rnd]) + 1e-6 + (rnd == i1) * 10)
+    # mutual is an involution: matching the other way gives the transposed pair set
+    mi, mj = engine.match_mutual(f0, f1, i1)
+    r1, _ = engine.match_nn(f1, f0)
+    ni, nj = engine.match_mutual(f1, f0, r1)
+    a = torch.stack([mi, mj], 1)
+    b = torch.stack([nj, ni], 1)
+    b = b[torch.argsort(b[:, 0])]
+    assert torch.equal(a, b) and torch.all(mi[1:] > mi[:-1])
+    # exact check of a random row sample against the oracle arithmetic
+    rows = torch.randint(0, N, (64,), device="cuda").cpu().numpy()
+    _, o1, o2 = O.find_nn(f0.cpu().numpy()[rows], f1.cpu().numpy(), return_2nd=True)
+    assert np.array_equal(i1.cpu().numpy()[rows], o1) and np.array_equal(i2.cpu().numpy()[rows], o2)
+
+
+def test_gather_and_errors():
+    xyz = torch.arange(30, dtype=torch.float32).reshape(10, 3)
+    idx = torch.tensor([9, 0, 3, 3])
+    out = engine.gather_xyz(xyz, idx).cpu()
+    assert torch.equal(out, xyz[idx])
+    with pytest.raises(RuntimeError):
+        engine.match_nn(torch.zeros(4, 20), torch.zeros(4, 20))  # unsupported D
