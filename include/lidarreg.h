@@ -70,6 +70,15 @@ int lr_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* release every device workspace held by the library */
 int lr_shutdown(void);
 
+/* ---- measurement hooks (used by bench.py only) -------------------------- */
+enum { LR_PROF_SCORE = 0, LR_PROF_GEN = 1, LR_PROF_NN = 2, LR_PROF_RECOUNT = 3 };
+/* bracket the heavy kernels with CUDA events on their stream (off by default) */
+int lr_prof_enable(int on);
+/* [host] device milliseconds and launch count of one kernel class since the last read */
+int lr_prof_read(int kind, double *total_ms, int64_t *launches);
+/* [host] measured FP32 FMA throughput (TFLOP/s): mode 0 = FFMA, 1 = packed fma.rn.f32x2 */
+int lr_peak_fp32(int mode, double *tflops);
+
 /* ---- correspondence search (Experiments/algorithms/matching.py) ------- */
 
 /* find_nn (matching.py:22-65).  f0[N,D], f1[M,D] fp32 row-major; D multiple of

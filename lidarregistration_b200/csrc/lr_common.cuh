@@ -52,6 +52,11 @@ struct Lock {
     ~Lock();
 };
 
+// optional device-time accounting (lr_prof.cu); tokens are -1 when disabled
+enum ProfKind { PROF_SCORE = 0, PROF_GEN = 1, PROF_NN = 2, PROF_RECOUNT = 3 };
+int prof_begin(int kind, cudaStream_t st);
+void prof_end(int token, cudaStream_t st);
+
 // carve 256-byte aligned pieces out of one arena block
 struct Carver {
     char *base;

@@ -384,6 +384,7 @@ int nn_sweep(const float *f0, int64_t N, const float *f1, int64_t M, int D, int6
     k_sqnorms<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(f1, M, D, n1);
     int rc;
     const bool want2 = idx2 != nullptr;
+    const int tok = lr::prof_begin(lr::PROF_NN, st);
     switch (D) {
         case 8: rc = launch_nn_d<8>(f0, N, f1, M, n0, n1, part, tps, nsplit, want2, st); break;
         case 16: rc = launch_nn_d<16>(f0, N, f1, M, n0, n1, part, tps, nsplit, want2, st); break;
@@ -392,6 +393,7 @@ int nn_sweep(const float *f0, int64_t N, const float *f1, int64_t M, int D, int6
         default: lr::set_error("unsupported feature dimension D=%d (8, 16, 32 or 64)", D); return LR_ERR_ARG;
     }
     if (rc) return rc;
+    lr::prof_end(tok, st);
     k_nn_merge<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(part, N, nsplit, idx1, idx2);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;

@@ -56,6 +56,7 @@ struct Ws {
     float4 *m32;      // 4 x float4 per slot: R rows + t, then (lo, hi, -, -)
     double *m64;      // 12 per slot
     int *flagged;
+    int2 *cnt;        // per slot: (#r2 < lo, #r2 < hi) accumulated over point splits
     int *need;        // per round: inlier count that triggers the confidence exit
     double *scratchT; // 16 doubles of staging
     int64_t n_pad;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(kGenThreads)
 k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, uint64_t seed, int sampler,
       int use_elc, double elc_ratio, double thr2, int64_t id_lo, int64_t id_hi,
       const int32_t *__restrict__ fed, Ctl *ctl, uint32_t *__restrict__ slot_id, float4 *__restrict__ m32,
-      double *__restrict__ m64)
+      double *__restrict__ m64, int2 *__restrict__ cnt)
 {
     if (ctl->done) return;
     int64_t id = id_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -395,6 +396,7 @@ k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, u
     if (!ok) return;
     int slot = base + __popc(ballot & ((1u << lane) - 1u));
     slot_id[slot] = (uint32_t)id;
+    cnt[slot] = make_int2(0, 0);
 #pragma unroll
     for (int k = 0; k < 12; ++k) m64[(size_t)slot * 12 + k] = T[k];
     // fp32 copy + error band of the inlier test (DESIGN.md "fp32 bracket")
@@ -424,25 +426,35 @@ __device__ __forceinline__ void cp_async_wait()
 }
 
 // Inlier sweep.  Each thread owns one surviving hypothesis ([R|t] in fp32
-// registers) and walks every correspondence; correspondences are staged
-// through shared memory in double-buffered chunks with cp.async and read as
-// warp-wide broadcasts (LDS.128 + LDS.64 per point per warp).  Per pair:
-// 12 FFMA/FADD for R p + t - q, 3 for |.|^2, two compare+add for the bracket.
+// registers) and walks correspondences staged through shared memory in
+// double-buffered chunks with cp.async, read as warp-wide broadcasts
+// (LDS.128 + LDS.64 per point per warp).  Per pair: 12 FFMA/FADD for
+// R p + t - q, 3 for |.|^2, two compare+add for the bracket.
+// Work item = (block of 128 survivors) x (range of point chunks); the split
+// over points is chosen on the device from the survivor count so that a round
+// with few survivors (ELC rejects ~97 % at 70 % outliers) still fills the chip.
 __global__ void __launch_bounds__(kScoreThreads)
 k_score(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n_pad, Ctl *ctl,
-        const uint32_t *__restrict__ slot_id, const float4 *__restrict__ m32, int *__restrict__ flagged,
-        int32_t *__restrict__ counts_out, int64_t id_base)
+        const float4 *__restrict__ m32, int2 *__restrict__ cnt)
 {
     if (ctl->done) return;
     __shared__ __align__(16) float4 sP[2][kChunk];
     __shared__ __align__(16) float2 sQ[2][kChunk];
     const int tid = threadIdx.x;
     const int nsurv = ctl->n_surv;
-    const int nitems = (nsurv + kScoreThreads - 1) / kScoreThreads;
+    const int nhb = (nsurv + kScoreThreads - 1) / kScoreThreads;
+    if (nhb == 0) return;
     const int nchunks = (int)(n_pad / kChunk);
+    int nps = (2 * (int)gridDim.x + nhb - 1) / nhb;
+    nps = nps < 1 ? 1 : (nps > nchunks ? nchunks : nps);
+    const int cpp = (nchunks + nps - 1) / nps;  // chunks per point split
+    nps = (nchunks + cpp - 1) / cpp;
+    const int nitems = nhb * nps;
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int slot = item * kScoreThreads + tid;
+        const int hb = item / nps, ps = item - hb * nps;
+        const int c_lo = ps * cpp, c_hi = min(nchunks, c_lo + cpp);
+        const int slot = hb * kScoreThreads + tid;
         const bool valid = slot < nsurv;
         float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, bw = make_float4(-1.f, -1.f, 0, 0);
         if (valid) {
@@ -465,10 +477,10 @@ k_score(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n_
             cp_async_commit();
         };
 
-        stage(0, 0);
-        for (int c = 0; c < nchunks; ++c) {
-            const int buf = c & 1;
-            if (c + 1 < nchunks) {
+        stage(c_lo, 0);
+        for (int c = c_lo; c < c_hi; ++c) {
+            const int buf = (c - c_lo) & 1;
+            if (c + 1 < c_hi) {
                 stage(c + 1, buf ^ 1);
                 cp_async_wait<1>();
             } else {
@@ -488,20 +500,39 @@ k_score(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n_
             }
             __syncthreads();
         }
-
-        unsigned long long key = 0ULL;
         if (valid) {
-            if (cnt_lo == cnt_hi) {
-                const uint32_t id = slot_id[slot];
-                key = make_key(cnt_lo, id);
-                if (counts_out) counts_out[(int64_t)id - id_base] = cnt_lo;
+            if (nps == 1) {
+                cnt[slot] = make_int2(cnt_lo, cnt_hi);
             } else {
-                flagged[atomicAdd(&ctl->n_flag, 1)] = slot;
+                if (cnt_lo) atomicAdd(&cnt[slot].x, cnt_lo);
+                if (cnt_hi) atomicAdd(&cnt[slot].y, cnt_hi);
             }
         }
-        key = warp_max_u64(key);
-        if ((tid & 31) == 0 && key) atomicMax(&ctl->round_key, key);
     }
+}
+
+// closes the bracket: exact slots feed the packed arg-max, open ones are queued
+// for the fp64 recount
+__global__ void __launch_bounds__(256)
+k_resolve(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int2 *__restrict__ cnt, int *__restrict__ flagged,
+          int32_t *__restrict__ counts_out, int64_t id_base)
+{
+    if (ctl->done) return;
+    const int nsurv = ctl->n_surv;
+    unsigned long long key = 0ULL;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
+        const int2 c = cnt[slot];
+        if (c.x == c.y) {
+            const uint32_t id = slot_id[slot];
+            const unsigned long long k = make_key(c.x, id);
+            key = k > key ? k : key;
+            if (counts_out) counts_out[(int64_t)id - id_base] = c.x;
+        } else {
+            flagged[atomicAdd(&ctl->n_flag, 1)] = slot;
+        }
+    }
+    key = warp_max_u64(key);
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(&ctl->round_key, key);
 }
 
 // exact fp64 recount of the hypotheses whose fp32 bracket stayed open
@@ -748,6 +779,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
     size_t bytes = lr::padded(sizeof(Ctl)) + lr::padded(sizeof(float4) * ws.n_pad) + lr::padded(sizeof(float2) * ws.n_pad) +
                    lr::padded(sizeof(uint32_t) * round) + lr::padded(sizeof(float4) * 4 * round) +
                    lr::padded(sizeof(double) * 12 * round) + lr::padded(sizeof(int) * round) +
+                   lr::padded(sizeof(int2) * round) +
                    lr::padded(sizeof(int) * (nrounds + 1)) + lr::padded(sizeof(double) * 16);
     void *base = lr::arena_get(lr::SLOT_RANSAC, bytes);
     if (!base) return LR_ERR_ALLOC;
@@ -759,6 +791,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
     ws.m32 = cv.take<float4>(4 * round);
     ws.m64 = cv.take<double>(12 * round);
     ws.flagged = cv.take<int>(round);
+    ws.cnt = cv.take<int2>(round);
     ws.need = cv.take<int>(nrounds + 1);
     ws.scratchT = cv.take<double>(16);
     return LR_OK;
@@ -772,9 +805,15 @@ int check_params(const LrRansacParams *p, int64_t n)
                "sampler must be LR_SAMPLER_UNIFORM or LR_SAMPLER_REPLACE (PROSAC: not implemented)");
     LR_REQUIRE(p->threshold > 0.0, "threshold must be positive");
     LR_REQUIRE(p->max_iters >= 0 && p->max_iters < (int64_t)0xFFFFFFFFLL, "max_iters out of range");
-    LR_REQUIRE(p->round_size > 0 && p->round_size <= (1 << 22), "round_size out of range");
+    LR_REQUIRE(p->round_size > 0 && p->round_size <= (1 << 20), "round_size out of range");
     LR_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "n out of range");
     return LR_OK;
+}
+
+int64_t batch_len(int64_t total)
+{
+    const int64_t cap = (int64_t)1 << 20;
+    return total < 1 ? 1 : (total < cap ? total : cap);
 }
 
 int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cudaStream_t st)
@@ -794,19 +833,27 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     if (len <= 0) return LR_OK;
     const double thr2 = p.threshold * p.threshold;
     int gblocks = (int)((len + kGenThreads - 1) / kGenThreads);
+    int tok = lr::prof_begin(lr::PROF_GEN, st);
     if (p.sample_size == 3)
         k_gen<3><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, thr2, lo, hi,
-                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64);
+                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64, ws.cnt);
     else
         k_gen<4><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, thr2, lo, hi,
-                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64);
+                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64, ws.cnt);
+    lr::prof_end(tok, st);
     int items = (int)((len + kScoreThreads - 1) / kScoreThreads);
-    int sblocks = lr::sm_count() * 4;
-    if (sblocks > items) sblocks = items;
-    k_score<<<sblocks, kScoreThreads, 0, st>>>(ws.P4, ws.Q2, ws.n_pad, ws.ctl, ws.slot_id, ws.m32, ws.flagged,
-                                               counts_out, lo);
+    int sblocks = lr::sm_count() * 4;  // 4 resident CTAs of 128 threads per SM (48 KB smem each)
+    (void)items;
+    tok = lr::prof_begin(lr::PROF_SCORE, st);
+    k_score<<<sblocks, kScoreThreads, 0, st>>>(ws.P4, ws.Q2, ws.n_pad, ws.ctl, ws.m32, ws.cnt);
+    lr::prof_end(tok, st);
+    int rblocks = (int)((len + 255) / 256);
+    if (rblocks > lr::sm_count() * 4) rblocks = lr::sm_count() * 4;
+    k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, ws.flagged, counts_out, lo);
+    tok = lr::prof_begin(lr::PROF_RECOUNT, st);
     k_recount<<<lr::sm_count() * 2, 256, 0, st>>>(ws.P4, ws.Q2, n, ws.ctl, ws.slot_id, ws.m64, ws.flagged, thr2,
                                                   counts_out, lo);
+    lr::prof_end(tok, st);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -903,7 +950,12 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
         LR_CUDA_TRY(cudaStreamSynchronize(st));
         return LR_OK;
     }
-    const int64_t R = p.round_size;
+    // With the confidence exit the round length is part of the result's
+    // definition (the exit is evaluated at round ends); with a fixed budget the
+    // result is a plain arg-max, so hypotheses are batched as large as the
+    // scratch allows to keep every launch chip-filling.
+    const bool use_conf = p.confidence < 1.0 && p.max_iters > 0;
+    const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
     const int64_t nrounds = (p.max_iters + R - 1) / R;
     Ws ws;
     rc = ws_setup(n, R, nrounds, ws);
@@ -912,7 +964,6 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
     if (rc) return rc;
     // confidence exit: need[r] = smallest best-count that lets the loop stop
     // after round r (conf_iters is non-increasing in the count)
-    const bool use_conf = p.confidence < 1.0 && nrounds > 0;
     std::vector<int> need;
     if (use_conf) {
         need.resize(nrounds);
@@ -957,7 +1008,7 @@ LR_EXPORT int lr_ransac_score_samples(const float *src, const float *tgt, int64_
     p.sample_size = m;
     p.sampler = LR_SAMPLER_UNIFORM;
     p.use_elc = use_elc;
-    const int64_t R = H < 65536 ? H : 65536;
+    const int64_t R = batch_len(H);
     p.round_size = (int32_t)R;
     Ws ws;
     int rc = ws_setup(n, R, 1, ws);
@@ -995,7 +1046,7 @@ LR_EXPORT int lr_ransac_shard(const float *src, const float *tgt, int64_t n, con
     LR_REQUIRE(id_lo >= 0 && id_hi >= id_lo && id_hi < (int64_t)0xFFFFFFFFLL, "id range out of bounds");
     cudaStream_t st = (cudaStream_t)stream;
     const LrRansacParams &p = *params;
-    const int64_t R = p.round_size;
+    const int64_t R = batch_len(id_hi - id_lo);
     Ws ws;
     rc = ws_setup(n, R, 1, ws);
     if (rc) return rc;

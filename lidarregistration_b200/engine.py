@@ -202,3 +202,25 @@ def key_unpack(key):
 
 def key_pack(count, hid):
     return ((int(count) + 1) << 32) | (0xFFFFFFFF - int(hid))
+
+
+# ------------------------------------------------------------- measurement
+PROF_SCORE, PROF_GEN, PROF_NN, PROF_RECOUNT = 0, 1, 2, 3
+
+
+def prof_enable(on=True):
+    _lib.check(_lib.lib().lr_prof_enable(int(bool(on))), "lr_prof_enable")
+
+
+def prof_read(kind):
+    """-> (device milliseconds, launches) of one kernel class since the last read"""
+    ms, cnt = ctypes.c_double(0.0), ctypes.c_int64(0)
+    _lib.check(_lib.lib().lr_prof_read(int(kind), ctypes.byref(ms), ctypes.byref(cnt)), "lr_prof_read")
+    return float(ms.value), int(cnt.value)
+
+
+def peak_fp32(mode=0):
+    _lib.require_cuda()
+    v = ctypes.c_double(0.0)
+    _lib.check(_lib.lib().lr_peak_fp32(int(mode), ctypes.byref(v)), "lr_peak_fp32")
+    return float(v.value)
