@@ -88,6 +88,11 @@ int lr_peak_fp32(int mode, double *tflops);
 int lr_match_nn(const float *f0, int64_t N, const float *f1, int64_t M, int D, int64_t *idx1,
                 int64_t *idx1_2nd, void *stream);
 
+/* Implementation switch for lr_match_nn / lr_match_mutual (both give identical indices):
+ * 0 = tensor-core sweep (tcgen05, fp16 operands) + exact fp32 re-rank when D == 32 [default];
+ * 1 = exact fp32 CUDA-core sweep for every D. */
+int lr_match_set_mode(int mode);
+
 /* nn_to_mutual (matching.py:222-239) incl. torch_intersect (:67-87): keeps
  * (i, idx1[i]) iff i is the nearest neighbour of idx1[i] in f0.  out_i/out_j
  * have room for N entries and come out sorted by i; *K [device] = count. */

@@ -20,9 +20,12 @@
 // compares d2 against the smallest d2 whose sqrt reaches the current value.
 #include <math.h>
 
-#include "lr_common.cuh"
+#include "lr_match_tc.cuh"
 
 namespace {
+
+int g_match_mode = 0;  // 0: tensor-core sweep when D == 32; 1: always the exact CUDA-core sweep
+
 
 constexpr int BM = 128, BN = 128, NT = 256;  // block tile and threads (8 x 8 outputs per thread)
 
@@ -416,9 +419,25 @@ LR_EXPORT int lr_match_nn(const float *f0, int64_t N, const float *f1, int64_t M
     LR_REQUIRE(f0 && f1 && idx1, "null pointer");
     LR_REQUIRE(N > 0 && M > 0 && N < ((int64_t)1 << 31) && M < ((int64_t)1 << 31), "N/M out of range");
     cudaStream_t st = (cudaStream_t)stream;
+    if (D == 32 && g_match_mode == 0) {
+        char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH, lr_tc::scratch_bytes(N, M));
+        if (!scratch) return LR_ERR_ALLOC;
+        lr_tc::Prepared P;
+        int rc = lr_tc::prepare(f0, N, f1, M, scratch, P, st);
+        if (rc) return rc;
+        return lr_tc::sweep(P, false, f0, N, f1, M, idx1, idx1_2nd, st);
+    }
     char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH, nn_scratch_bytes(N, M));
     if (!scratch) return LR_ERR_ALLOC;
     return nn_sweep(f0, N, f1, M, D, idx1, idx1_2nd, scratch, st);
+}
+
+LR_EXPORT int lr_match_set_mode(int mode)
+{
+    lr::Lock lock;
+    LR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (auto) or 1 (exact CUDA-core sweep)");
+    g_match_mode = mode;
+    return LR_OK;
 }
 
 LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64_t M, int D, const int64_t *idx1,
@@ -432,10 +451,20 @@ LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64
     // does it for unique(idx1) only (matching.py:224-225); rows outside that
     // set are never consulted by the intersection, so the result is identical.
     const size_t rev_bytes = lr::padded(sizeof(int64_t) * M);
-    char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH, rev_bytes + nn_scratch_bytes(M, N));
+    const bool tc = D == 32 && g_match_mode == 0;
+    char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH,
+                                          rev_bytes + (tc ? lr_tc::scratch_bytes(N, M) : nn_scratch_bytes(M, N)));
     if (!scratch) return LR_ERR_ALLOC;
     int64_t *rev = reinterpret_cast<int64_t *>(scratch);
-    int rc = nn_sweep(f1, M, f0, N, D, rev, nullptr, scratch + rev_bytes, st);
+    int rc;
+    if (tc) {
+        lr_tc::Prepared P;
+        rc = lr_tc::prepare(f0, N, f1, M, scratch + rev_bytes, P, st);
+        if (rc) return rc;
+        rc = lr_tc::sweep(P, true, f0, N, f1, M, rev, nullptr, st);
+    } else {
+        rc = nn_sweep(f1, M, f0, N, D, rev, nullptr, scratch + rev_bytes, st);
+    }
     if (rc) return rc;
     k_mutual_compact<<<1, 1024, 0, st>>>(idx1, rev, N, M, out_i, out_j, K);
     LR_CUDA_TRY(cudaGetLastError());

@@ -1,0 +1,622 @@
+// lr_match_tc.cu -- tensor-core nearest-neighbour sweep (tcgen05 + TMEM + bulk-TMA) for D = 32.
+//
+// Replaces the inner loop of find_nn (Experiments/algorithms/matching.py:22-65 of the
+// reference: 250-row SGEMM chunks + norms + sqrt + min) with a distance GEMM on the 5th-gen
+// tensor cores whose epilogue never leaves the SM:
+//
+//   operands   fp16 copies of the (power-of-two scaled) features in the canonical no-swizzle
+//              K-major "core matrix" layout, 128 B per row: 4 cores of 8 features, 2 cores of
+//              A-role extension (1, 1, 0..) and 2 cores of B-role extension (c_hi, c_lo, 0..)
+//              with c = -s^2 |b|^2 / 2, so that one K = 48 MMA chain yields
+//              v_ij = s^2 (a_i . b_j - |b_j|^2 / 2)  =  -s^2 (d2_ij - |a_i|^2) / 2
+//   staging    cp.async.bulk (UBLKCP, the TMA engine) global -> shared, completion on mbarriers,
+//              4-stage ring of 256-row target tiles, double-buffered 128-row query tile
+//   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N 256, K 16) x 3
+//              into one of two 256-column fp32 accumulators in TMEM
+//   epilogue   4 warps read their TMEM lane quadrant with tcgen05.ld.32x32b.x32; a thread owns a
+//              query row, keeps its running maximum and collects every column whose v is within
+//              `beta` of it (3-input FMNMX tree per 32 columns, one compare, rare slow path)
+//
+// `beta` bounds the fp16/tensor-core error, so the collected set provably contains the argmin
+// of the reference's fp32 expression; k_rerank then evaluates that expression exactly (same
+// operation order as oracle/lr_oracle.c) on the few candidates, which makes the indices
+// bit-exact.  Rows whose candidate list overflows are redone by an exact scan.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "lr_match_tc.cuh"
+
+namespace lr_tc {
+
+constexpr int TM = 128;                      // query rows per tile (UMMA M)
+constexpr int TN = 256;                      // target rows per tile (UMMA N)
+constexpr int KCORES = 8;                    // 16-byte K cores per row (4 data + 2 A-ext + 2 B-ext)
+constexpr int RG_BYTES = KCORES * 128;       // one group of 8 rows
+constexpr int A_TILE_BYTES = TM / 8 * RG_BYTES;  // 16 KB
+constexpr int B_TILE_BYTES = TN / 8 * RG_BYTES;  // 32 KB
+constexpr int STAGES = 4;
+constexpr int CAND = 32;                     // candidate slots per query row
+constexpr int NTHREADS = 192;                // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// A, B = f16 (format 0), both K-major (0), no negate, dense
+
+struct Params {
+    float scale;   // power of two applied to both feature sets before the fp16 conversion
+    float beta;    // half-width of the candidate band in v units
+    unsigned maxn0_bits, maxn1_bits;
+    int ovf_count;
+    int pad[3];
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// K-major, no swizzle: 8-row groups SBO apart, K cores LBO apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(RG_BYTES >> 4) << 32) |
+           (1ull << 46);
+}
+// tcgen05.ld is asynchronous: the registers are valid only after tcgen05.wait::ld.  The wait lists
+// them as in/out operands so the compiler cannot schedule a use above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- operand preparation
+__global__ void k_params_reset(Params *p)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        p->maxn0_bits = 0u;
+        p->maxn1_bits = 0u;
+        p->ovf_count = 0;
+    }
+}
+
+// canonical squared norms (8-lane order, == oracle) + their maximum
+__global__ void k_sqnorms_max(const float *__restrict__ F, int64_t N, float *__restrict__ out, unsigned *maxbits)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float s = 0.f;
+    if (i < N) {
+        const float4 *x = reinterpret_cast<const float4 *>(F + i * 32);
+        float lane[8];
+        float4 a = x[0], b = x[1];
+        lane[0] = a.x * a.x; lane[1] = a.y * a.y; lane[2] = a.z * a.z; lane[3] = a.w * a.w;
+        lane[4] = b.x * b.x; lane[5] = b.y * b.y; lane[6] = b.z * b.z; lane[7] = b.w * b.w;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            a = x[2 * k];
+            b = x[2 * k + 1];
+            lane[0] = lane[0] + a.x * a.x; lane[1] = lane[1] + a.y * a.y;
+            lane[2] = lane[2] + a.z * a.z; lane[3] = lane[3] + a.w * a.w;
+            lane[4] = lane[4] + b.x * b.x; lane[5] = lane[5] + b.y * b.y;
+            lane[6] = lane[6] + b.z * b.z; lane[7] = lane[7] + b.w * b.w;
+        }
+        s = lane[0];
+#pragma unroll
+        for (int l = 1; l < 8; ++l) s = s + lane[l];
+        out[i] = s;
+    }
+    float m = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits, __float_as_uint(m));
+}
+
+// scale = 2^-ceil(log2 sqrt(max |f|^2)): every scaled element and row norm is <= 1.
+// beta (v units): fp16 rounding of both operands 2^-10 |a'||b'|, hi/lo split of the norm term,
+// tensor-core accumulation (2^-20 of the term magnitudes, generous), rounding of the canonical
+// fp32 expression itself (2^-18); doubled because the maximum and the true argmin both move.
+__global__ void k_params_finish(Params *p)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float mx = fmaxf(__uint_as_float(p->maxn0_bits), __uint_as_float(p->maxn1_bits));
+    float scale = 1.f;
+    if (mx > 0.f) {
+        int e;
+        frexpf(sqrtf(mx) * 1.000001f, &e);  // sqrt(mx) <= 2^e
+        e = e < -60 ? -60 : (e > 60 ? 60 : e);
+        scale = ldexpf(1.f, -e);
+    }
+    const float an = scale * sqrtf(__uint_as_float(p->maxn0_bits)) * 1.000001f;
+    const float bn = scale * sqrtf(__uint_as_float(p->maxn1_bits)) * 1.000001f;
+    const float nm = fmaxf(an, bn);  // either side can play the B role (reverse sweep)
+    const float e_dot = 9.9e-4f * an * bn + 3.5e-7f;
+    const float e_norm = 2.4e-7f * nm * nm + 6e-8f;
+    const float e_acc = 9.6e-7f * (an * bn + 0.5f * nm * nm);
+    const float e_canon = 3.9e-6f * (an * bn + an * an + bn * bn);
+    p->scale = scale;
+    p->beta = 2.f * (e_dot + e_norm + e_acc) + 2.f * e_canon;
+}
+
+// fp32 [N,32] -> fp16 core-matrix image (128 B per row), padded to n_pad rows
+__global__ void k_prep16(const float *__restrict__ F, const float *__restrict__ nsq, int64_t N, int64_t n_pad,
+                         const Params *__restrict__ p, uint4 *__restrict__ out)
+{
+    const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t row = gid >> 3;
+    const int core = (int)(gid & 7);
+    if (row >= n_pad) return;
+    const float s = p->scale;
+    union {
+        __half h[8];
+        uint4 u;
+    } v;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.h[k] = __float2half_rn(0.f);
+    if (core < 4) {
+        if (row < N) {
+            const float4 a = reinterpret_cast<const float4 *>(F + row * 32 + core * 8)[0];
+            const float4 b = reinterpret_cast<const float4 *>(F + row * 32 + core * 8)[1];
+            v.h[0] = __float2half_rn(a.x * s); v.h[1] = __float2half_rn(a.y * s);
+            v.h[2] = __float2half_rn(a.z * s); v.h[3] = __float2half_rn(a.w * s);
+            v.h[4] = __float2half_rn(b.x * s); v.h[5] = __float2half_rn(b.y * s);
+            v.h[6] = __float2half_rn(b.z * s); v.h[7] = __float2half_rn(b.w * s);
+        }
+    } else if (core == 4) {  // A role: picks up the B-role norm term twice (hi + lo)
+        v.h[0] = __float2half_rn(1.f);
+        v.h[1] = __float2half_rn(1.f);
+    } else if (core == 6) {  // B role: c = -s^2 |b|^2 / 2 as hi + lo halves
+        if (row < N) {
+            const float c = -0.5f * (s * s) * nsq[row];
+            const __half hi = __float2half_rn(c);
+            v.h[0] = hi;
+            v.h[1] = __float2half_rn(c - __half2float(hi));
+        } else {
+            v.h[0] = __float2half_rn(-60000.f);  // padding rows can never be a maximum
+        }
+    }
+    out[((row >> 3) * KCORES + core) * 8 + (row & 7)] = v.u;
+}
+
+// ---------------------------------------------------------------- the sweep
+struct __align__(8) Smem {
+    uint64_t a_full[2], a_empty[2], b_full[STAGES], b_empty[STAGES], t_full[2], t_empty[2];
+    uint32_t tmem_base;
+};
+
+template <bool WANT2>
+__device__ __forceinline__ void slow_chunk(const uint32_t (&v)[32], int64_t col0, int64_t M, int64_t row, bool valid,
+                                           float beta, float &m1, float &m2, float &thr, int *__restrict__ cand,
+                                           int *__restrict__ cand_cnt)
+{
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const float x = __uint_as_float(v[r]);
+        if (x > thr) {
+            const int64_t col = col0 + r;
+            if (valid && col < M) {
+                const int pos = atomicAdd(&cand_cnt[row], 1);
+                if (pos < CAND) cand[row * CAND + pos] = (int)col;
+            }
+            if (WANT2) {
+                if (x > m1) {
+                    m2 = m1;
+                    m1 = x;
+                } else if (x > m2) {
+                    m2 = x;
+                }
+                thr = m2 - beta;
+            } else {
+                if (x > m1) m1 = x;
+                thr = m1 - beta;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float max32(const uint32_t (&r)[32])
+{
+    float m[11];
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+        m[k] = fmaxf(fmaxf(__uint_as_float(r[3 * k]), __uint_as_float(r[3 * k + 1])), __uint_as_float(r[3 * k + 2]));
+    m[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+    const float a = fmaxf(fmaxf(m[0], m[1]), m[2]), b = fmaxf(fmaxf(m[3], m[4]), m[5]);
+    const float c = fmaxf(fmaxf(m[6], m[7]), m[8]), d = fmaxf(m[9], m[10]);
+    return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+template <bool WANT2>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N, int64_t M, int n_rowblocks,
+        int n_coltiles, int tiles_per_split, int nsplit, const Params *__restrict__ params, int *__restrict__ cand,
+        int *__restrict__ cand_cnt)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t *sA = smem_raw;                            // 2 x 16 KB
+    uint8_t *sB = smem_raw + 2 * A_TILE_BYTES;         // STAGES x 32 KB
+    Smem *sm = reinterpret_cast<Smem *>(smem_raw + 2 * A_TILE_BYTES + STAGES * B_TILE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nitems = n_rowblocks * nsplit;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int k = 0; k < 2; ++k) {
+                mbar_init(&sm->a_full[k], 1);
+                mbar_init(&sm->a_empty[k], 1);
+                mbar_init(&sm->t_full[k], 1);
+                mbar_init(&sm->t_empty[k], 4);
+            }
+            for (int k = 0; k < STAGES; ++k) {
+                mbar_init(&sm->b_full[k], 1);
+                mbar_init(&sm->b_empty[k], 1);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == 0) {
+        // ===== producer: bulk-TMA copies of operand tiles =====
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int rb = item / nsplit, cs = item - rb * nsplit;
+                const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
+                const int ab = a_it & 1;
+                mbar_wait(&sm->a_empty[ab], ((a_it >> 1) & 1) ^ 1);
+                mbar_expect_tx(&sm->a_full[ab], A_TILE_BYTES);
+                bulk_g2s(sA + ab * A_TILE_BYTES, reinterpret_cast<const uint8_t *>(Aop) + (size_t)rb * A_TILE_BYTES,
+                         A_TILE_BYTES, &sm->a_full[ab]);
+                ++a_it;
+                for (int t = t_lo; t < t_hi; ++t) {
+                    const int s = b_it % STAGES;
+                    mbar_wait(&sm->b_empty[s], ((b_it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&sm->b_full[s], B_TILE_BYTES);
+                    const uint8_t *src = reinterpret_cast<const uint8_t *>(Bop) + (size_t)t * B_TILE_BYTES;
+                    bulk_g2s(sB + s * B_TILE_BYTES, src, B_TILE_BYTES / 2, &sm->b_full[s]);
+                    bulk_g2s(sB + s * B_TILE_BYTES + B_TILE_BYTES / 2, src + B_TILE_BYTES / 2, B_TILE_BYTES / 2,
+                             &sm->b_full[s]);
+                    ++b_it;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread drives the tensor core =====
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0, t_it = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int rb = item / nsplit, cs = item - rb * nsplit;
+                const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
+                (void)rb;
+                const int ab = a_it & 1;
+                mbar_wait(&sm->a_full[ab], (a_it >> 1) & 1);
+                const uint32_t a_addr = smem_u32(sA + ab * A_TILE_BYTES);
+                for (int t = t_lo; t < t_hi; ++t) {
+                    const int s = b_it % STAGES;
+                    const int acc = t_it & 1;
+                    mbar_wait(&sm->b_full[s], (b_it / STAGES) & 1);
+                    mbar_wait(&sm->t_empty[acc], ((t_it >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(sB + s * B_TILE_BYTES);
+                    const uint32_t d = tmem_base + (uint32_t)acc * TN;
+                    // K = 16 per instruction = two 16-byte cores: features 0-15, 16-31, then the extension
+                    tc_mma_f16(d, smem_desc(a_addr), smem_desc(b_addr), IDESC, 0u);
+                    tc_mma_f16(d, smem_desc(a_addr + 2 * 128), smem_desc(b_addr + 2 * 128), IDESC, 1u);
+                    tc_mma_f16(d, smem_desc(a_addr + 4 * 128), smem_desc(b_addr + 6 * 128), IDESC, 1u);
+                    tc_commit(&sm->b_empty[s]);   // smem stage reusable once these MMAs have read it
+                    tc_commit(&sm->t_full[acc]);  // accumulator ready for the epilogue
+                    ++b_it;
+                    ++t_it;
+                }
+                tc_commit(&sm->a_empty[ab]);
+                ++a_it;
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers, running max + candidate collection =====
+        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        const float beta = params->beta;
+        uint32_t t_it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int rb = item / nsplit, cs = item - rb * nsplit;
+            const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
+            const int64_t row = (int64_t)rb * TM + q * 32 + lane;
+            const bool valid = row < N;
+            float m1 = -INFINITY, m2 = -INFINITY, thr = -INFINITY;
+            for (int t = t_lo; t < t_hi; ++t) {
+                const int acc = t_it & 1;
+                mbar_wait(&sm->t_full[acc], (t_it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
+                // software pipeline: the load of the next 32 columns is in flight while this chunk is scanned
+                uint32_t va[32], vb[32];
+                tmem_ld32_issue(taddr, va);
+                tmem_ld32_wait(va);
+#pragma unroll 1
+                for (int c = 0; c < TN / 32; c += 2) {
+                    tmem_ld32_issue(taddr + (c + 1) * 32, vb);
+                    if (max32(va) > thr)
+                        slow_chunk<WANT2>(va, (int64_t)t * TN + c * 32, M, row, valid, beta, m1, m2, thr, cand, cand_cnt);
+                    tmem_ld32_wait(vb);
+                    if (c + 2 < TN / 32) tmem_ld32_issue(taddr + (c + 2) * 32, va);
+                    if (max32(vb) > thr)
+                        slow_chunk<WANT2>(vb, (int64_t)t * TN + (c + 1) * 32, M, row, valid, beta, m1, m2, thr, cand,
+                                          cand_cnt);
+                    if (c + 2 < TN / 32) tmem_ld32_wait(va);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm->t_empty[acc]);
+                ++t_it;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- exact re-rank
+struct Top2 {
+    float s1;
+    int j1;
+    float s2;
+    int j2;
+};
+
+__device__ __forceinline__ void top2_put(Top2 &c, float s, int j)
+{
+    if (s < c.s1 || (s == c.s1 && j < c.j1)) {
+        c.s2 = c.s1;
+        c.j2 = c.j1;
+        c.s1 = s;
+        c.j1 = j;
+    } else if (s < c.s2 || (s == c.s2 && j < c.j2)) {
+        c.s2 = s;
+        c.j2 = j;
+    }
+}
+
+// the reference's fp32 expression (matching.py:29-30), oracle operation order
+__device__ __forceinline__ float canon_dist(const float *__restrict__ a, const float *__restrict__ b, float na, float nb)
+{
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc = fmaf(a[k], b[k], acc);
+    const float d2 = fmaf(-2.f, acc, na + nb);
+    return __fsqrt_rn(fmaxf(d2, 1e-30f));
+}
+
+// one thread per query row: exact distances of its candidates, lexicographic (dist, index) top-2
+__global__ void __launch_bounds__(128)
+k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float *__restrict__ n0,
+         const float *__restrict__ n1, int64_t N, const int *__restrict__ cand, const int *__restrict__ cand_cnt,
+         Params *p, int *__restrict__ ovf_rows, int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    const int cnt = cand_cnt[row];
+    if (cnt > CAND) {  // too many near-ties for the slots: exact scan of the whole row instead
+        ovf_rows[atomicAdd(&p->ovf_count, 1)] = (int)row;
+        return;
+    }
+    float a[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 x = reinterpret_cast<const float4 *>(F0 + row * 32)[k];
+        a[4 * k] = x.x; a[4 * k + 1] = x.y; a[4 * k + 2] = x.z; a[4 * k + 3] = x.w;
+    }
+    const float na = n0[row];
+    Top2 c;
+    c.s1 = INFINITY; c.j1 = 0x7fffffff; c.s2 = INFINITY; c.j2 = 0x7fffffff;
+    for (int k = 0; k < cnt; ++k) {
+        const int j = cand[row * CAND + k];
+        float b[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 x = reinterpret_cast<const float4 *>(F1 + (int64_t)j * 32)[q];
+            b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+        }
+        top2_put(c, canon_dist(a, b, na, n1[j]), j);
+    }
+    idx1[row] = c.j1 == 0x7fffffff ? 0 : c.j1;
+    if (idx2) idx2[row] = c.j2 == 0x7fffffff ? 0 : c.j2;
+}
+
+// exact scan of the overflowed rows: one block per row, canonical arithmetic over every column
+__global__ void __launch_bounds__(256)
+k_row_exact(const float *__restrict__ F0, const float *__restrict__ F1, const float *__restrict__ n0,
+            const float *__restrict__ n1, int64_t M, const Params *__restrict__ p, const int *__restrict__ ovf_rows,
+            int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
+{
+    __shared__ Top2 sh[256];
+    __shared__ float a[32];
+    const int novf = p->ovf_count;
+    for (int o = blockIdx.x; o < novf; o += gridDim.x) {
+        const int64_t row = ovf_rows[o];
+        __syncthreads();
+        if (threadIdx.x < 32) a[threadIdx.x] = F0[row * 32 + threadIdx.x];
+        __syncthreads();
+        const float na = n0[row];
+        Top2 c;
+        c.s1 = INFINITY; c.j1 = 0x7fffffff; c.s2 = INFINITY; c.j2 = 0x7fffffff;
+        for (int64_t j = threadIdx.x; j < M; j += blockDim.x) {
+            float b[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 x = reinterpret_cast<const float4 *>(F1 + j * 32)[q];
+                b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+            }
+            top2_put(c, canon_dist(a, b, na, n1[j]), (int)j);
+        }
+        sh[threadIdx.x] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Top2 m;
+            m.s1 = INFINITY; m.j1 = 0x7fffffff; m.s2 = INFINITY; m.j2 = 0x7fffffff;
+            for (int k = 0; k < 256; ++k) {
+                if (sh[k].j1 != 0x7fffffff) top2_put(m, sh[k].s1, sh[k].j1);
+                if (sh[k].j2 != 0x7fffffff) top2_put(m, sh[k].s2, sh[k].j2);
+            }
+            idx1[row] = m.j1 == 0x7fffffff ? 0 : m.j1;
+            if (idx2) idx2[row] = m.j2 == 0x7fffffff ? 0 : m.j2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int64_t pad_rows(int64_t n) { return (n + TN - 1) / TN * TN; }
+
+size_t scratch_bytes(int64_t N, int64_t M)
+{
+    const int64_t mx = N > M ? N : M;
+    return lr::padded(sizeof(Params)) + lr::padded(pad_rows(N) * 128) + lr::padded(pad_rows(M) * 128) +
+           lr::padded(sizeof(float) * N) + lr::padded(sizeof(float) * M) + lr::padded(sizeof(int) * mx * CAND) +
+           2 * lr::padded(sizeof(int) * mx);
+}
+
+// norms, scale, band and the fp16 operand images of both feature sets (once per match call)
+int prepare(const float *f0, int64_t N, const float *f1, int64_t M, char *scratch, Prepared &P, cudaStream_t st)
+{
+    const int64_t mx = N > M ? N : M;
+    lr::Carver cv(scratch);
+    P.params = cv.take<Params>(1);
+    P.pad0 = pad_rows(N);
+    P.pad1 = pad_rows(M);
+    P.op0 = reinterpret_cast<uint4 *>(cv.take<char>(P.pad0 * 128));
+    P.op1 = reinterpret_cast<uint4 *>(cv.take<char>(P.pad1 * 128));
+    P.n0 = cv.take<float>(N);
+    P.n1 = cv.take<float>(M);
+    P.cand = cv.take<int>(mx * CAND);
+    P.cand_cnt = cv.take<int>(mx);
+    P.ovf_rows = cv.take<int>(mx);
+    k_params_reset<<<1, 32, 0, st>>>(P.params);
+    k_sqnorms_max<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f0, N, P.n0, &P.params->maxn0_bits);
+    k_sqnorms_max<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(f1, M, P.n1, &P.params->maxn1_bits);
+    k_params_finish<<<1, 32, 0, st>>>(P.params);
+    k_prep16<<<(unsigned)((P.pad0 * 8 + 255) / 256), 256, 0, st>>>(f0, P.n0, N, P.pad0, P.params, P.op0);
+    k_prep16<<<(unsigned)((P.pad1 * 8 + 255) / 256), 256, 0, st>>>(f1, P.n1, M, P.pad1, P.params, P.op1);
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+// nearest (and second nearest) neighbour of every row of side `a` among the rows of side `b`
+int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float *f1, int64_t M, int64_t *idx1,
+          int64_t *idx2, cudaStream_t st)
+{
+    const float *fa = swap ? f1 : f0, *fb = swap ? f0 : f1;
+    const float *na = swap ? P.n1 : P.n0, *nb = swap ? P.n0 : P.n1;
+    const uint4 *opa = swap ? P.op1 : P.op0, *opb = swap ? P.op0 : P.op1;
+    const int64_t Na = swap ? M : N, Nb = swap ? N : M;
+    const int n_rowblocks = (int)((Na + TM - 1) / TM);
+    const int n_coltiles = (int)((Nb + TN - 1) / TN);
+    const int sms = lr::sm_count();
+    // split the columns only when there are too few row blocks to fill the chip
+    int nsplit = 1;
+    if (n_rowblocks < 2 * sms) nsplit = (2 * sms + n_rowblocks - 1) / n_rowblocks;
+    if (nsplit > n_coltiles) nsplit = n_coltiles;
+    const int tps = (n_coltiles + nsplit - 1) / nsplit;
+    nsplit = (n_coltiles + tps - 1) / tps;
+    const int nitems = n_rowblocks * nsplit;
+    const int grid = nitems < sms ? nitems : sms;
+    const size_t smem = 2 * A_TILE_BYTES + STAGES * B_TILE_BYTES + sizeof(Smem) + 1024 + 64;
+    LR_CUDA_TRY(cudaMemsetAsync(P.cand_cnt, 0, sizeof(int) * Na, st));
+    LR_CUDA_TRY(cudaMemsetAsync(&P.params->ovf_count, 0, sizeof(int), st));
+    const int tok = lr::prof_begin(lr::PROF_NN, st);
+    if (idx2) {
+        LR_CUDA_TRY(cudaFuncSetAttribute(k_nn_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_nn_tc<true><<<grid, NTHREADS, smem, st>>>(opa, opb, Na, Nb, n_rowblocks, n_coltiles, tps, nsplit, P.params,
+                                                    P.cand, P.cand_cnt);
+    } else {
+        LR_CUDA_TRY(cudaFuncSetAttribute(k_nn_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_nn_tc<false><<<grid, NTHREADS, smem, st>>>(opa, opb, Na, Nb, n_rowblocks, n_coltiles, tps, nsplit, P.params,
+                                                     P.cand, P.cand_cnt);
+    }
+    lr::prof_end(tok, st);
+    k_rerank<<<(unsigned)((Na + 127) / 128), 128, 0, st>>>(fa, fb, na, nb, Na, P.cand, P.cand_cnt, P.params, P.ovf_rows,
+                                                           idx1, idx2);
+    k_row_exact<<<sms * 2, 256, 0, st>>>(fa, fb, na, nb, Nb, P.params, P.ovf_rows, idx1, idx2);
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+}  // namespace lr_tc

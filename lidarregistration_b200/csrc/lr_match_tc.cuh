@@ -1,0 +1,22 @@
+// lr_match_tc.cuh -- interface of the tensor-core matching sweep (lr_match_tc.cu)
+#pragma once
+#include "lr_common.cuh"
+
+namespace lr_tc {
+
+struct Params;
+struct Prepared {
+    uint4 *op0, *op1;   // fp16 operand images of f0 / f1
+    float *n0, *n1;     // canonical squared norms
+    Params *params;
+    int *cand, *cand_cnt, *ovf_rows;
+    int64_t pad0, pad1;
+};
+
+size_t scratch_bytes(int64_t N, int64_t M);
+int prepare(const float *f0, int64_t N, const float *f1, int64_t M, char *scratch, Prepared &P, cudaStream_t st);
+// swap = false: neighbours of f0's rows in f1; swap = true: neighbours of f1's rows in f0
+int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float *f1, int64_t M, int64_t *idx1,
+          int64_t *idx2, cudaStream_t st);
+
+}  // namespace lr_tc

@@ -8,17 +8,16 @@
 //                                        GC-RANSAC/src/pygcransac/include/preemption/preemption_edge_length.h:71-128
 //   inlier refit                         Experiments/algorithms/FR.py:99-111
 //
-// Structure of one round of R hypotheses (DESIGN.md "RANSAC kernels"):
-//   k_gen    one thread per hypothesis id: counter-based sample, ELC in fp64,
-//            fixed-sweep Jacobi Kabsch in fp64 registers; survivors are
-//            compacted (warp-aggregated) with an fp32 copy of [R|t] and the
-//            rigorous fp32 error band of the inlier test
-//   k_score  thread-owns-hypothesis sweep over all correspondences staged
-//            through shared memory with cp.async (float4 + float2 per point,
-//            broadcast reads); two counters bracket the exact count
-//   k_recount  the few hypotheses whose bracket is open are recounted in the
-//            canonical fp64 arithmetic, one warp each
-//   k_round_end  packed (count, id) arg-max merge, confidence exit flag
+// Structure of one batch of hypotheses (DESIGN.md "RANSAC kernels"):
+//   k_gen    one thread per hypothesis id: counter-based sample, edge-length
+//            test in fp64; survivors are compacted (warp-aggregated)
+//   k_kabsch dense over survivors: fixed-sweep Jacobi Kabsch in fp64 registers,
+//            fp32 copy of [R|t] + the rigorous fp32 error band of the inlier test
+//   k_score  thread-owns-two-hypotheses sweep (packed f32x2 FMAs) over all
+//            correspondences staged through shared memory with cp.async;
+//            residuals inside the error band are decided in fp64 on the spot,
+//            so every count is exact
+//   k_resolve / k_round_end  packed (count, id) arg-max, confidence exit flag
 // fp64 arithmetic follows oracle/lr_oracle.c operation for operation (this
 // file is compiled with -fmad=false; FMAs are written explicitly where wanted).
 #include <math.h>
@@ -29,8 +28,10 @@
 
 namespace {
 
-constexpr int kScoreThreads = 128;  // hypotheses per score item (one per thread)
-constexpr int kChunk = 1024;        // correspondences per shared-memory stage
+constexpr int kScoreThreads = 128;  // threads per score CTA; each thread owns TWO hypotheses (packed f32x2)
+constexpr int kHypPerItem = 2 * kScoreThreads;
+constexpr int kChunk = 512;         // correspondences per shared-memory stage (48 B each, double buffered)
+constexpr int kGroup = 4;           // points between two checks of the "some residual is in the band" flag
 constexpr int kGenThreads = 128;
 
 struct Ctl {
@@ -50,13 +51,12 @@ struct Ctl {
 
 struct Ws {
     Ctl *ctl;
-    float4 *P4;       // (px, py, pz, qx)
-    float2 *Q2;       // (qy, qz)
+    float4 *P12;      // 3 x float4 per point: (px,px,py,py) (pz,pz,-qx,-qx) (-qy,-qy,-qz,-qz)
+    int32_t *samp;    // sample indices of the survivors, 4 per slot
     uint32_t *slot_id;
-    float4 *m32;      // 4 x float4 per slot: R rows + t, then (lo, hi, -, -)
+    float4 *m32;      // fp32 [R|t], lo, hi of two slots interleaved: see m32_index()
     double *m64;      // 12 per slot
-    int *flagged;
-    int2 *cnt;        // per slot: (#r2 < lo, #r2 < hi) accumulated over point splits
+    int *cnt;         // per slot: exact inlier count, accumulated over point splits
     int *need;        // per round: inlier count that triggers the confidence exit
     double *scratchT; // 16 doubles of staging
     int64_t n_pad;
@@ -308,35 +308,32 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // kernels
 // ------------------------------------------------------------------------
 
-// AoS [n,3] x2  ->  (px,py,pz,qx) + (qy,qz), padded to a multiple of kChunk with
-// far-away points that can never be inliers; also the coordinate bounds that
-// enter the fp32 error band.
+// AoS [n,3] x2  ->  3 x float4 per correspondence with every value duplicated,
+// so one LDS.128 yields two ready-made f32x2 operands (the target is stored
+// negated: the sweep then only adds).  Padded to a multiple of kChunk with
+// far-away points that can never be inliers.  Also the coordinate bound that
+// enters the fp32 error band.
 __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, int64_t n_pad,
-                       float4 *__restrict__ P4, float2 *__restrict__ Q2, Ctl *ctl)
+                       float4 *__restrict__ P12, Ctl *ctl)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    float p1 = 0.f, qm = 0.f;
+    float p1 = 0.f;
     if (i < n) {
         float px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
         float qx = tgt[3 * i], qy = tgt[3 * i + 1], qz = tgt[3 * i + 2];
-        P4[i] = make_float4(px, py, pz, qx);
-        Q2[i] = make_float2(qy, qz);
+        P12[3 * i + 0] = make_float4(px, px, py, py);
+        P12[3 * i + 1] = make_float4(pz, pz, -qx, -qx);
+        P12[3 * i + 2] = make_float4(-qy, -qy, -qz, -qz);
         p1 = fabsf(px) + fabsf(py) + fabsf(pz);
-        qm = fmaxf(fabsf(qx), fmaxf(fabsf(qy), fabsf(qz)));
     } else if (i < n_pad) {
-        P4[i] = make_float4(0.f, 0.f, 0.f, 1e18f);
-        Q2[i] = make_float2(1e18f, 1e18f);
+        P12[3 * i + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        P12[3 * i + 1] = make_float4(0.f, 0.f, -1e18f, -1e18f);
+        P12[3 * i + 2] = make_float4(-1e18f, -1e18f, -1e18f, -1e18f);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        p1 = fmaxf(p1, __shfl_xor_sync(0xffffffffu, p1, o));
-        qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        // round p1 up a little: the fp32 sum above is itself rounded
-        atomicMax(&ctl->p1max_bits, __float_as_uint(p1 * 1.000001f));
-        atomicMax(&ctl->qmax_bits, __float_as_uint(qm));
-    }
+    for (int o = 16; o > 0; o >>= 1) p1 = fmaxf(p1, __shfl_xor_sync(0xffffffffu, p1, o));
+    // round up a little: the fp32 sum above is itself rounded
+    if ((threadIdx.x & 31) == 0) atomicMax(&ctl->p1max_bits, __float_as_uint(p1 * 1.000001f));
 }
 
 __global__ void k_ctl_reset(Ctl *ctl)
@@ -356,38 +353,71 @@ __global__ void k_ctl_reset(Ctl *ctl)
     }
 }
 
-// one thread per hypothesis: sample -> ELC -> Kabsch -> compacted slot
+// fp32 models are stored so that the sweep can load ready-made f32x2 operands:
+// slots s and s + 128 of the same 256-slot block share 16 float2
+// {r00 r01 r02 t0 | r10 r11 r12 t1 | r20 r21 r22 t2 | lo hi - -}, value v of slot s
+// sits at float index ((s / 256 * 128 + s % 128) * 16 + v) * 2 + (s % 256) / 128.
+__device__ __forceinline__ size_t m32_index(int slot, int v)
+{
+    const int blk = slot / kHypPerItem, r = slot % kHypPerItem;
+    return ((size_t)(blk * kScoreThreads + (r % kScoreThreads)) * 16 + v) * 2 + (r / kScoreThreads);
+}
+
+// edge-length test on squared lengths; falls back to the reference's
+// sqrt form (preemption_edge_length.h:116-123) only when a comparison is within
+// 1e-14 (relative) of equality, so the decision is always the reference's.
+template <int M>
+__device__ __forceinline__ bool elc_pass_fast(const double (&P)[M][3], const double (&Q)[M][3], double ratio)
+{
+    const double c2 = ratio * ratio;
+    const double c_lo = c2 * (1.0 - 1e-14), c_hi = c2 * (1.0 + 1e-14);
+    bool ok = true, unsure = false;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = i + 1; j < M; ++j) {
+            double ax = P[j][0] - P[i][0], ay = P[j][1] - P[i][1], az = P[j][2] - P[i][2];
+            double bx = Q[j][0] - Q[i][0], by = Q[j][1] - Q[i][1], bz = Q[j][2] - Q[i][2];
+            double S = (ax * ax + ay * ay) + az * az;
+            double T = (bx * bx + by * by) + bz * bz;
+            if (S < c_lo * T || T < c_lo * S) ok = false;               // certainly rejected
+            else if (!(S > c_hi * T && T > c_hi * S)) unsure = true;    // too close to call on squares
+        }
+    if (ok && unsure) ok = elc_pass<M>(P, Q, ratio);
+    return ok;
+}
+
+// one thread per hypothesis id: counter-based sample -> ELC; survivors are
+// compacted (warp-aggregated) as (id, sample indices)
 template <int M>
 __global__ void __launch_bounds__(kGenThreads)
 k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, uint64_t seed, int sampler,
-      int use_elc, double elc_ratio, double thr2, int64_t id_lo, int64_t id_hi,
-      const int32_t *__restrict__ fed, Ctl *ctl, uint32_t *__restrict__ slot_id, float4 *__restrict__ m32,
-      double *__restrict__ m64, int2 *__restrict__ cnt)
+      int use_elc, double elc_ratio, int64_t id_lo, int64_t id_hi, const int32_t *__restrict__ fed, Ctl *ctl,
+      uint32_t *__restrict__ slot_id, int32_t *__restrict__ samp)
 {
     if (ctl->done) return;
     int64_t id = id_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool ok = id < id_hi;
-    double T[12];
+    int32_t s[M];
     if (ok) {
-        int32_t s[M];
         if (fed) {
 #pragma unroll
             for (int d = 0; d < M; ++d) s[d] = fed[(id - id_lo) * M + d];
         } else {
             sample_ids<M>(seed, (uint64_t)id, sampler, n, s);
         }
-        double P[M][3], Q[M][3];
+        if (use_elc) {
+            double P[M][3], Q[M][3];
 #pragma unroll
-        for (int d = 0; d < M; ++d)
+            for (int d = 0; d < M; ++d)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                P[d][c] = (double)src[3 * (int64_t)s[d] + c];
-                Q[d][c] = (double)tgt[3 * (int64_t)s[d] + c];
-            }
-        if (use_elc) ok = elc_pass<M>(P, Q, elc_ratio);
-        if (ok) kabsch_small<M>(P, Q, T);
+                for (int c = 0; c < 3; ++c) {
+                    P[d][c] = (double)src[3 * (int64_t)s[d] + c];
+                    Q[d][c] = (double)tgt[3 * (int64_t)s[d] + c];
+                }
+            ok = elc_pass_fast<M>(P, Q, elc_ratio);
+        }
     }
-    // warp-aggregated compaction
     unsigned ballot = __ballot_sync(0xffffffffu, ok);
     int lane = threadIdx.x & 31;
     int base = 0;
@@ -396,21 +426,59 @@ k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, u
     if (!ok) return;
     int slot = base + __popc(ballot & ((1u << lane) - 1u));
     slot_id[slot] = (uint32_t)id;
-    cnt[slot] = make_int2(0, 0);
 #pragma unroll
-    for (int k = 0; k < 12; ++k) m64[(size_t)slot * 12 + k] = T[k];
-    // fp32 copy + error band of the inlier test (DESIGN.md "fp32 bracket")
-    const double u = 5.9604644775390625e-08;  // 2^-24
-    double tinf = fmax(fabs(T[3]), fmax(fabs(T[7]), fabs(T[11])));
-    double E = 8.0 * u * ((double)__uint_as_float(ctl->p1max_bits) + (double)__uint_as_float(ctl->qmax_bits) + tinf);
-    double thr = sqrt(thr2);
-    double delta = 4.0 * E * thr + 4.0 * E * E + 8.0 * u * thr2 + 1e-9;
-    float lo = __double2float_rd(thr2 - delta);
-    float hi = __double2float_ru(thr2 + delta);
-    m32[(size_t)slot * 4 + 0] = make_float4((float)T[0], (float)T[1], (float)T[2], (float)T[3]);
-    m32[(size_t)slot * 4 + 1] = make_float4((float)T[4], (float)T[5], (float)T[6], (float)T[7]);
-    m32[(size_t)slot * 4 + 2] = make_float4((float)T[8], (float)T[9], (float)T[10], (float)T[11]);
-    m32[(size_t)slot * 4 + 3] = make_float4(lo, hi, 0.f, 0.f);
+    for (int d = 0; d < M; ++d) samp[(size_t)slot * 4 + d] = s[d];
+}
+
+// dense over the survivors: fp64 Kabsch in registers, fp32 copy of [R|t] and the
+// rigorous fp32 error band of the inlier test (DESIGN.md "fp32 bracket")
+template <int M>
+__global__ void __launch_bounds__(kGenThreads)
+k_kabsch(const float *__restrict__ src, const float *__restrict__ tgt, double thr2, Ctl *ctl,
+         const int32_t *__restrict__ samp, float4 *__restrict__ m32, double *__restrict__ m64,
+         int *__restrict__ cnt)
+{
+    if (ctl->done) return;
+    const int nsurv = ctl->n_surv;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
+        double P[M][3], Q[M][3], T[12];
+#pragma unroll
+        for (int d = 0; d < M; ++d) {
+            const int64_t k = samp[(size_t)slot * 4 + d];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                P[d][c] = (double)src[3 * k + c];
+                Q[d][c] = (double)tgt[3 * k + c];
+            }
+        }
+        kabsch_small<M>(P, Q, T);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) m64[(size_t)slot * 12 + k] = T[k];
+        cnt[slot] = 0;
+        // |fp32 residual component - canonical fp64 one| <= E for every correspondence:
+        // rounding of R (u |p|_1), of t (u |t|), three FMAs (3u (|p|_1 + |t|)); the final
+        // add is exact to u |d| which is O(thr) near the threshold.  6u leaves slack.
+        const double u = 5.9604644775390625e-08;  // 2^-24
+        double tinf = fmax(fabs(T[3]), fmax(fabs(T[7]), fabs(T[11])));
+        double E = 6.0 * u * ((double)__uint_as_float(ctl->p1max_bits) + tinf + 1.0);
+        double thr = sqrt(thr2);
+        double delta = 4.0 * E * thr + 4.0 * E * E + 8.0 * u * thr2 + 1e-9;
+        float lo = __double2float_rd(thr2 - delta);
+        float hi = __double2float_ru(thr2 + delta);
+        float *mf = reinterpret_cast<float *>(m32);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) mf[m32_index(slot, k)] = (float)T[k];
+        mf[m32_index(slot, 12)] = lo;
+        mf[m32_index(slot, 13)] = hi;
+        // the partner slot of the last, half-filled block must never count anything
+        const int partner = (slot % kHypPerItem) < kScoreThreads ? slot + kScoreThreads : -1;
+        if (partner >= nsurv) {
+            mf[m32_index(partner, 12)] = -1.f;
+            mf[m32_index(partner, 13)] = -1.f;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) mf[m32_index(partner, k)] = 0.f;
+        }
+    }
 }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -425,55 +493,128 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// Inlier sweep.  Each thread owns one surviving hypothesis ([R|t] in fp32
-// registers) and walks correspondences staged through shared memory in
-// double-buffered chunks with cp.async, read as warp-wide broadcasts
-// (LDS.128 + LDS.64 per point per warp).  Per pair: 12 FFMA/FADD for
-// R p + t - q, 3 for |.|^2, two compare+add for the bracket.
-// Work item = (block of 128 survivors) x (range of point chunks); the split
-// over points is chosen on the device from the survivor count so that a round
-// with few survivors (ELC rejects ~97 % at 70 % outliers) still fills the chip.
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float a, float b)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// cl += (r < lo); ch += (r < hi)  as two FSETP + two predicated IADD
+__device__ __forceinline__ void count2(float r, float lo, float hi, int &cl, int &ch)
+{
+    asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f32 p, %2, %3;\n\tsetp.lt.f32 q, %2, %4;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t@q add.s32 %1, %1, 1;\n\t}"
+        : "+r"(cl), "+r"(ch)
+        : "f"(r), "f"(lo), "f"(hi));
+}
+
+// Rare path of the sweep: some residual of this group of kGroup points fell
+// inside the fp32 error band of hypothesis `slot`.  Recompute the group's fp32
+// residuals (same operations, same order => same bits), and decide the in-band
+// ones with the canonical fp64 arithmetic of the oracle.
+__device__ __noinline__ int recheck_group(const float4 *grp, const float4 *__restrict__ m32, int slot,
+                                          const double *__restrict__ m64s, double thr2, unsigned long long *n_rechecked)
+{
+    const float *mf = reinterpret_cast<const float *>(m32);
+    float v[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) v[k] = mf[m32_index(slot, k)];
+    const float4 r0 = make_float4(v[0], v[1], v[2], v[3]), r1 = make_float4(v[4], v[5], v[6], v[7]);
+    const float4 r2 = make_float4(v[8], v[9], v[10], v[11]), bw = make_float4(v[12], v[13], 0.f, 0.f);
+    int add = 0, evals = 0;
+    for (int g = 0; g < kGroup; ++g) {
+        const float4 A = grp[3 * g + 0], B = grp[3 * g + 1], C = grp[3 * g + 2];
+        const float px = A.x, py = A.z, pz = B.x;
+        float d0 = fmaf(r0.x, px, fmaf(r0.y, py, fmaf(r0.z, pz, r0.w))) + B.z;
+        float d1 = fmaf(r1.x, px, fmaf(r1.y, py, fmaf(r1.z, pz, r1.w))) + C.x;
+        float d2 = fmaf(r2.x, px, fmaf(r2.y, py, fmaf(r2.z, pz, r2.w))) + C.z;
+        float rr = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+        if (rr >= bw.x && rr < bw.y) {
+            double T[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) T[k] = m64s[k];
+            add += res2_f64(T, (double)px, (double)py, (double)pz, -(double)B.z, -(double)C.x, -(double)C.z) < thr2 ? 1 : 0;
+            ++evals;
+        }
+    }
+    if (evals) atomicAdd(n_rechecked, (unsigned long long)evals);
+    return add;
+}
+
+// Inlier sweep -- the dominant kernel.  Each thread owns TWO surviving
+// hypotheses whose [R|t] live in registers as packed f32x2 pairs; every
+// correspondence is read from shared memory as three warp-wide broadcast
+// LDS.128 whose halves are ready-made (v, v) operands, so R p + t - q and
+// |.|^2 cost 15 packed FFMA2/FADD2/FMUL2 for two residuals (7.5 issue slots per
+// residual instead of 15).  Correspondences are staged with cp.async in
+// double-buffered chunks.  Counting is exact: residuals below `lo` are inliers,
+// above `hi` outliers, and the rare ones in between are decided in fp64 by
+// recheck_group().  Work item = (256 survivors) x (range of point chunks); the
+// split over points is chosen on the device from the survivor count so that a
+// round with few survivors (ELC rejects ~97 % at 70 % outliers) fills the chip.
 __global__ void __launch_bounds__(kScoreThreads)
-k_score(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n_pad, Ctl *ctl,
-        const float4 *__restrict__ m32, int2 *__restrict__ cnt)
+k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *__restrict__ m32,
+        const double *__restrict__ m64, int *__restrict__ cnt, double thr2)
 {
     if (ctl->done) return;
-    __shared__ __align__(16) float4 sP[2][kChunk];
-    __shared__ __align__(16) float2 sQ[2][kChunk];
+    __shared__ __align__(16) float4 sP[2][3 * kChunk];
     const int tid = threadIdx.x;
     const int nsurv = ctl->n_surv;
-    const int nhb = (nsurv + kScoreThreads - 1) / kScoreThreads;
+    const int nhb = (nsurv + kHypPerItem - 1) / kHypPerItem;
     if (nhb == 0) return;
     const int nchunks = (int)(n_pad / kChunk);
-    int nps = (2 * (int)gridDim.x + nhb - 1) / nhb;
+    int nps = (8 * (int)gridDim.x + nhb - 1) / nhb;
     nps = nps < 1 ? 1 : (nps > nchunks ? nchunks : nps);
     const int cpp = (nchunks + nps - 1) / nps;  // chunks per point split
     nps = (nchunks + cpp - 1) / cpp;
     const int nitems = nhb * nps;
+    unsigned long long *n_rechecked = reinterpret_cast<unsigned long long *>(&ctl->n_rechecked);
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int hb = item / nps, ps = item - hb * nps;
         const int c_lo = ps * cpp, c_hi = min(nchunks, c_lo + cpp);
-        const int slot = hb * kScoreThreads + tid;
-        const bool valid = slot < nsurv;
-        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0, r2 = r0, bw = make_float4(-1.f, -1.f, 0, 0);
-        if (valid) {
-            r0 = m32[(size_t)slot * 4 + 0];
-            r1 = m32[(size_t)slot * 4 + 1];
-            r2 = m32[(size_t)slot * 4 + 2];
-            bw = m32[(size_t)slot * 4 + 3];
-        }
-        const float lo = bw.x, hi = bw.y;
-        int cnt_lo = 0, cnt_hi = 0;
+        const int slotA = hb * kHypPerItem + tid, slotB = slotA + kScoreThreads;
+        const bool vA = slotA < nsurv, vB = slotB < nsurv;
+        // 16 float2 (slot A, slot B) = 8 x 16-byte loads, already paired for f32x2 math
+        const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(m32) + ((size_t)hb * kScoreThreads + tid) * 8;
+        const ulonglong2 q0 = mp[0], q1 = mp[1], q2 = mp[2], q3 = mp[3], q4 = mp[4], q5 = mp[5], q6 = mp[6];
+        const u64 R00 = q0.x, R01 = q0.y, R02 = q1.x, T0 = q1.y;
+        const u64 R10 = q2.x, R11 = q2.y, R12 = q3.x, T1 = q3.y;
+        const u64 R20 = q4.x, R21 = q4.y, R22 = q5.x, T2 = q5.y;
+        float loA, loB, hiA, hiB;
+        upk2(q6.x, loA, loB);
+        upk2(q6.y, hiA, hiB);
+        // running #(rr < lo), #(rr < hi) per hypothesis; their difference grows only when a residual
+        // lands inside the error band, which sends the group to the fp64 recheck
+        int loCntA = 0, hiCntA = 0, loCntB = 0, hiCntB = 0, seenA = 0, seenB = 0, exactA = 0, exactB = 0;
 
         auto stage = [&](int c, int buf) {
-            const float4 *gp = P4 + (size_t)c * kChunk;
-            const float4 *gq = reinterpret_cast<const float4 *>(Q2 + (size_t)c * kChunk);
-            float4 *sq = reinterpret_cast<float4 *>(&sQ[buf][0]);
+            const float4 *gp = P12 + (size_t)c * 3 * kChunk;
 #pragma unroll
-            for (int k = 0; k < kChunk / kScoreThreads; ++k) cp_async16(&sP[buf][tid + k * kScoreThreads], gp + tid + k * kScoreThreads);
-#pragma unroll
-            for (int k = 0; k < kChunk / 2 / kScoreThreads; ++k) cp_async16(sq + tid + k * kScoreThreads, gq + tid + k * kScoreThreads);
+            for (int k = 0; k < 3 * kChunk / kScoreThreads; ++k)
+                cp_async16(&sP[buf][tid + k * kScoreThreads], gp + tid + k * kScoreThreads);
             cp_async_commit();
         };
 
@@ -487,84 +628,60 @@ k_score(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n_
                 cp_async_wait<0>();
             }
             __syncthreads();
-#pragma unroll 8
-            for (int i = 0; i < kChunk; ++i) {
-                const float4 a = sP[buf][i];
-                const float2 b = sQ[buf][i];
-                float d0 = fmaf(r0.x, a.x, fmaf(r0.y, a.y, fmaf(r0.z, a.z, r0.w))) - a.w;
-                float d1 = fmaf(r1.x, a.x, fmaf(r1.y, a.y, fmaf(r1.z, a.z, r1.w))) - b.x;
-                float d2 = fmaf(r2.x, a.x, fmaf(r2.y, a.y, fmaf(r2.z, a.z, r2.w))) - b.y;
-                float rr = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
-                cnt_lo += (rr < lo) ? 1 : 0;
-                cnt_hi += (rr < hi) ? 1 : 0;
+            const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&sP[buf][0]);
+#pragma unroll 2
+            for (int i = 0; i < kChunk; i += kGroup) {
+#pragma unroll
+                for (int g = 0; g < kGroup; ++g) {
+                    const ulonglong2 A = sp[3 * (i + g) + 0], B = sp[3 * (i + g) + 1], C = sp[3 * (i + g) + 2];
+                    u64 d0 = add2(fma2(R00, A.x, fma2(R01, A.y, fma2(R02, B.x, T0))), B.y);
+                    u64 d1 = add2(fma2(R10, A.x, fma2(R11, A.y, fma2(R12, B.x, T1))), C.x);
+                    u64 d2 = add2(fma2(R20, A.x, fma2(R21, A.y, fma2(R22, B.x, T2))), C.y);
+                    u64 rr = fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
+                    float ra, rb;
+                    upk2(rr, ra, rb);
+                    count2(ra, loA, hiA, loCntA, hiCntA);
+                    count2(rb, loB, hiB, loCntB, hiCntB);
+                }
+                if (hiCntA - loCntA != seenA) {
+                    seenA = hiCntA - loCntA;
+                    exactA += recheck_group(&sP[buf][3 * i], m32, slotA, m64 + (size_t)slotA * 12, thr2, n_rechecked);
+                }
+                if (hiCntB - loCntB != seenB) {
+                    seenB = hiCntB - loCntB;
+                    exactB += recheck_group(&sP[buf][3 * i], m32, slotB, m64 + (size_t)slotB * 12, thr2, n_rechecked);
+                }
             }
             __syncthreads();
         }
-        if (valid) {
-            if (nps == 1) {
-                cnt[slot] = make_int2(cnt_lo, cnt_hi);
-            } else {
-                if (cnt_lo) atomicAdd(&cnt[slot].x, cnt_lo);
-                if (cnt_hi) atomicAdd(&cnt[slot].y, cnt_hi);
-            }
+        const int cntA = loCntA + exactA, cntB = loCntB + exactB;
+        if (nps == 1) {
+            if (vA) cnt[slotA] = cntA;
+            if (vB) cnt[slotB] = cntB;
+        } else {
+            if (vA && cntA) atomicAdd(&cnt[slotA], cntA);
+            if (vB && cntB) atomicAdd(&cnt[slotB], cntB);
         }
     }
 }
 
-// closes the bracket: exact slots feed the packed arg-max, open ones are queued
-// for the fp64 recount
+// exact counts -> packed arg-max
 __global__ void __launch_bounds__(256)
-k_resolve(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int2 *__restrict__ cnt, int *__restrict__ flagged,
+k_resolve(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restrict__ cnt,
           int32_t *__restrict__ counts_out, int64_t id_base)
 {
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
     unsigned long long key = 0ULL;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
-        const int2 c = cnt[slot];
-        if (c.x == c.y) {
-            const uint32_t id = slot_id[slot];
-            const unsigned long long k = make_key(c.x, id);
-            key = k > key ? k : key;
-            if (counts_out) counts_out[(int64_t)id - id_base] = c.x;
-        } else {
-            flagged[atomicAdd(&ctl->n_flag, 1)] = slot;
-        }
+        const int c = cnt[slot];
+        const uint32_t id = slot_id[slot];
+        const unsigned long long k = make_key(c, id);
+        key = k > key ? k : key;
+        if (counts_out) counts_out[(int64_t)id - id_base] = c;
     }
     key = warp_max_u64(key);
     if ((threadIdx.x & 31) == 0 && key) atomicMax(&ctl->round_key, key);
-}
-
-// exact fp64 recount of the hypotheses whose fp32 bracket stayed open
-__global__ void __launch_bounds__(256)
-k_recount(const float4 *__restrict__ P4, const float2 *__restrict__ Q2, int64_t n, Ctl *ctl,
-          const uint32_t *__restrict__ slot_id, const double *__restrict__ m64, const int *__restrict__ flagged,
-          double thr2, int32_t *__restrict__ counts_out, int64_t id_base)
-{
-    if (ctl->done) return;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int nflag = ctl->n_flag;
-    for (int f = warp; f < nflag; f += nwarps) {
-        const int slot = flagged[f];
-        double T[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) T[k] = m64[(size_t)slot * 12 + k];
-        int cnt = 0;
-        for (int64_t i = lane; i < n; i += 32) {
-            const float4 a = P4[i];
-            const float2 b = Q2[i];
-            cnt += res2_f64(T, a.x, a.y, a.z, a.w, b.x, b.y) < thr2 ? 1 : 0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) {
-            const uint32_t id = slot_id[slot];
-            atomicMax(&ctl->round_key, make_key(cnt, id));
-            if (counts_out) counts_out[(int64_t)id - id_base] = cnt;
-        }
-    }
 }
 
 __global__ void k_round_end(Ctl *ctl, int64_t round_len, const int *__restrict__ need, int round_idx,
@@ -576,7 +693,6 @@ __global__ void k_round_end(Ctl *ctl, int64_t round_len, const int *__restrict__
     if (user_key && ctl->round_key > *user_key) *user_key = ctl->round_key;
     ctl->iters_run += round_len;
     ctl->n_scored += ctl->n_surv;
-    ctl->n_rechecked += ctl->n_flag;
     ctl->round_key = 0ULL;
     ctl->n_surv = 0;
     ctl->n_flag = 0;
@@ -776,22 +892,21 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
 {
     ws.n_pad = ((n + kChunk - 1) / kChunk) * kChunk;
     if (ws.n_pad == 0) ws.n_pad = kChunk;
-    size_t bytes = lr::padded(sizeof(Ctl)) + lr::padded(sizeof(float4) * ws.n_pad) + lr::padded(sizeof(float2) * ws.n_pad) +
-                   lr::padded(sizeof(uint32_t) * round) + lr::padded(sizeof(float4) * 4 * round) +
+    size_t bytes = lr::padded(sizeof(Ctl)) + lr::padded(sizeof(float4) * 3 * ws.n_pad) +
+                   lr::padded(sizeof(int32_t) * 4 * round) +
+                   lr::padded(sizeof(uint32_t) * round) + lr::padded(sizeof(float4) * 4 * (round + kHypPerItem)) +
                    lr::padded(sizeof(double) * 12 * round) + lr::padded(sizeof(int) * round) +
-                   lr::padded(sizeof(int2) * round) +
                    lr::padded(sizeof(int) * (nrounds + 1)) + lr::padded(sizeof(double) * 16);
     void *base = lr::arena_get(lr::SLOT_RANSAC, bytes);
     if (!base) return LR_ERR_ALLOC;
     lr::Carver cv(base);
     ws.ctl = cv.take<Ctl>(1);
-    ws.P4 = cv.take<float4>(ws.n_pad);
-    ws.Q2 = cv.take<float2>(ws.n_pad);
+    ws.P12 = cv.take<float4>(3 * ws.n_pad);
+    ws.samp = cv.take<int32_t>(4 * round);
     ws.slot_id = cv.take<uint32_t>(round);
-    ws.m32 = cv.take<float4>(4 * round);
+    ws.m32 = cv.take<float4>(4 * (round + kHypPerItem));
     ws.m64 = cv.take<double>(12 * round);
-    ws.flagged = cv.take<int>(round);
-    ws.cnt = cv.take<int2>(round);
+    ws.cnt = cv.take<int>(round);
     ws.need = cv.take<int>(nrounds + 1);
     ws.scratchT = cv.take<double>(16);
     return LR_OK;
@@ -820,7 +935,7 @@ int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cud
 {
     k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
     int blocks = (int)((ws.n_pad + 255) / 256);
-    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P4, ws.Q2, ws.ctl);
+    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.ctl);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -832,28 +947,27 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     const int64_t len = hi - lo;
     if (len <= 0) return LR_OK;
     const double thr2 = p.threshold * p.threshold;
+    const int sms = lr::sm_count();
     int gblocks = (int)((len + kGenThreads - 1) / kGenThreads);
+    int kblocks = gblocks < sms * 8 ? gblocks : sms * 8;
     int tok = lr::prof_begin(lr::PROF_GEN, st);
-    if (p.sample_size == 3)
-        k_gen<3><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, thr2, lo, hi,
-                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64, ws.cnt);
-    else
-        k_gen<4><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, thr2, lo, hi,
-                                                  fed, ws.ctl, ws.slot_id, ws.m32, ws.m64, ws.cnt);
+    if (p.sample_size == 3) {
+        k_gen<3><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
+                                                  ws.ctl, ws.slot_id, ws.samp);
+        k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
+    } else {
+        k_gen<4><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
+                                                  ws.ctl, ws.slot_id, ws.samp);
+        k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
+    }
     lr::prof_end(tok, st);
-    int items = (int)((len + kScoreThreads - 1) / kScoreThreads);
-    int sblocks = lr::sm_count() * 4;  // 4 resident CTAs of 128 threads per SM (48 KB smem each)
-    (void)items;
     tok = lr::prof_begin(lr::PROF_SCORE, st);
-    k_score<<<sblocks, kScoreThreads, 0, st>>>(ws.P4, ws.Q2, ws.n_pad, ws.ctl, ws.m32, ws.cnt);
+    // 4 resident CTAs of 128 threads per SM (48 KB of staging each)
+    k_score<<<sms * 4, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
     lr::prof_end(tok, st);
     int rblocks = (int)((len + 255) / 256);
-    if (rblocks > lr::sm_count() * 4) rblocks = lr::sm_count() * 4;
-    k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, ws.flagged, counts_out, lo);
-    tok = lr::prof_begin(lr::PROF_RECOUNT, st);
-    k_recount<<<lr::sm_count() * 2, 256, 0, st>>>(ws.P4, ws.Q2, n, ws.ctl, ws.slot_id, ws.m64, ws.flagged, thr2,
-                                                  counts_out, lo);
-    lr::prof_end(tok, st);
+    if (rblocks > sms * 4) rblocks = sms * 4;
+    k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, counts_out, lo);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }

@@ -224,3 +224,8 @@ def peak_fp32(mode=0):
     v = ctypes.c_double(0.0)
     _lib.check(_lib.lib().lr_peak_fp32(int(mode), ctypes.byref(v)), "lr_peak_fp32")
     return float(v.value)
+
+
+def match_set_mode(mode):
+    """0 = tensor-core sweep + exact re-rank (D == 32, default); 1 = exact CUDA-core sweep."""
+    _lib.check(_lib.lib().lr_match_set_mode(int(mode)), "lr_match_set_mode")

@@ -86,3 +86,40 @@ def test_gather_and_errors():
     assert torch.equal(out, xyz[idx])
     with pytest.raises(RuntimeError):
         engine.match_nn(torch.zeros(4, 20), torch.zeros(4, 20))  # unsupported D
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_both_sweep_implementations_agree_with_oracle(mode):
+    """mode 0 = tcgen05 sweep + exact re-rank, mode 1 = exact CUDA-core sweep: identical indices."""
+    engine.match_set_mode(mode)
+    try:
+        for (N, M, seed) in [(1000, 777, 1), (300, 5000, 2), (2500, 260, 3)]:
+            rng = np.random.default_rng(seed)
+            f0 = rng.standard_normal((N, 32)).astype(np.float32) * rng.uniform(0.5, 2.0, (N, 1)).astype(np.float32)
+            f1 = rng.standard_normal((M, 32)).astype(np.float32) * rng.uniform(0.5, 2.0, (M, 1)).astype(np.float32)
+            k = min(N, M) // 2
+            f1[:k] = f0[:k] + 0.05 * rng.standard_normal((k, 32)).astype(np.float32)
+            i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+            j1, _ = engine.match_nn(f0, f1, want_2nd=False)
+            _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
+            assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2), (mode, N, M)
+            assert torch.equal(i1, j1)
+            mi, mj = engine.match_mutual(f0, f1, i1)
+            oi, oj = O.nn_to_mutual(f0, f1, o1)
+            assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mj.cpu().numpy(), oj), (mode, N, M)
+    finally:
+        engine.match_set_mode(0)
+
+
+def test_candidate_overflow_falls_back_to_exact_scan():
+    """More near-ties than candidate slots: the tensor-core path must hand the row to the exact scan."""
+    rng = np.random.default_rng(9)
+    f1 = rng.standard_normal((3000, 32)).astype(np.float32)
+    f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+    f1[500:700] = f1[500] + 1e-4 * rng.standard_normal((200, 32)).astype(np.float32)  # 200 near-duplicates
+    f1[1000:1100] = f1[1000]                                                            # 100 exact duplicates
+    f0 = np.concatenate([f1[500:520], f1[1000:1010], f1[:300]]).copy()
+    i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+    _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
+    assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2)
+    assert np.all(o1[20:30] == 1000) and np.all(o2[20:30] == 1001)
