@@ -28,6 +28,11 @@
 
 namespace lr_tc {
 
+static inline float __uint_as_float_host(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+#ifdef LR_TC_TIMING
+extern Prepared g_last; extern int g_last_regions; extern int64_t g_last_rows;
+#endif
+
 constexpr int TM = 128;                      // query rows per tile (UMMA M)
 constexpr int TN = 256;                      // target rows per tile (UMMA N)
 constexpr int KCORES = 8;                    // 16-byte K cores per row (4 data + 2 A-ext + 2 B-ext)
@@ -35,8 +40,9 @@ constexpr int RG_BYTES = KCORES * 128;       // one group of 8 rows
 constexpr int A_TILE_BYTES = TM / 8 * RG_BYTES;  // 16 KB
 constexpr int B_TILE_BYTES = TN / 8 * RG_BYTES;  // 32 KB
 constexpr int STAGES = 4;
-constexpr int CAND = 32;                     // candidate slots per query row
-constexpr int NTHREADS = 192;                // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+constexpr int CAND = 24;                     // candidate slots per (query row, column split, epilogue group)
+constexpr int NGROUPS = 2;                   // epilogue groups of four warps (one TMEM lane quadrant each)
+constexpr int NTHREADS = 64 + 128 * NGROUPS; // warp 0 producer, warp 1 MMA, then the epilogue groups
 constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 // A, B = f16 (format 0), both K-major (0), no negate, dense
 
@@ -244,39 +250,34 @@ __global__ void k_prep16(const float *__restrict__ F, const float *__restrict__ 
 }
 
 // ---------------------------------------------------------------- the sweep
+#ifdef LR_TC_TIMING
+__device__ unsigned long long g_tc_timing[16];
+#define TC_T0() const long long _t0 = clock64()
+#define TC_ACC(var) var += clock64() - _t0
+#else
+#define TC_T0()
+#define TC_ACC(var)
+#endif
+
 struct __align__(8) Smem {
     uint64_t a_full[2], a_empty[2], b_full[STAGES], b_empty[STAGES], t_full[2], t_empty[2];
     uint32_t tmem_base;
 };
 
-template <bool WANT2>
-__device__ __forceinline__ void slow_chunk(const uint32_t (&v)[32], int64_t col0, int64_t M, int64_t row, bool valid,
-                                           float beta, float &m1, float &m2, float &thr, int *__restrict__ cand,
-                                           int *__restrict__ cand_cnt)
+// rare path, part 2: append the flagged columns of a 32-column chunk to this thread's private
+// region of the candidate table (one writer per region: register counter, plain stores).  Kept
+// out of line and compact -- the epilogue is instruction-cache sensitive.
+__device__ __noinline__ int push_cols(unsigned mask, int col0, int M, int *__restrict__ slots, int cnt)
 {
-#pragma unroll
-    for (int r = 0; r < 32; ++r) {
-        const float x = __uint_as_float(v[r]);
-        if (x > thr) {
-            const int64_t col = col0 + r;
-            if (valid && col < M) {
-                const int pos = atomicAdd(&cand_cnt[row], 1);
-                if (pos < CAND) cand[row * CAND + pos] = (int)col;
-            }
-            if (WANT2) {
-                if (x > m1) {
-                    m2 = m1;
-                    m1 = x;
-                } else if (x > m2) {
-                    m2 = x;
-                }
-                thr = m2 - beta;
-            } else {
-                if (x > m1) m1 = x;
-                thr = m1 - beta;
-            }
+    while (mask) {
+        const int col = col0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (col < M) {
+            if (cnt < CAND) slots[cnt] = col;
+            ++cnt;
         }
     }
+    return cnt;
 }
 
 __device__ __forceinline__ float max32(const uint32_t (&r)[32])
@@ -289,6 +290,37 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32])
     const float a = fmaxf(fmaxf(m[0], m[1]), m[2]), b = fmaxf(fmaxf(m[3], m[4]), m[5]);
     const float c = fmaxf(fmaxf(m[6], m[7]), m[8]), d = fmaxf(m[9], m[10]);
     return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
+// One 32-column chunk of one query row.  Hot path: a 3-input-max tree and one compare.  When the
+// chunk maximum reaches the row's threshold (running max, or running second max for the 2-NN
+// variant, minus beta) the running maxima absorb the chunk and every column above the new
+// threshold is recorded.  The threshold never exceeds (final max - beta), so the recorded set
+// is a superset of the columns the exact re-rank has to see.
+template <bool WANT2>
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float mx, int col0, int M, bool valid, float beta,
+                                           float &m1, float &m2, float &thr, int *__restrict__ slots, int &cnt)
+{
+    if (mx > thr) {
+        // move the running maxima first: a column of this chunk can only matter if it is within
+        // beta of the maximum (second maximum) seen so far INCLUDING this chunk
+        if (WANT2) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float x = __uint_as_float(v[r]);
+                m2 = fmaxf(m2, fminf(m1, x));
+                m1 = fmaxf(m1, x);
+            }
+            thr = m2 - beta;
+        } else {
+            m1 = fmaxf(m1, mx);
+            thr = m1 - beta;
+        }
+        unsigned mask = 0u;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) mask |= (__uint_as_float(v[r]) > thr) ? (1u << r) : 0u;
+        if (valid) cnt = push_cols(mask, col0, M, slots, cnt);
+    }
 }
 
 template <bool WANT2>
@@ -311,7 +343,7 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 mbar_init(&sm->a_full[k], 1);
                 mbar_init(&sm->a_empty[k], 1);
                 mbar_init(&sm->t_full[k], 1);
-                mbar_init(&sm->t_empty[k], 4);
+                mbar_init(&sm->t_empty[k], 4 * NGROUPS);
             }
             for (int k = 0; k < STAGES; ++k) {
                 mbar_init(&sm->b_full[k], 1);
@@ -359,6 +391,11 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         // ===== MMA issuer: one thread drives the tensor core =====
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0, t_it = 0;
+            long long w_bfull = 0, w_tempty = 0, w_issue = 0, w_total = 0;
+            (void)w_bfull; (void)w_tempty; (void)w_issue; (void)w_total;
+#ifdef LR_TC_TIMING
+            const long long t_start = clock64();
+#endif
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int rb = item / nsplit, cs = item - rb * nsplit;
                 const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
@@ -369,9 +406,10 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 for (int t = t_lo; t < t_hi; ++t) {
                     const int s = b_it % STAGES;
                     const int acc = t_it & 1;
-                    mbar_wait(&sm->b_full[s], (b_it / STAGES) & 1);
-                    mbar_wait(&sm->t_empty[acc], ((t_it >> 1) & 1) ^ 1);
+                    { TC_T0(); mbar_wait(&sm->b_full[s], (b_it / STAGES) & 1); TC_ACC(w_bfull); }
+                    { TC_T0(); mbar_wait(&sm->t_empty[acc], ((t_it >> 1) & 1) ^ 1); TC_ACC(w_tempty); }
                     tc_fence_after();
+                    TC_T0();
                     const uint32_t b_addr = smem_u32(sB + s * B_TILE_BYTES);
                     const uint32_t d = tmem_base + (uint32_t)acc * TN;
                     // K = 16 per instruction = two 16-byte cores: features 0-15, 16-31, then the extension
@@ -380,51 +418,95 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                     tc_mma_f16(d, smem_desc(a_addr + 4 * 128), smem_desc(b_addr + 6 * 128), IDESC, 1u);
                     tc_commit(&sm->b_empty[s]);   // smem stage reusable once these MMAs have read it
                     tc_commit(&sm->t_full[acc]);  // accumulator ready for the epilogue
+                    TC_ACC(w_issue);
                     ++b_it;
                     ++t_it;
                 }
                 tc_commit(&sm->a_empty[ab]);
                 ++a_it;
             }
+#ifdef LR_TC_TIMING
+            w_total = clock64() - t_start;
+            atomicAdd(&g_tc_timing[0], (unsigned long long)w_bfull);
+            atomicAdd(&g_tc_timing[1], (unsigned long long)w_tempty);
+            atomicAdd(&g_tc_timing[2], (unsigned long long)w_issue);
+            atomicAdd(&g_tc_timing[3], (unsigned long long)w_total);
+            atomicAdd(&g_tc_timing[4], (unsigned long long)t_it);
+#endif
         }
     } else {
         // ===== epilogue: TMEM -> registers, running max + candidate collection =====
-        const int q = warp & 3;  // TMEM lane quadrant this warp may read
+        // two epilogue groups of four warps share every tile: group g scans 128 of its 256 columns,
+        // so a tile is drained in half the time and the two accumulator buffers give real double
+        // buffering against the MMA; a row's running maximum and candidate region are per group
+        const int q = warp & 3;            // TMEM lane quadrant this warp may read
+        const int grp = (warp - 2) >> 2;   // 0 or 1
         const float beta = params->beta;
         uint32_t t_it = 0;
+        long long e_wait = 0, e_work = 0, e_ld = 0;
+        (void)e_wait; (void)e_work; (void)e_ld;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int rb = item / nsplit, cs = item - rb * nsplit;
             const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
             const int64_t row = (int64_t)rb * TM + q * 32 + lane;
             const bool valid = row < N;
             float m1 = -INFINITY, m2 = -INFINITY, thr = -INFINITY;
+            const int64_t region = valid ? (row * nsplit + cs) * NGROUPS + grp : 0;
+            int *slots = cand + region * CAND;
+            int cnt = 0;
             for (int t = t_lo; t < t_hi; ++t) {
                 const int acc = t_it & 1;
-                mbar_wait(&sm->t_full[acc], (t_it >> 1) & 1);
+                { TC_T0(); mbar_wait(&sm->t_full[acc], (t_it >> 1) & 1); TC_ACC(e_wait); }
                 tc_fence_after();
+                TC_T0();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
-                // software pipeline: the load of the next 32 columns is in flight while this chunk is scanned
-                uint32_t va[32], vb[32];
-                tmem_ld32_issue(taddr, va);
-                tmem_ld32_wait(va);
+                // tcgen05.ld is latency-bound (~600 cycles per ld/wait round trip, measured with
+                // tools/micro_b200.cu): keep four 32-column loads in flight per warp and let the two
+                // epilogue groups interleave, which brings TMEM reads to ~100 B/clk/SM
+#ifdef LR_TC_SKIP_EPI
+                if (false)
+#endif
 #pragma unroll 1
-                for (int c = 0; c < TN / 32; c += 2) {
-                    tmem_ld32_issue(taddr + (c + 1) * 32, vb);
-                    if (max32(va) > thr)
-                        slow_chunk<WANT2>(va, (int64_t)t * TN + c * 32, M, row, valid, beta, m1, m2, thr, cand, cand_cnt);
+                for (int h = grp; h < TN / 128; h += NGROUPS) {  // with two groups: group g scans columns [128 g, 128 g + 128)
+                    uint32_t va[32], vb[32], vc[32], vd[32];
+                    const uint32_t ta = taddr + h * 128;
+#ifdef LR_TC_TIMING
+                    const long long tl0 = clock64();
+#endif
+                    tmem_ld32_issue(ta, va);
+                    tmem_ld32_issue(ta + 32, vb);
+                    tmem_ld32_issue(ta + 64, vc);
+                    tmem_ld32_issue(ta + 96, vd);
+                    tmem_ld32_wait(va);
                     tmem_ld32_wait(vb);
-                    if (c + 2 < TN / 32) tmem_ld32_issue(taddr + (c + 2) * 32, va);
-                    if (max32(vb) > thr)
-                        slow_chunk<WANT2>(vb, (int64_t)t * TN + (c + 1) * 32, M, row, valid, beta, m1, m2, thr, cand,
-                                          cand_cnt);
-                    if (c + 2 < TN / 32) tmem_ld32_wait(va);
+                    tmem_ld32_wait(vc);
+                    tmem_ld32_wait(vd);
+#ifdef LR_TC_TIMING
+                    e_ld += clock64() - tl0;
+#endif
+                    const int col0 = t * TN + h * 128;
+                    // the four max trees are independent: issue them back to back (ILP), then branch
+                    const float xa = max32(va), xb = max32(vb), xc = max32(vc), xd = max32(vd);
+                    scan_chunk<WANT2>(va, xa, col0, (int)M, valid, beta, m1, m2, thr, slots, cnt);
+                    scan_chunk<WANT2>(vb, xb, col0 + 32, (int)M, valid, beta, m1, m2, thr, slots, cnt);
+                    scan_chunk<WANT2>(vc, xc, col0 + 64, (int)M, valid, beta, m1, m2, thr, slots, cnt);
+                    scan_chunk<WANT2>(vd, xd, col0 + 96, (int)M, valid, beta, m1, m2, thr, slots, cnt);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm->t_empty[acc]);
+                TC_ACC(e_work);
                 ++t_it;
             }
+            if (valid) cand_cnt[region] = cnt;
         }
+#ifdef LR_TC_TIMING
+        if (warp == 2 && lane == 0) {
+            atomicAdd(&g_tc_timing[5], (unsigned long long)e_wait);
+            atomicAdd(&g_tc_timing[6], (unsigned long long)e_work);
+            atomicAdd(&g_tc_timing[7], (unsigned long long)e_ld);
+        }
+#endif
     }
 
     tc_fence_before();
@@ -469,13 +551,15 @@ __device__ __forceinline__ float canon_dist(const float *__restrict__ a, const f
 // one thread per query row: exact distances of its candidates, lexicographic (dist, index) top-2
 __global__ void __launch_bounds__(128)
 k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float *__restrict__ n0,
-         const float *__restrict__ n1, int64_t N, const int *__restrict__ cand, const int *__restrict__ cand_cnt,
-         Params *p, int *__restrict__ ovf_rows, int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
+         const float *__restrict__ n1, int64_t N, int nregions, const int *__restrict__ cand,
+         const int *__restrict__ cand_cnt, Params *p, int *__restrict__ ovf_rows, int64_t *__restrict__ idx1,
+         int64_t *__restrict__ idx2)
 {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (row >= N) return;
-    const int cnt = cand_cnt[row];
-    if (cnt > CAND) {  // too many near-ties for the slots: exact scan of the whole row instead
+    bool overflow = false;
+    for (int g = 0; g < nregions; ++g) overflow |= cand_cnt[row * nregions + g] > CAND;
+    if (overflow) {  // too many near-ties for the slots: exact scan of the whole row instead
         ovf_rows[atomicAdd(&p->ovf_count, 1)] = (int)row;
         return;
     }
@@ -488,15 +572,18 @@ k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float
     const float na = n0[row];
     Top2 c;
     c.s1 = INFINITY; c.j1 = 0x7fffffff; c.s2 = INFINITY; c.j2 = 0x7fffffff;
-    for (int k = 0; k < cnt; ++k) {
-        const int j = cand[row * CAND + k];
-        float b[32];
+    for (int g = 0; g < nregions; ++g) {
+        const int cnt = cand_cnt[row * nregions + g];
+        for (int k = 0; k < cnt; ++k) {
+            const int j = cand[(row * nregions + g) * CAND + k];
+            float b[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 x = reinterpret_cast<const float4 *>(F1 + (int64_t)j * 32)[q];
-            b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+            for (int q = 0; q < 8; ++q) {
+                const float4 x = reinterpret_cast<const float4 *>(F1 + (int64_t)j * 32)[q];
+                b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+            }
+            top2_put(c, canon_dist(a, b, na, n1[j]), j);
         }
-        top2_put(c, canon_dist(a, b, na, n1[j]), j);
     }
     idx1[row] = c.j1 == 0x7fffffff ? 0 : c.j1;
     if (idx2) idx2[row] = c.j2 == 0x7fffffff ? 0 : c.j2;
@@ -545,13 +632,19 @@ k_row_exact(const float *__restrict__ F0, const float *__restrict__ F1, const fl
 
 // ---------------------------------------------------------------- host side
 static int64_t pad_rows(int64_t n) { return (n + TN - 1) / TN * TN; }
+// candidate regions (row x column split x epilogue group) the scratch is sized for
+static int64_t region_budget(int64_t rows)
+{
+    const int64_t floor_regions = (int64_t)1 << 20;  // lets small problems split their columns finely
+    return rows * NGROUPS > floor_regions ? rows * NGROUPS : floor_regions;
+}
 
 size_t scratch_bytes(int64_t N, int64_t M)
 {
     const int64_t mx = N > M ? N : M;
     return lr::padded(sizeof(Params)) + lr::padded(pad_rows(N) * 128) + lr::padded(pad_rows(M) * 128) +
-           lr::padded(sizeof(float) * N) + lr::padded(sizeof(float) * M) + lr::padded(sizeof(int) * mx * CAND) +
-           2 * lr::padded(sizeof(int) * mx);
+           lr::padded(sizeof(float) * N) + lr::padded(sizeof(float) * M) + lr::padded(sizeof(int) * region_budget(mx) * CAND) +
+           lr::padded(sizeof(int) * region_budget(mx)) + lr::padded(sizeof(int) * mx);
 }
 
 // norms, scale, band and the fp16 operand images of both feature sets (once per match call)
@@ -566,8 +659,8 @@ int prepare(const float *f0, int64_t N, const float *f1, int64_t M, char *scratc
     P.op1 = reinterpret_cast<uint4 *>(cv.take<char>(P.pad1 * 128));
     P.n0 = cv.take<float>(N);
     P.n1 = cv.take<float>(M);
-    P.cand = cv.take<int>(mx * CAND);
-    P.cand_cnt = cv.take<int>(mx);
+    P.cand = cv.take<int>(region_budget(mx) * CAND);
+    P.cand_cnt = cv.take<int>(region_budget(mx));
     P.ovf_rows = cv.take<int>(mx);
     k_params_reset<<<1, 32, 0, st>>>(P.params);
     k_sqnorms_max<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f0, N, P.n0, &P.params->maxn0_bits);
@@ -594,12 +687,16 @@ int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float 
     int nsplit = 1;
     if (n_rowblocks < 2 * sms) nsplit = (2 * sms + n_rowblocks - 1) / n_rowblocks;
     if (nsplit > n_coltiles) nsplit = n_coltiles;
+    {   // the candidate table holds region_budget() regions
+        const int64_t cap = region_budget(N > M ? N : M) / (Na * NGROUPS);
+        if (nsplit > cap) nsplit = (int)(cap < 1 ? 1 : cap);
+    }
     const int tps = (n_coltiles + nsplit - 1) / nsplit;
     nsplit = (n_coltiles + tps - 1) / tps;
     const int nitems = n_rowblocks * nsplit;
     const int grid = nitems < sms ? nitems : sms;
     const size_t smem = 2 * A_TILE_BYTES + STAGES * B_TILE_BYTES + sizeof(Smem) + 1024 + 64;
-    LR_CUDA_TRY(cudaMemsetAsync(P.cand_cnt, 0, sizeof(int) * Na, st));
+    LR_CUDA_TRY(cudaMemsetAsync(P.cand_cnt, 0, sizeof(int) * Na * nsplit * NGROUPS, st));
     LR_CUDA_TRY(cudaMemsetAsync(&P.params->ovf_count, 0, sizeof(int), st));
     const int tok = lr::prof_begin(lr::PROF_NN, st);
     if (idx2) {
@@ -612,11 +709,54 @@ int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float 
                                                      P.cand, P.cand_cnt);
     }
     lr::prof_end(tok, st);
-    k_rerank<<<(unsigned)((Na + 127) / 128), 128, 0, st>>>(fa, fb, na, nb, Na, P.cand, P.cand_cnt, P.params, P.ovf_rows,
-                                                           idx1, idx2);
+#ifdef LR_TC_TIMING
+    g_last = P; g_last_regions = nsplit * NGROUPS; g_last_rows = Na;
+#endif
+    k_rerank<<<(unsigned)((Na + 127) / 128), 128, 0, st>>>(fa, fb, na, nb, Na, nsplit * NGROUPS, P.cand, P.cand_cnt,
+                                                           P.params, P.ovf_rows, idx1, idx2);
     k_row_exact<<<sms * 2, 256, 0, st>>>(fa, fb, na, nb, Nb, P.params, P.ovf_rows, idx1, idx2);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
 
+#ifdef LR_TC_TIMING
+void timing_dump()
+{
+    unsigned long long h[16];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
+    const double t = (double)(h[4] ? h[4] : 1);
+    fprintf(stderr, "[tc timing] tiles %llu | MMA per tile: wait b_full %.0f, wait t_empty %.0f, issue %.0f, total %.0f | "
+            "epilogue per tile: wait t_full %.0f, work %.0f (of which tcgen05.ld+wait %.0f)\n", h[4], h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[5] / t, h[6] / t, h[7] / t);
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(g_tc_timing, h, sizeof(h));
+}
+#endif
+
 }  // namespace lr_tc
+
+#ifdef LR_TC_TIMING
+namespace lr_tc { Prepared g_last; int g_last_regions = 0; int64_t g_last_rows = 0; }
+LR_EXPORT int lr_tc_debug_stats(void)
+{
+    using namespace lr_tc;
+    cudaDeviceSynchronize();
+    Params hp;
+    cudaMemcpy(&hp, g_last.params, sizeof(hp), cudaMemcpyDeviceToHost);
+    const int64_t n = g_last_rows * g_last_regions;
+    int *h = (int *)malloc(sizeof(int) * n);
+    cudaMemcpy(h, g_last.cand_cnt, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    double sum = 0; int mx = 0; int64_t over = 0;
+    for (int64_t i = 0; i < n; ++i) { sum += h[i]; if (h[i] > mx) mx = h[i]; if (h[i] > CAND) ++over; }
+    fprintf(stderr, "[tc debug] scale %g beta %g maxn0 %g maxn1 %g ovf_rows %d | regions/row %d avg cand/region %.2f max %d regions over %lld\n",
+            hp.scale, hp.beta, __uint_as_float_host(hp.maxn0_bits), __uint_as_float_host(hp.maxn1_bits), hp.ovf_count,
+            g_last_regions, sum / n, mx, (long long)over);
+    free(h);
+    return 0;
+}
+LR_EXPORT int lr_tc_timing_dump(void)
+{
+    lr_tc::timing_dump();
+    return 0;
+}
+#endif
