@@ -1,0 +1,89 @@
+"""Multi-GPU sharding of the hot path; one process per GPU, torch.distributed.
+
+Two modes, as in BASELINE.json's north star:
+
+* pairs of a registration set are split across ranks with no collective during compute
+  (`shard_pairs`, the reference's DistributedSampler split, Experiments/dataloader/data_loaders.py:111-116),
+  followed by one gather of the per-pair stat rows (`gather_rows`; the reference writes per-rank
+  .npy files instead, Experiments/test.py:257);
+* the hypotheses of ONE pair are split across ranks (`ransac_rigid_sharded`): a hypothesis is a
+  pure function of (seed, id), rank g scores a contiguous slice of every round, and the ranks
+  exchange one 8-byte packed (inlier count, hypothesis id) key per round with an NCCL MAX
+  all-reduce over NVLink.  Ties go to the lowest id, so the result is independent of the number
+  of GPUs; every rank regenerates the winning model from the id, so nothing is broadcast.
+
+`backend` is the object that does the scoring: lidarregistration_b200.engine (CUDA) by default.
+The CPU tests of this module (gloo, world size 2) pass a stand-in built on the oracle.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_pairs(num_pairs, rank, world_size):
+    """pair p -> rank p mod G; no padding / duplication (unlike DistributedSampler's drop_last=False)."""
+    return list(range(rank, num_pairs, world_size))
+
+
+def shard_range(lo, hi, rank, world_size):
+    """contiguous, near-equal slice of the hypothesis ids [lo, hi) owned by `rank`"""
+    n = hi - lo
+    a = lo + (n * rank) // world_size
+    b = lo + (n * (rank + 1)) // world_size
+    return a, b
+
+
+def gather_rows(rows, group=None):
+    """per-rank [k_r, C] float arrays -> one [sum k_r, C] array on every rank (rank order)"""
+    rank, ws = world(group)
+    rows = np.asarray(rows, dtype=np.float64)
+    if ws == 1:
+        return rows
+    out = [None] * ws
+    dist.all_gather_object(out, rows, group=group)
+    return np.concatenate([o for o in out if len(o)], axis=0) if any(len(o) for o in out) else rows
+
+
+def ransac_rigid_sharded(src, tgt, params, backend=None, group=None, device=None):
+    """RANSAC over one correspondence set with the hypotheses of every round split across ranks.
+
+    params: engine.LrRansacParams.  Returns the same dict as engine.ransac_rigid on every rank.
+    Semantics are those of the single-GPU call: with a confidence < 1 the exit is evaluated at
+    round ends (round_size hypotheses, all ranks together); with a fixed budget the whole budget is
+    one round per rank and a single all-reduce.
+    """
+    if backend is None:
+        from . import engine as backend
+    rank, ws = world(group)
+    n = int(src.shape[0])
+    m = int(params.sample_size)
+    max_iters = int(params.max_iters)
+    conf = float(params.confidence)
+    use_conf = conf < 1.0
+    R = int(params.round_size) if use_conf else max(max_iters, 1)
+    if device is None:
+        device = src.device if torch.is_tensor(src) else torch.device("cpu")
+    key = torch.zeros(1, dtype=torch.int64, device=device)
+    done = 0
+    if n >= m:
+        while done < max_iters:
+            lo, hi = done, min(done + R, max_iters)
+            a, b = shard_range(lo, hi, rank, ws)
+            if b > a:
+                backend.ransac_shard(src, tgt, params, a, b, key)
+            if ws > 1:
+                dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
+            done = hi
+            if use_conf:
+                cnt, _ = backend.key_unpack(int(key.item()))  # one 8-byte D2H per round
+                if cnt > 0 and done >= backend.conf_iters(cnt, n, m, conf, max_iters):
+                    break
+    out = backend.ransac_finalize(src, tgt, params, int(key.item()))
+    out["iters_run"] = done
+    return out

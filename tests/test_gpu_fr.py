@@ -1,0 +1,97 @@
+"""The algorithm interface (FR / GC_RANSAC / RANSAC_registration, reference Experiments/algorithms/FR.py:16-139)
+end to end on the GPU, against the oracle pipeline and the reference's success criterion."""
+import subprocess
+import sys
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from lidarregistration_b200 import engine, metrics, parallel, synthetic
+from lidarregistration_b200.algorithms import FR, GC_RANSAC, RANSAC_registration, PointCloud, find_nn, nn_to_mutual
+from oracle import lr_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_args(**kw):
+    a = dict(mode="MNN", iters=20000, codebase="GC", prosac=False, spatial_coherence_weight=0.0, GC_conf=0.9995,
+             fast_rejection="ELC", GC_LO=True, GPF_factor=2.0, GPF_grid_wid=10, GPF_max_matches=10 ** 9, seed=51)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+def tensors(p):
+    return (torch.from_numpy(p["xyz0"]), torch.from_numpy(p["xyz1"]), torch.from_numpy(p["feat0"]),
+            torch.from_numpy(p["feat1"]))
+
+
+@pytest.mark.parametrize("mode", ["MMN", "MNN", "no_filter", "GPF"])
+@pytest.mark.parametrize("codebase", ["GC", "open3D"])
+def test_fr_contract_and_accuracy(mode, codebase):
+    p = synthetic.make_pair(6000, seed=51 + 1000, overlap=0.7)
+    args = make_args(mode=mode, codebase=codebase, prosac=(mode == "GPF"))
+    out = FR(*tensors(p), args, p["T_gt"])
+    T, elapsed, pcd0, pcd1, n_init, ir_init, n_filt, ir_filt = out
+    assert T.shape == (4, 4) and T.dtype == np.float64 and elapsed > 0
+    assert n_init == 6000 and 0 < n_filt <= n_init and 0.0 <= ir_init <= ir_filt + 0.05 <= 1.05
+    assert np.asarray(pcd0.points).shape == (6000, 3)
+    assert metrics.registration_success(T, p["T_gt"])  # RE < 5 deg and TE < 60 cm (test.py:330-331)
+
+
+def test_unknown_mode_and_codebase_assert():
+    p = synthetic.make_pair(500, seed=3)
+    with pytest.raises(AssertionError):
+        FR(*tensors(p), make_args(mode="bogus"), p["T_gt"])
+    with pytest.raises(AssertionError):
+        FR(*tensors(p), make_args(codebase="bogus"), p["T_gt"])
+
+
+def test_gc_ransac_equals_oracle_pipeline():
+    """same correspondences, same seed: GC_RANSAC's pose is the oracle loop's refit (fixed budget)"""
+    p = synthetic.make_pair(4000, seed=77, overlap=0.6)
+    i0, i1, _ = find_nn(torch.from_numpy(p["feat0"]), torch.from_numpy(p["feat1"]))
+    m0, m1 = nn_to_mutual(torch.from_numpy(p["feat0"]), torch.from_numpy(p["feat1"]), i0, i1)
+    A, B = p["xyz0"][m0.numpy()], p["xyz1"][m1.numpy()]
+    T, secs = GC_RANSAC(A, B, 0.6, 30000, make_args(GC_conf=1.0), None)
+    ref = O.ransac(A, B, m=3, sampler=0, use_elc=True, thr=0.6, conf=1.0, max_iters=30000, seed=51)
+    assert np.abs(T - ref["T_refit"]).max() < 1e-5 and secs > 0
+    # no inliers at all -> identity, like `pose_T is None` (GC_RANSAC.py:51-52)
+    far = (B + 1000.0).astype(np.float32)[::-1].copy()
+    T0, _ = GC_RANSAC(A, far, 1e-6, 100, make_args(fast_rejection="NONE", GC_conf=1.0), None)
+    assert np.array_equal(T0, np.eye(4))
+    with pytest.raises(NotImplementedError):
+        GC_RANSAC(A, B, 0.6, 100, make_args(fast_rejection="SPRT"), None)
+
+
+def test_open3d_branch_equals_oracle_pipeline():
+    p = synthetic.make_pair(4000, seed=78, overlap=0.6)
+    _, o1, _ = O.find_nn(p["feat0"], p["feat1"])
+    mi, mj = O.nn_to_mutual(p["feat0"], p["feat1"], o1)
+    T = RANSAC_registration(PointCloud(p["xyz0"]), PointCloud(p["xyz1"]), torch.from_numpy(mi), torch.from_numpy(mj),
+                            0.6, 20000, make_args())
+    ref = O.ransac(p["xyz0"][mi], p["xyz1"][mj], m=4, sampler=1, use_elc=True, thr=0.6, conf=0.9995, max_iters=20000,
+                   round_size=65536, seed=51)
+    assert np.array_equal(T, ref["T"])
+
+
+def test_sharded_ransac_single_process_equals_plain_call():
+    d = synthetic.make_correspondences(6000, inlier_ratio=0.3, seed=9)
+    src, tgt = engine.to_dev_f32(d["src"]), engine.to_dev_f32(d["tgt"])
+    for conf, R in ((1.0, 65536), (0.999, 2048)):
+        params = engine.make_params(confidence=conf, max_iters=50000, seed=5, round_size=R)
+        a = engine.ransac_rigid(src, tgt, params)
+        b = parallel.ransac_rigid_sharded(src, tgt, params)
+        assert a["best_id"] == b["best_id"] and a["best_count"] == b["best_count"] and a["iters_run"] == b["iters_run"]
+        assert np.array_equal(a["T"], b["T"])
+
+
+def test_cli_entry_runs():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "Experiments", "test.py"), "--algo", "RANSAC", "--mode", "MMN",
+                          "--iters", "50000", "--GC_conf", "0.9995", "--max_samples", "3", "--num_points", "4000",
+                          "--prosac", "False"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "recall 100.00%" in out.stderr + out.stdout

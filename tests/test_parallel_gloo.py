@@ -1,0 +1,88 @@
+"""Host-side logic of the N > 1 paths on CPU: world size 2 over gloo.  The scoring backend is a
+stand-in built on the oracle (test infrastructure); the product default is the CUDA engine."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lidarregistration_b200 import engine, parallel, synthetic
+from oracle import lr_oracle as O
+
+
+class OracleBackend:
+    """what engine.ransac_shard / ransac_finalize / conf_iters do, on the CPU oracle"""
+    key_unpack = staticmethod(engine.key_unpack)
+    conf_iters = staticmethod(O.conf_iters)
+
+    @staticmethod
+    def ransac_shard(src, tgt, p, lo, hi, key):
+        samples = np.stack([O.sample(p.seed, h, 0 if p.sampler == 0 else 1, p.sample_size, len(src))
+                            for h in range(lo, hi)]).astype(np.int32)
+        counts, best = O.score_samples(src, tgt, samples, p.threshold, bool(p.use_elc), p.elc_ratio)
+        if best >= 0:
+            key[0] = max(int(key[0]), engine.key_pack(int(counts[best]), lo + best))
+
+    @staticmethod
+    def ransac_finalize(src, tgt, p, key):
+        cnt, hid = engine.key_unpack(key)
+        T = np.eye(4)
+        if cnt > 0:
+            s = O.sample(p.seed, hid, 0 if p.sampler == 0 else 1, p.sample_size, len(src))
+            T = O.kabsch(src[s].astype(float), tgt[s].astype(float))
+        return dict(T=T, best_id=hid, best_count=cnt)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = synthetic.make_correspondences(1500, inlier_ratio=0.35, seed=123)
+    out = {}
+    for name, conf, iters, R in (("fixed", 1.0, 3000, 65536), ("conf", 0.999, 20000, 512)):
+        p = engine.make_params(confidence=conf, max_iters=iters, seed=7, round_size=R, use_elc=True)
+        r = parallel.ransac_rigid_sharded(d["src"], d["tgt"], p, backend=OracleBackend)
+        out[name] = (r["best_id"], r["best_count"], r["iters_run"], r["T"].tolist())
+    rows = np.full((3 + rank, 22), float(rank))
+    out["rows"] = parallel.gather_rows(rows).tolist()
+    out["pairs"] = parallel.shard_pairs(11, rank, world)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharding_helpers():
+    assert parallel.shard_pairs(7, 0, 2) == [0, 2, 4, 6] and parallel.shard_pairs(7, 1, 2) == [1, 3, 5]
+    cover = []
+    for r in range(3):
+        a, b = parallel.shard_range(100, 1111, r, 3)
+        cover += list(range(a, b))
+    assert cover == list(range(100, 1111))
+    assert parallel.shard_range(5, 5, 0, 2) == (5, 5)
+
+
+def test_world2_matches_single_process():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = synthetic.make_correspondences(1500, inlier_ratio=0.35, seed=123)
+    for name, conf, iters, R in (("fixed", 1.0, 3000, 65536), ("conf", 0.999, 20000, 512)):
+        ref = O.ransac(d["src"], d["tgt"], conf=conf, max_iters=iters, round_size=R, seed=7)
+        for rank in (0, 1):
+            bid, bcnt, run, T = res[rank][name]
+            assert (bid, bcnt, run) == (ref["best_id"], ref["best_count"], ref["iters_run"]), (name, rank)
+            assert np.array_equal(np.array(T), ref["T"])
+    rows = np.array(res[0]["rows"])
+    assert rows.shape == (7, 22) and np.all(rows[:3] == 0) and np.all(rows[3:] == 1)
+    assert res[0]["rows"] == res[1]["rows"]
+    assert sorted(res[0]["pairs"] + res[1]["pairs"]) == list(range(11))
