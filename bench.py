@@ -233,6 +233,26 @@ def run_ours(args):
                     "d2h_bytes_per_step": PAIRS_PER_STEP * (N_CORR + 2 * 128 + 120)},
             "gpu_launches": launches_per_pair * PAIRS_PER_STEP * args.steps}
 
+    # second multi-GPU mode of the north star: the hypotheses of ONE pair split across the ranks,
+    # one 8-byte NCCL MAX all-reduce of the packed (count, id) key per round
+    if world > 1:
+        from lidarregistration_b200 import parallel
+        a0, b0 = (t.clone() for t in resident[0])
+        for t in (a0, b0):
+            dist.broadcast(t, src=0)
+        for _ in range(3):
+            parallel.ransac_rigid_sharded(a0, b0, params)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            shard_res = parallel.ransac_rigid_sharded(a0, b0, params)
+        e1.record()
+        barrier()
+        hyp_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        line["hypothesis_sharding"] = {"ms_per_pair": hyp_ms, "pairs_per_s": 1e3 / hyp_ms, "best_count": shard_res["best_count"],
+                                       "note": "one pair, 1M hypotheses split over %d ranks, 1 all-reduce(MAX, 8 B)" % world}
     if rank == 0:
         line["clocks"] = clocks
         # ---- roofline of the dominant kernel (k_score, the inlier sweep): SM FP32-bound

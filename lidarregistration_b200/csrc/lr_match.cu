@@ -265,43 +265,88 @@ __global__ void k_nn_merge(const Cand *__restrict__ part, int64_t N, int nsplit,
     if (idx2) idx2[r] = (m.j2 == 0x7fffffff) ? 0 : m.j2;
 }
 
-// mutual check + order-preserving compaction (single block, N is a few 10^4..10^6)
-__global__ void __launch_bounds__(1024)
-k_mutual_compact(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev, int64_t N, int64_t M,
-                 int64_t *__restrict__ out_i, int64_t *__restrict__ out_j, int64_t *__restrict__ K)
+// mutual check + order-preserving compaction in three small launches:
+// per-block survivor counts, exclusive scan of the (few) block counts, ordered scatter
+constexpr int kCompactBlock = 1024;
+
+__device__ __forceinline__ bool is_mutual(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev, int64_t i,
+                                          int64_t N, int64_t M, int64_t &j)
+{
+    if (i >= N) return false;
+    j = idx1[i];
+    return j >= 0 && j < M && rev[j] == i;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+k_mutual_count(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev, int64_t N, int64_t M,
+               int *__restrict__ block_cnt)
 {
     __shared__ int warp_tot[32];
-    __shared__ long long carry;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) carry = 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t j;
+    const bool keep = is_mutual(idx1, rev, blockIdx.x * (int64_t)kCompactBlock + threadIdx.x, N, M, j);
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[w] = __popc(b);
     __syncthreads();
-    for (int64_t base = 0; base < N; base += 1024) {
-        const int64_t i = base + tid;
-        int64_t j = -1;
-        bool keep = false;
-        if (i < N) {
-            j = idx1[i];
-            keep = j >= 0 && j < M && rev[j] == i;
+    if (w == 0) {
+        int v = warp_tot[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) block_cnt[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_block_scan(int *__restrict__ block_cnt, int nblocks, int64_t *__restrict__ K)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + tid;
+        const int v = i < nblocks ? block_cnt[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        const unsigned b = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[w] = __popc(b);
+        if (lane == 31) warp_tot[w] = incl;
         __syncthreads();
         int before = 0, total = 0;
         for (int k = 0; k < 32; ++k) {
-            const int v = warp_tot[k];
-            before += (k < w) ? v : 0;
-            total += v;
+            before += k < w ? warp_tot[k] : 0;
+            total += warp_tot[k];
         }
-        const long long off = carry + before + __popc(b & ((1u << lane) - 1u));
-        if (keep) {
-            out_i[off] = i;
-            out_j[off] = j;
-        }
+        if (i < nblocks) block_cnt[i] = carry_s + before + incl - v;  // exclusive prefix
         __syncthreads();
-        if (tid == 0) carry += total;
+        if (tid == 0) carry_s += total;
         __syncthreads();
     }
-    if (tid == 0) *K = carry;
+    if (tid == 0) *K = carry_s;
+}
+
+__global__ void __launch_bounds__(kCompactBlock)
+k_mutual_scatter(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev, int64_t N, int64_t M,
+                 const int *__restrict__ block_off, int64_t *__restrict__ out_i, int64_t *__restrict__ out_j)
+{
+    __shared__ int warp_tot[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = blockIdx.x * (int64_t)kCompactBlock + threadIdx.x;
+    int64_t j = -1;
+    const bool keep = is_mutual(idx1, rev, i, N, M, j);
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[w] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int k = 0; k < w; ++k) before += warp_tot[k];
+    if (keep) {
+        const int64_t off = (int64_t)block_off[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+        out_i[off] = i;
+        out_j[off] = j;
+    }
 }
 
 __device__ __forceinline__ float diffnorm(const float *a, const float *b, int D)
@@ -450,12 +495,14 @@ LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64
     // reverse sweep: nearest neighbour in f0 of every row of f1.  The reference
     // does it for unique(idx1) only (matching.py:224-225); rows outside that
     // set are never consulted by the intersection, so the result is identical.
-    const size_t rev_bytes = lr::padded(sizeof(int64_t) * M);
+    const int nblocks = (int)((N + kCompactBlock - 1) / kCompactBlock);
+    const size_t rev_bytes = lr::padded(sizeof(int64_t) * M) + lr::padded(sizeof(int) * nblocks);
     const bool tc = D == 32 && g_match_mode == 0;
     char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH,
                                           rev_bytes + (tc ? lr_tc::scratch_bytes(N, M) : nn_scratch_bytes(M, N)));
     if (!scratch) return LR_ERR_ALLOC;
     int64_t *rev = reinterpret_cast<int64_t *>(scratch);
+    int *block_cnt = reinterpret_cast<int *>(scratch + lr::padded(sizeof(int64_t) * M));
     int rc;
     if (tc) {
         lr_tc::Prepared P;
@@ -466,7 +513,9 @@ LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64
         rc = nn_sweep(f1, M, f0, N, D, rev, nullptr, scratch + rev_bytes, st);
     }
     if (rc) return rc;
-    k_mutual_compact<<<1, 1024, 0, st>>>(idx1, rev, N, M, out_i, out_j, K);
+    k_mutual_count<<<nblocks, kCompactBlock, 0, st>>>(idx1, rev, N, M, block_cnt);
+    k_block_scan<<<1, 1024, 0, st>>>(block_cnt, nblocks, K);
+    k_mutual_scatter<<<nblocks, kCompactBlock, 0, st>>>(idx1, rev, N, M, block_cnt, out_i, out_j);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
