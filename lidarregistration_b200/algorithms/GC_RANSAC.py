@@ -11,8 +11,8 @@ What the flags select here (DESIGN.md "GC codebase mapping"):
   --fast_rejection ELC  -> edge-length pre-rejection (preemption_edge_length.h:71-128)
   --fast_rejection NONE -> no pre-rejection
   --fast_rejection SPRT -> not implemented (raises)
-  --prosac True         -> correspondences pre-sorted best-first (GC_RANSAC.py:39-43);
-                           progressive sampling itself is SURVEY row f1 (uniform for now)
+  --prosac True         -> correspondences pre-sorted best-first (GC_RANSAC.py:39-43) and the
+                           PROSAC progressive sampler (sampler id 1, gcransac_python.cpp:464-465)
   --GC_conf c           -> confidence of the stopping rule
   --GC_LO               -> graph-cut LO is SURVEY row f3; the final least-squares
                            refit over the inliers is always returned, as pygcransac does
@@ -35,7 +35,8 @@ def findRigidTransform(x1y1z1, x2y2z2, threshold, conf, spatial_coherence_weight
     if use_sprt and not (min_inlier_ratio_for_sprt < 0):
         raise NotImplementedError("SPRT pre-verification is not part of the B200 hot path (use ELC or NONE)")
     params = engine.make_params(threshold=threshold, confidence=conf, max_iters=max_iters, seed=seed, sample_size=3,
-                                sampler=engine.SAMPLER_UNIFORM, use_elc=bool(use_sprt), elc_ratio=0.9,
+                                sampler=engine.SAMPLER_PROSAC if int(sampler) == 1 else engine.SAMPLER_UNIFORM,
+                                use_elc=bool(use_sprt), elc_ratio=0.9,
                                 round_size=round_size, refit=True)
     res = engine.ransac_rigid(x1y1z1, x2y2z2, params, want_mask=True)
     mask = res["mask"].cpu().numpy()

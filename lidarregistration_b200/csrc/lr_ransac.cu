@@ -58,6 +58,7 @@ struct Ws {
     double *m64;      // 12 per slot
     int *cnt;         // per slot: exact inlier count, accumulated over point splits
     int *need;        // per round: inlier count that triggers the confidence exit
+    uint32_t *growth; // PROSAC growth function T'_n (null unless the sampler is PROSAC)
     double *scratchT; // 16 doubles of staging
     int64_t n_pad;
 };
@@ -79,32 +80,56 @@ __device__ __forceinline__ uint32_t draw(uint64_t seed, uint64_t id, uint32_t d,
     return (uint32_t)(((r >> 32) * (uint64_t)m) >> 32);
 }
 
-template <int M>
-__device__ __forceinline__ void sample_ids(uint64_t seed, uint64_t id, int sampler, int64_t n, int32_t (&out)[M])
+constexpr uint64_t kProsacTN = 100000;  // ProsacSampler(points, m, T_N = 100 000), SURVEY App. A
+
+// K unique indices out of [0, n): draw d picks the r-th index not yet taken
+template <int K>
+__device__ __forceinline__ void unique_ids(uint64_t seed, uint64_t id, int64_t n, int32_t *out)
 {
-    if (sampler == LR_SAMPLER_REPLACE) {
+    int32_t taken[K > 0 ? K : 1];
 #pragma unroll
-        for (int d = 0; d < M; ++d) out[d] = (int32_t)draw(seed, id, d, (uint32_t)n);
-        return;
-    }
-    int32_t taken[M];
-#pragma unroll
-    for (int d = 0; d < M; ++d) {
+    for (int d = 0; d < K; ++d) {
         int32_t r = (int32_t)draw(seed, id, d, (uint32_t)(n - d));
 #pragma unroll
-        for (int e = 0; e < M; ++e)
+        for (int e = 0; e < K; ++e)
             if (e < d && r >= taken[e]) ++r;
         out[d] = r;
-        // sorted insert (fully unrolled bubble from the back)
         taken[d] = r;
 #pragma unroll
-        for (int e = M - 1; e > 0; --e)
+        for (int e = K - 1; e > 0; --e)
             if (e <= d && taken[e - 1] > taken[e]) {
                 int32_t tmp = taken[e];
                 taken[e] = taken[e - 1];
                 taken[e - 1] = tmp;
             }
     }
+}
+
+// sampler ids of include/lidarreg.h (== oracle lro_sample): uniform-unique, PROSAC, with replacement
+template <int M>
+__device__ __forceinline__ void sample_ids(uint64_t seed, uint64_t id, int sampler, int64_t n,
+                                           const uint32_t *__restrict__ growth, int32_t (&out)[M])
+{
+    if (sampler == LR_SAMPLER_REPLACE) {
+#pragma unroll
+        for (int d = 0; d < M; ++d) out[d] = (int32_t)draw(seed, id, d, (uint32_t)n);
+        return;
+    }
+    if (sampler == LR_SAMPLER_PROSAC && growth != nullptr && id + 1 <= kProsacTN) {
+        // draw k = id + 1 uses the n_k best correspondences, n_k = smallest n in [M, N] with T'_n >= k;
+        // M - 1 unique indices below n_k - 1 plus correspondence n_k - 1 itself
+        const uint64_t k = id + 1;
+        int64_t lo = M, hi = n;
+        while (lo < hi) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if ((uint64_t)growth[mid - 1] >= k) hi = mid;
+            else lo = mid + 1;
+        }
+        unique_ids<M - 1>(seed, id, lo - 1, out);
+        out[M - 1] = (int32_t)(lo - 1);
+        return;
+    }
+    unique_ids<M>(seed, id, n, out);
 }
 
 __device__ __forceinline__ double len3(const double *a, const double *b)
@@ -392,8 +417,8 @@ __device__ __forceinline__ bool elc_pass_fast(const double (&P)[M][3], const dou
 template <int M>
 __global__ void __launch_bounds__(kGenThreads)
 k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, uint64_t seed, int sampler,
-      int use_elc, double elc_ratio, int64_t id_lo, int64_t id_hi, const int32_t *__restrict__ fed, Ctl *ctl,
-      uint32_t *__restrict__ slot_id, int32_t *__restrict__ samp)
+      int use_elc, double elc_ratio, int64_t id_lo, int64_t id_hi, const int32_t *__restrict__ fed,
+      const uint32_t *__restrict__ growth, Ctl *ctl, uint32_t *__restrict__ slot_id, int32_t *__restrict__ samp)
 {
     if (ctl->done) return;
     int64_t id = id_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -404,7 +429,7 @@ k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, u
 #pragma unroll
             for (int d = 0; d < M; ++d) s[d] = fed[(id - id_lo) * M + d];
         } else {
-            sample_ids<M>(seed, (uint64_t)id, sampler, n, s);
+            sample_ids<M>(seed, (uint64_t)id, sampler, n, growth, s);
         }
         if (use_elc) {
             double P[M][3], Q[M][3];
@@ -705,7 +730,8 @@ __global__ void k_round_end(Ctl *ctl, int64_t round_len, const int *__restrict__
 // key -> model of the selected hypothesis (identity when none / zero inliers)
 template <int M>
 __global__ void k_model_from_key(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n,
-                                 uint64_t seed, int sampler, unsigned long long key_in, int use_ctl_key, Ctl *ctl)
+                                 uint64_t seed, int sampler, const uint32_t *__restrict__ growth,
+                                 unsigned long long key_in, int use_ctl_key, Ctl *ctl)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     unsigned long long key = use_ctl_key ? ctl->best_key : key_in;
@@ -715,7 +741,7 @@ __global__ void k_model_from_key(const float *__restrict__ src, const float *__r
     if (key != 0ULL && cnt > 0) {
         uint64_t id = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFULL));
         int32_t s[M];
-        sample_ids<M>(seed, id, sampler, n, s);
+        sample_ids<M>(seed, id, sampler, n, growth, s);
         double P[M][3], Q[M][3];
 #pragma unroll
         for (int d = 0; d < M; ++d)
@@ -865,12 +891,13 @@ __global__ void k_set_T(Ctl *ctl, const double *T12)
 }
 
 template <int M>
-__global__ void k_sample_only(uint64_t seed, int sampler, int64_t n, int64_t id_lo, int64_t H, int32_t *out)
+__global__ void k_sample_only(uint64_t seed, int sampler, int64_t n, const uint32_t *__restrict__ growth, int64_t id_lo,
+                              int64_t H, int32_t *out)
 {
     int64_t h = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (h >= H) return;
     int32_t s[M];
-    sample_ids<M>(seed, (uint64_t)(id_lo + h), sampler, n, s);
+    sample_ids<M>(seed, (uint64_t)(id_lo + h), sampler, n, growth, s);
 #pragma unroll
     for (int d = 0; d < M; ++d) out[h * M + d] = s[d];
 }
@@ -888,7 +915,7 @@ __global__ void k_scatter_models(const Ctl *ctl, const uint32_t *slot_id, const 
 // host side
 // ------------------------------------------------------------------------
 
-int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
+int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false)
 {
     ws.n_pad = ((n + kChunk - 1) / kChunk) * kChunk;
     if (ws.n_pad == 0) ws.n_pad = kChunk;
@@ -896,7 +923,8 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
                    lr::padded(sizeof(int32_t) * 4 * round) +
                    lr::padded(sizeof(uint32_t) * round) + lr::padded(sizeof(float4) * 4 * (round + kHypPerItem)) +
                    lr::padded(sizeof(double) * 12 * round) + lr::padded(sizeof(int) * round) +
-                   lr::padded(sizeof(int) * (nrounds + 1)) + lr::padded(sizeof(double) * 16);
+                   lr::padded(sizeof(int) * (nrounds + 1)) + lr::padded(sizeof(double) * 16) +
+                   lr::padded(sizeof(uint32_t) * (prosac ? n : 1));
     void *base = lr::arena_get(lr::SLOT_RANSAC, bytes);
     if (!base) return LR_ERR_ALLOC;
     lr::Carver cv(base);
@@ -909,6 +937,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws)
     ws.cnt = cv.take<int>(round);
     ws.need = cv.take<int>(nrounds + 1);
     ws.scratchT = cv.take<double>(16);
+    ws.growth = prosac ? cv.take<uint32_t>(n) : nullptr;
     return LR_OK;
 }
 
@@ -916,8 +945,8 @@ int check_params(const LrRansacParams *p, int64_t n)
 {
     LR_REQUIRE(p != nullptr, "params is null");
     LR_REQUIRE(p->sample_size == 3 || p->sample_size == 4, "sample_size must be 3 or 4");
-    LR_REQUIRE(p->sampler == LR_SAMPLER_UNIFORM || p->sampler == LR_SAMPLER_REPLACE,
-               "sampler must be LR_SAMPLER_UNIFORM or LR_SAMPLER_REPLACE (PROSAC: not implemented)");
+    LR_REQUIRE(p->sampler == LR_SAMPLER_UNIFORM || p->sampler == LR_SAMPLER_REPLACE || p->sampler == LR_SAMPLER_PROSAC,
+               "sampler must be one of LR_SAMPLER_*");
     LR_REQUIRE(p->threshold > 0.0, "threshold must be positive");
     LR_REQUIRE(p->max_iters >= 0 && p->max_iters < (int64_t)0xFFFFFFFFLL, "max_iters out of range");
     LR_REQUIRE(p->round_size > 0 && p->round_size <= (1 << 20), "round_size out of range");
@@ -929,6 +958,32 @@ int64_t batch_len(int64_t total)
 {
     const int64_t cap = (int64_t)1 << 20;
     return total < 1 ? 1 : (total < cap ? total : cap);
+}
+
+// PROSAC growth function T'_n (same expressions as the oracle's lro_prosac_growth)
+int upload_growth(const Ws &ws, int64_t N, int m, cudaStream_t st)
+{
+    if (!ws.growth) return LR_OK;
+    std::vector<uint32_t> g((size_t)N);
+    double T_n = (double)kProsacTN;
+    for (int i = 0; i < m; ++i) T_n *= (double)(m - i) / (double)(N - i);
+    uint32_t T_prime = 1;
+    for (int64_t i = 0; i < N; ++i) {
+        if (i + 1 <= m) {
+            g[i] = T_prime;
+            continue;
+        }
+        double T_next = (double)(i + 1) * T_n / (double)(i + 1 - m);
+        double inc = ceil(T_next - T_n);
+        if (!(inc < 4.0e9)) inc = 4.0e9;
+        uint64_t v = (uint64_t)T_prime + (uint64_t)inc;
+        g[i] = v > 0xFFFFFFF0ULL ? 0xFFFFFFF0U : (uint32_t)v;
+        T_n = T_next;
+        T_prime = g[i];
+    }
+    LR_CUDA_TRY(cudaMemcpyAsync(ws.growth, g.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));  // g is a local
+    return LR_OK;
 }
 
 int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cudaStream_t st)
@@ -953,11 +1008,11 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     int tok = lr::prof_begin(lr::PROF_GEN, st);
     if (p.sample_size == 3) {
         k_gen<3><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
-                                                  ws.ctl, ws.slot_id, ws.samp);
+                                                  ws.growth, ws.ctl, ws.slot_id, ws.samp);
         k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
     } else {
         k_gen<4><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
-                                                  ws.ctl, ws.slot_id, ws.samp);
+                                                  ws.growth, ws.ctl, ws.slot_id, ws.samp);
         k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
     }
     lr::prof_end(tok, st);
@@ -991,9 +1046,9 @@ int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &
 {
     const double thr2 = p.threshold * p.threshold;
     if (p.sample_size == 3)
-        k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, key, use_ctl_key, ws.ctl);
+        k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
     else
-        k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, key, use_ctl_key, ws.ctl);
+        k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
     const bool want_refit = (T_refit != nullptr) && p.refit;
     if (want_refit || mask || stats) {
         int blocks = (int)((n + 255) / 256);
@@ -1072,7 +1127,9 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
     const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
     const int64_t nrounds = (p.max_iters + R - 1) / R;
     Ws ws;
-    rc = ws_setup(n, R, nrounds, ws);
+    rc = ws_setup(n, R, nrounds, ws, p.sampler == LR_SAMPLER_PROSAC);
+    if (rc) return rc;
+    rc = upload_growth(ws, n, p.sample_size, st);
     if (rc) return rc;
     rc = launch_pack(src, tgt, n, ws, st);
     if (rc) return rc;
@@ -1162,7 +1219,9 @@ LR_EXPORT int lr_ransac_shard(const float *src, const float *tgt, int64_t n, con
     const LrRansacParams &p = *params;
     const int64_t R = batch_len(id_hi - id_lo);
     Ws ws;
-    rc = ws_setup(n, R, 1, ws);
+    rc = ws_setup(n, R, 1, ws, p.sampler == LR_SAMPLER_PROSAC);
+    if (rc) return rc;
+    rc = upload_growth(ws, n, p.sample_size, st);
     if (rc) return rc;
     rc = launch_pack(src, tgt, n, ws, st);
     if (rc) return rc;
@@ -1187,7 +1246,9 @@ LR_EXPORT int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, 
     LR_REQUIRE(n >= params->sample_size, "fewer correspondences than the sample size");
     cudaStream_t st = (cudaStream_t)stream;
     Ws ws;
-    rc = ws_setup(n, params->round_size, 1, ws);
+    rc = ws_setup(n, params->round_size, 1, ws, params->sampler == LR_SAMPLER_PROSAC);
+    if (rc) return rc;
+    rc = upload_growth(ws, n, params->sample_size, st);
     if (rc) return rc;
     k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
     return finish(src, tgt, n, *params, ws, 0, key, T_out, T_refit, mask, stats, st);
@@ -1200,12 +1261,18 @@ LR_EXPORT int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t 
     if (rc) return rc;
     LR_REQUIRE(samples && H >= 0 && n >= params->sample_size, "bad arguments");
     if (H == 0) return LR_OK;
+    lr::Lock lock;
     cudaStream_t st = (cudaStream_t)stream;
+    Ws ws;
+    rc = ws_setup(n, 1, 1, ws, params->sampler == LR_SAMPLER_PROSAC);
+    if (rc) return rc;
+    rc = upload_growth(ws, n, params->sample_size, st);
+    if (rc) return rc;
     int blocks = (int)((H + 255) / 256);
     if (params->sample_size == 3)
-        k_sample_only<3><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, id_lo, H, samples);
+        k_sample_only<3><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, ws.growth, id_lo, H, samples);
     else
-        k_sample_only<4><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, id_lo, H, samples);
+        k_sample_only<4><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, ws.growth, id_lo, H, samples);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }

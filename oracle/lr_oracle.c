@@ -196,27 +196,70 @@ static inline uint32_t lro_draw(uint64_t seed, uint64_t id, uint32_t d, uint32_t
     return (uint32_t)(((r >> 32) * (uint64_t)m) >> 32);
 }
 
-/* sampler 0: m unique indices, uniform over m-subsets in draw order
- *            (GC UniformSampler semantics);
- * sampler 1: m indices with replacement (Open3D semantics). */
-LRO_API void lro_sample(uint64_t seed, uint64_t id, int sampler, int m, int64_t n, int32_t *out)
+/* k unique indices out of [0, n), uniform over k-subsets in draw order: draw d
+ * picks the r-th index not yet taken (taken list kept sorted) */
+static void lro_unique(uint64_t seed, uint64_t id, int k, int64_t n, int32_t *out)
 {
-    if (sampler == 1) {
-        for (int d = 0; d < m; ++d) out[d] = (int32_t)lro_draw(seed, id, (uint32_t)d, (uint32_t)n);
-        return;
-    }
-    /* unique: draw d picks the r-th index not yet taken (taken list kept sorted) */
     int32_t taken[4];
-    for (int d = 0; d < m; ++d) {
+    for (int d = 0; d < k; ++d) {
         int32_t r = (int32_t)lro_draw(seed, id, (uint32_t)d, (uint32_t)(n - d));
         for (int e = 0; e < d; ++e)
             if (r >= taken[e]) ++r;
         out[d] = r;
-        /* insert r into the sorted taken list */
         int e = d;
         while (e > 0 && taken[e - 1] > r) { taken[e] = taken[e - 1]; --e; }
         taken[e] = r;
     }
+}
+
+#define LRO_PROSAC_TN 100000 /* ProsacSampler(points, m, T_N = 100 000), SURVEY App. A */
+
+/* PROSAC growth function: growth[n-1] = T'_n, the last draw (1-based)
+ * made from the n best correspondences; T_n = T_N prod_{i<m} (n-i)/(N-i),
+ * T'_{n+1} = T'_n + ceil(T_{n+1} - T_n); T'_n = 1 for n <= m. */
+LRO_API void lro_prosac_growth(int64_t N, int m, uint32_t *growth)
+{
+    double T_n = (double)LRO_PROSAC_TN;
+    for (int i = 0; i < m; ++i) T_n *= (double)(m - i) / (double)(N - i);
+    uint32_t T_prime = 1;
+    for (int64_t i = 0; i < N; ++i) {
+        if (i + 1 <= m) { growth[i] = T_prime; continue; }
+        double T_next = (double)(i + 1) * T_n / (double)(i + 1 - m);
+        double inc = ceil(T_next - T_n);
+        if (!(inc < 4.0e9)) inc = 4.0e9;
+        uint64_t g = (uint64_t)T_prime + (uint64_t)inc;
+        growth[i] = g > 0xFFFFFFF0ULL ? 0xFFFFFFF0U : (uint32_t)g;
+        T_n = T_next;
+        T_prime = growth[i];
+    }
+}
+
+/* sampler ids as in include/lidarreg.h:
+ *   0 uniform: m unique indices (GC UniformSampler semantics);
+ *   1 PROSAC : draw k = id + 1 takes m-1 unique indices from the first n_k - 1
+ *              correspondences plus correspondence n_k - 1, n_k = smallest n with
+ *              k <= T'_n; uniform after T_N draws (needs `growth`, inputs sorted best first);
+ *   2 replace: m indices with replacement (Open3D semantics). */
+LRO_API void lro_sample(uint64_t seed, uint64_t id, int sampler, int m, int64_t n, const uint32_t *growth,
+                        int32_t *out)
+{
+    if (sampler == 2) {
+        for (int d = 0; d < m; ++d) out[d] = (int32_t)lro_draw(seed, id, (uint32_t)d, (uint32_t)n);
+        return;
+    }
+    if (sampler == 1 && growth && id + 1 <= LRO_PROSAC_TN) {
+        const uint64_t k = id + 1;
+        int64_t lo = m, hi = n; /* smallest subset size in [m, n] whose T' covers draw k */
+        while (lo < hi) {
+            int64_t mid = lo + (hi - lo) / 2;
+            if ((uint64_t)growth[mid - 1] >= k) hi = mid;
+            else lo = mid + 1;
+        }
+        lro_unique(seed, id, m - 1, lo - 1, out);
+        out[m - 1] = (int32_t)(lo - 1);
+        return;
+    }
+    lro_unique(seed, id, m, n, out);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -469,6 +512,11 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
 {
     int64_t best_id = -1, best_cnt = -1, passed = 0, done = 0;
     double bestT[12];
+    uint32_t *growth = NULL;
+    if (sampler == 1 && n >= m) {
+        growth = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+        lro_prosac_growth(n, m, growth);
+    }
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) bestT[4 * r + c] = (r == c) ? 1.0 : 0.0;
     if (n >= m && round > 0) {
         while (done < max_iters) {
@@ -481,7 +529,7 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
                 for (int64_t id = lo; id < hi; ++id) {
                     int32_t s[4];
                     double Th[12];
-                    lro_sample(seed, (uint64_t)id, sampler, m, n, s);
+                    lro_sample(seed, (uint64_t)id, sampler, m, n, growth, s);
                     if (!lro_model_from_sample(src, tgt, s, m, use_elc, elc_ratio, Th)) continue;
                     ++t_pass;
                     int64_t c = lro_count_inliers(src, tgt, n, Th, thr, NULL);
@@ -501,7 +549,7 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
     }
     if (best_id >= 0 && best_cnt > 0) { /* a 0-inlier model never replaces the identity (App. B: fitness must improve on 0) */
         int32_t s[4];
-        lro_sample(seed, (uint64_t)best_id, sampler, m, n, s);
+        lro_sample(seed, (uint64_t)best_id, sampler, m, n, growth, s);
         lro_model_from_sample(src, tgt, s, m, 0, elc_ratio, bestT);
     }
     memcpy(T, bestT, sizeof(bestT));
@@ -523,6 +571,7 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
         }
         if (!mask) free(mk);
     }
+    free(growth);
     if (st) {
         st->iters_run = done; st->n_passed = passed; st->best_id = best_id;
         st->best_count = best_cnt; st->refit_count = refit_cnt;

@@ -111,9 +111,21 @@ def ratio(F0, F1, i0, i1, i2):
     return out
 
 
-def sample(seed, hid, sampler, m, n):
+UNIFORM, PROSAC, REPLACE = 0, 1, 2  # sampler ids of include/lidarreg.h
+
+
+def prosac_growth(n, m):
+    g = np.empty(n, np.uint32)
+    lib().lro_prosac_growth(ctypes.c_int64(n), int(m), g.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    return g
+
+
+def sample(seed, hid, sampler, m, n, growth=None):
     out = np.empty(m, np.int32)
-    lib().lro_sample(ctypes.c_uint64(seed), ctypes.c_uint64(hid), int(sampler), int(m), ctypes.c_int64(n),
+    if sampler == PROSAC and growth is None:
+        growth = prosac_growth(n, m)
+    gp = growth.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)) if growth is not None else None
+    lib().lro_sample(ctypes.c_uint64(seed), ctypes.c_uint64(hid), int(sampler), int(m), ctypes.c_int64(n), gp,
                      _p(out, c_i32p))
     return out
 

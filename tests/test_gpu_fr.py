@@ -33,7 +33,7 @@ def tensors(p):
 @pytest.mark.parametrize("codebase", ["GC", "open3D"])
 def test_fr_contract_and_accuracy(mode, codebase):
     p = synthetic.make_pair(6000, seed=51 + 1000, overlap=0.7)
-    args = make_args(mode=mode, codebase=codebase, prosac=(mode == "GPF"))
+    args = make_args(mode=mode, codebase=codebase, prosac=True)  # the reference default (test.py:308)
     out = FR(*tensors(p), args, p["T_gt"])
     T, elapsed, pcd0, pcd1, n_init, ir_init, n_filt, ir_filt = out
     assert T.shape == (4, 4) and T.dtype == np.float64 and elapsed > 0
@@ -73,7 +73,7 @@ def test_open3d_branch_equals_oracle_pipeline():
     mi, mj = O.nn_to_mutual(p["feat0"], p["feat1"], o1)
     T = RANSAC_registration(PointCloud(p["xyz0"]), PointCloud(p["xyz1"]), torch.from_numpy(mi), torch.from_numpy(mj),
                             0.6, 20000, make_args())
-    ref = O.ransac(p["xyz0"][mi], p["xyz1"][mj], m=4, sampler=1, use_elc=True, thr=0.6, conf=0.9995, max_iters=20000,
+    ref = O.ransac(p["xyz0"][mi], p["xyz1"][mj], m=4, sampler=2, use_elc=True, thr=0.6, conf=0.9995, max_iters=20000,
                    round_size=65536, seed=51)
     assert np.array_equal(T, ref["T"])
 

@@ -49,23 +49,29 @@ def test_fed_triplets_cfg3_size():
 
 
 @pytest.mark.parametrize("sampler,m", [(engine.SAMPLER_UNIFORM, 3), (engine.SAMPLER_UNIFORM, 4),
-                                       (engine.SAMPLER_REPLACE, 4), (engine.SAMPLER_REPLACE, 3)])
+                                       (engine.SAMPLER_REPLACE, 4), (engine.SAMPLER_REPLACE, 3),
+                                       (engine.SAMPLER_PROSAC, 3), (engine.SAMPLER_PROSAC, 4)])
 def test_sampler_matches_oracle(sampler, m):
     p = engine.make_params(sample_size=m, sampler=sampler, seed=1234)
     for n in (m, 37, 30000):
         got = engine.ransac_sample(p, n, 1000, 4096).cpu().numpy()
-        osamp = 0 if sampler == engine.SAMPLER_UNIFORM else 1
-        want = np.stack([O.sample(1234, 1000 + h, osamp, m, n) for h in range(0, 4096, 16)])
+        if sampler == engine.SAMPLER_PROSAC and n > m:  # also the hand-over to uniform after T_N = 100000 draws
+            late = engine.ransac_sample(p, n, 99990, 32).cpu().numpy()
+            g = O.prosac_growth(n, m)
+            assert np.array_equal(late, np.stack([O.sample(1234, 99990 + h, sampler, m, n, g) for h in range(32)]))
+        growth = O.prosac_growth(n, m) if sampler == engine.SAMPLER_PROSAC else None
+        want = np.stack([O.sample(1234, 1000 + h, sampler, m, n, growth) for h in range(0, 4096, 16)])
         assert np.array_equal(got[::16], want)
 
 
-@pytest.mark.parametrize("inlier,use_elc,m,sampler", [(0.3, True, 3, 0), (0.3, False, 3, 0), (0.5, True, 4, 2)])
+@pytest.mark.parametrize("inlier,use_elc,m,sampler", [(0.3, True, 3, 0), (0.3, False, 3, 0), (0.5, True, 4, 2),
+                                                      (0.3, True, 3, 1)])
 def test_full_loop_matches_oracle(inlier, use_elc, m, sampler):
     d = synthetic.make_correspondences(8000, inlier_ratio=inlier, seed=33)
     params = engine.make_params(threshold=0.6, confidence=1.0, max_iters=20000, seed=51, sample_size=m,
                                 sampler=sampler, use_elc=use_elc, round_size=4096)
     res = engine.ransac_rigid(d["src"], d["tgt"], params, want_mask=True)
-    ref = O.ransac(d["src"], d["tgt"], m=m, sampler=1 if sampler == 2 else 0, use_elc=use_elc, thr=0.6, conf=1.0,
+    ref = O.ransac(d["src"], d["tgt"], m=m, sampler=sampler, use_elc=use_elc, thr=0.6, conf=1.0,
                    max_iters=20000, round_size=4096, seed=51, return_mask=True)
     assert res["best_id"] == ref["best_id"] and res["best_count"] == ref["best_count"]
     assert res["iters_run"] == ref["iters_run"] == 20000 and res["n_scored"] == ref["n_passed"]

@@ -76,13 +76,39 @@ def test_sampler_properties():
         seen.update(s.tolist())
         s4 = O.sample(51, hid, 0, 4, n)
         assert len(set(s4.tolist())) == 4
-        r = O.sample(51, hid, 1, 4, n)
+        r = O.sample(51, hid, 2, 4, n)
         assert r.min() >= 0 and r.max() < n
     assert seen == set(range(n))
     assert np.array_equal(O.sample(7, 123, 0, 3, 1000), O.sample(7, 123, 0, 3, 1000))
     assert not np.array_equal(O.sample(7, 123, 0, 3, 1000), O.sample(8, 123, 0, 3, 1000))
     # n == m: a permutation
     assert sorted(O.sample(1, 5, 0, 3, 3).tolist()) == [0, 1, 2]
+
+
+def test_prosac_sampler_properties():
+    # draw k uses the n_k best correspondences, the newest one is forced, uniform after T_N
+    n, m = 5000, 3
+    g = O.prosac_growth(n, m)
+    assert np.all(g[:m] == 1) and np.all(np.diff(g[m - 1:].astype(np.int64)) >= 1)
+    prev_top = 0
+    for hid in list(range(0, 300)) + [5000, 50000, 99999]:
+        s = O.sample(9, hid, O.PROSAC, m, n, g)
+        assert len(set(s.tolist())) == m and s.max() < n
+        k = hid + 1
+        nk = m + int(np.searchsorted(g[m - 1:], k, side="left"))  # smallest n >= m with g[n-1] >= k
+        assert s[-1] == nk - 1 and s[:-1].max() < nk - 1
+        assert nk >= prev_top
+        prev_top = nk
+    assert O.sample(9, 0, O.PROSAC, m, n, g).tolist()[-1] == m - 1      # first draw: the m best
+    late = np.array([O.sample(9, h, O.PROSAC, m, n, g) for h in range(100000, 100400)])
+    assert np.array_equal(late, np.array([O.sample(9, h, O.UNIFORM, m, n) for h in range(100000, 100400)]))
+    # sorted-by-quality inputs: PROSAC finds the model in far fewer draws than uniform sampling
+    d = synthetic.make_correspondences(4000, inlier_ratio=0.1, seed=3)
+    order = np.argsort(~d["is_inlier"], kind="stable")                   # inliers first = perfect quality ranking
+    src, tgt = d["src"][order], d["tgt"][order]
+    a = O.ransac(src, tgt, sampler=O.PROSAC, conf=1.0, max_iters=64, round_size=64, seed=1)
+    b = O.ransac(src, tgt, sampler=O.UNIFORM, conf=1.0, max_iters=64, round_size=64, seed=1)
+    assert a["best_count"] > 300 > b["best_count"]
 
 
 def test_planted_inliers_zero_noise():

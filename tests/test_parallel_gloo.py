@@ -19,7 +19,7 @@ class OracleBackend:
 
     @staticmethod
     def ransac_shard(src, tgt, p, lo, hi, key):
-        samples = np.stack([O.sample(p.seed, h, 0 if p.sampler == 0 else 1, p.sample_size, len(src))
+        samples = np.stack([O.sample(p.seed, h, p.sampler, p.sample_size, len(src))
                             for h in range(lo, hi)]).astype(np.int32)
         counts, best = O.score_samples(src, tgt, samples, p.threshold, bool(p.use_elc), p.elc_ratio)
         if best >= 0:
@@ -30,7 +30,7 @@ class OracleBackend:
         cnt, hid = engine.key_unpack(key)
         T = np.eye(4)
         if cnt > 0:
-            s = O.sample(p.seed, hid, 0 if p.sampler == 0 else 1, p.sample_size, len(src))
+            s = O.sample(p.seed, hid, p.sampler, p.sample_size, len(src))
             T = O.kabsch(src[s].astype(float), tgt[s].astype(float))
         return dict(T=T, best_id=hid, best_count=cnt)
 
