@@ -683,13 +683,24 @@ int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float 
     const int n_rowblocks = (int)((Na + TM - 1) / TM);
     const int n_coltiles = (int)((Nb + TN - 1) / TN);
     const int sms = lr::sm_count();
-    // split the columns only when there are too few row blocks to fill the chip
+    // Persistent CTAs take (row block, column split) items round-robin.  Pick the number of column
+    // splits that wastes the least of the last wave (391 row blocks on 148 SMs: 1 split = 3 waves
+    // for 2.64 waves of work, 3 splits = 8 waves for 7.93); every extra split costs one more
+    // candidate region per row and one more pass over the query tile, hence the small penalty.
+    const int64_t region_cap = region_budget(N > M ? N : M) / (Na * NGROUPS);
     int nsplit = 1;
-    if (n_rowblocks < 2 * sms) nsplit = (2 * sms + n_rowblocks - 1) / n_rowblocks;
-    if (nsplit > n_coltiles) nsplit = n_coltiles;
-    {   // the candidate table holds region_budget() regions
-        const int64_t cap = region_budget(N > M ? N : M) / (Na * NGROUPS);
-        if (nsplit > cap) nsplit = (int)(cap < 1 ? 1 : cap);
+    double best_cost = 1e30;
+    for (int cand_split = 1; cand_split <= 16; ++cand_split) {
+        if (cand_split > n_coltiles || cand_split > region_cap) break;
+        const int tps_c = (n_coltiles + cand_split - 1) / cand_split;
+        const int ns = (n_coltiles + tps_c - 1) / tps_c;
+        const long long items = (long long)n_rowblocks * ns;
+        const long long waves = (items + sms - 1) / sms;
+        const double cost = (double)waves * tps_c * (1.0 + 0.02 * (ns - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            nsplit = ns;
+        }
     }
     const int tps = (n_coltiles + nsplit - 1) / nsplit;
     nsplit = (n_coltiles + tps - 1) / tps;

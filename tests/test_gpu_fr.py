@@ -95,3 +95,16 @@ def test_cli_entry_runs():
                           "--prosac", "False"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "recall 100.00%" in out.stderr + out.stdout
+
+
+def test_batch_metrics_match_oracle_pipeline():
+    """cfg 5 in miniature: RRE / RTE / recall of a batch equal the CPU oracle pipeline's (north star: within 0.1 %)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "eval_pairs.py"), "--pairs", "6", "--points", "3000",
+                          "--iters", "30000"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    assert r["gpu"]["recall"] == r["cpu_oracle"]["recall"] and r["gpu"]["recall"] >= 0.8
+    assert r["max_abs_rotation_entry_diff"] < 1e-5 and r["max_abs_translation_diff_m"] < 1e-4
+    assert abs(r["gpu"]["RRE"] - r["cpu_oracle"]["RRE"]) < 1e-3 * max(r["cpu_oracle"]["RRE"], 1e-6) + 1e-6
+    assert abs(r["gpu"]["RTE"] - r["cpu_oracle"]["RTE"]) < 1e-3 * max(r["cpu_oracle"]["RTE"], 1e-6) + 1e-4
