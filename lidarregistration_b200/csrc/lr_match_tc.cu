@@ -41,7 +41,7 @@ constexpr int A_TILE_BYTES = TM / 8 * RG_BYTES;  // 16 KB
 constexpr int B_TILE_BYTES = TN / 8 * RG_BYTES;  // 32 KB
 constexpr int STAGES = 4;
 constexpr int CAND = 24;                     // candidate slots per (query row, column split, epilogue group)
-constexpr int NGROUPS = 2;                   // epilogue groups of four warps (one TMEM lane quadrant each)
+constexpr int NGROUPS = 4;                   // epilogue groups of four warps (one TMEM lane quadrant each)
 constexpr int NTHREADS = 64 + 128 * NGROUPS; // warp 0 producer, warp 1 MMA, then the epilogue groups
 constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 // A, B = f16 (format 0), both K-major (0), no negate, dense
@@ -68,12 +68,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}" ::"r"(addr), "r"(parity)
-        : "memory");
+        "}" ::"r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint (ns): sleep in hardware instead of
+        : "memory");                                   // burning issue slots the epilogue warps need
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -259,15 +259,36 @@ __device__ unsigned long long g_tc_timing[16];
 #define TC_ACC(var)
 #endif
 
+constexpr int SMAX_BUFS = 4;  // rotating per item; buffer (i + 1) % 4 is reset during item i (last used by item i - 3)
 struct __align__(8) Smem {
     uint64_t a_full[2], a_empty[2], b_full[STAGES], b_empty[STAGES], t_full[2], t_empty[2];
     uint32_t tmem_base;
+    int smax[SMAX_BUFS][TM];  // running maximum (2-NN variant: running second maximum) of every query row of the
+                              // tile, shared by the epilogue groups, as order-preserving integer keys
 };
 
+// float <-> signed integer key with the same ordering (atomicMax on shared memory)
+__device__ __forceinline__ int fkey(float v)
+{
+    const int i = __float_as_int(v);
+    return i >= 0 ? i : (i ^ 0x7fffffff);
+}
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+constexpr int KEY_NEG_INF = (int)(0xff800000u ^ 0x7fffffffu);
+
+// tile sequence of one work item: a short seed phase over tiles spread across the item's range
+// (running maxima only, no candidates) and then the full sweep.  Seeding makes the thresholds
+// tight before the sweep starts: ~ln(columns) prefix-maximum records per row become ~ln(16).
+__device__ __forceinline__ int seed_tiles(int ntl) { return ntl >= 32 ? 8 : 0; }
+__device__ __forceinline__ int tile_at(int sidx, int nseed, int t_lo, int ntl)
+{
+    return sidx < nseed ? t_lo + (int)(((long long)sidx * ntl) / nseed) : t_lo + (sidx - nseed);
+}
+
 // rare path, part 2: append the flagged columns of a 32-column chunk to this thread's private
-// region of the candidate table (one writer per region: register counter, plain stores).  Kept
-// out of line and compact -- the epilogue is instruction-cache sensitive.
-__device__ __noinline__ int push_cols(unsigned mask, int col0, int M, int *__restrict__ slots, int cnt)
+// region of the candidate table (one writer per region: register counter, plain stores).  A
+// compact loop, inlined: an out-of-line call here spills ~150 live registers around the call.
+__device__ __forceinline__ int push_cols(unsigned mask, int col0, int M, int *__restrict__ slots, int cnt)
 {
     while (mask) {
         const int col = col0 + __ffs(mask) - 1;
@@ -298,8 +319,9 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32])
 // threshold is recorded.  The threshold never exceeds (final max - beta), so the recorded set
 // is a superset of the columns the exact re-rank has to see.
 template <bool WANT2>
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float mx, int col0, int M, bool valid, float beta,
-                                           float &m1, float &m2, float &thr, int *__restrict__ slots, int &cnt)
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float mx, int col0, int M, bool valid, bool seed,
+                                           float beta, float shared_base, float &m1, float &m2, float &thr,
+                                           int *__restrict__ slots, int &cnt)
 {
     if (mx > thr) {
         // move the running maxima first: a column of this chunk can only matter if it is within
@@ -311,14 +333,25 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float mx, in
                 m2 = fmaxf(m2, fminf(m1, x));
                 m1 = fmaxf(m1, x);
             }
-            thr = m2 - beta;
+            thr = fmaxf(m2, shared_base) - beta;
         } else {
             m1 = fmaxf(m1, mx);
-            thr = m1 - beta;
+            thr = fmaxf(m1, shared_base) - beta;
         }
-        unsigned mask = 0u;
+        if (seed) return;  // seed phase: thresholds only
+        // Flag the columns above the threshold on the FMA pipe (the epilogue is bound by the 16-lane
+        // ALU pipe, where FMNMX3 / FSETP / LOP3 live): saturate((v - thr) * 2^40) is exactly 1 for
+        // v > thr (the difference of two fp32 values of this magnitude is >= 2^-30) and exactly 0
+        // otherwise; the indicators are packed into two 16-bit fields with exact fp32 FMAs.
+        const float big = 1099511627776.f;  // 2^40
+        const float nthr = -thr * big;
+        float lo16 = 0.f, hi16 = 0.f;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) mask |= (__uint_as_float(v[r]) > thr) ? (1u << r) : 0u;
+        for (int r = 0; r < 16; ++r) {
+            lo16 = fmaf(__saturatef(fmaf(__uint_as_float(v[r]), big, nthr)), (float)(1u << r), lo16);
+            hi16 = fmaf(__saturatef(fmaf(__uint_as_float(v[16 + r]), big, nthr)), (float)(1u << r), hi16);
+        }
+        const unsigned mask = __float2uint_rz(lo16) | (__float2uint_rz(hi16) << 16);
         if (valid) cnt = push_cols(mask, col0, M, slots, cnt);
     }
 }
@@ -357,6 +390,7 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int k = threadIdx.x; k < SMAX_BUFS * TM; k += NTHREADS) (&sm->smax[0][0])[k] = KEY_NEG_INF;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -375,7 +409,9 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 bulk_g2s(sA + ab * A_TILE_BYTES, reinterpret_cast<const uint8_t *>(Aop) + (size_t)rb * A_TILE_BYTES,
                          A_TILE_BYTES, &sm->a_full[ab]);
                 ++a_it;
-                for (int t = t_lo; t < t_hi; ++t) {
+                const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl);
+                for (int sidx = 0; sidx < nseed + ntl; ++sidx) {
+                    const int t = tile_at(sidx, nseed, t_lo, ntl);
                     const int s = b_it % STAGES;
                     mbar_wait(&sm->b_empty[s], ((b_it / STAGES) & 1) ^ 1);
                     mbar_expect_tx(&sm->b_full[s], B_TILE_BYTES);
@@ -403,7 +439,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 const int ab = a_it & 1;
                 mbar_wait(&sm->a_full[ab], (a_it >> 1) & 1);
                 const uint32_t a_addr = smem_u32(sA + ab * A_TILE_BYTES);
-                for (int t = t_lo; t < t_hi; ++t) {
+                const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl);
+                for (int sidx = 0; sidx < nseed + ntl; ++sidx) {
                     const int s = b_it % STAGES;
                     const int acc = t_it & 1;
                     { TC_T0(); mbar_wait(&sm->b_full[s], (b_it / STAGES) & 1); TC_ACC(w_bfull); }
@@ -436,15 +473,15 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         }
     } else {
         // ===== epilogue: TMEM -> registers, running max + candidate collection =====
-        // two epilogue groups of four warps share every tile: group g scans 128 of its 256 columns,
-        // so a tile is drained in half the time and the two accumulator buffers give real double
+        // NGROUPS epilogue groups of four warps share every tile: group g scans 256 / NGROUPS of its
+        // columns, so a tile is drained quickly and the two accumulator buffers give real double
         // buffering against the MMA; a row's running maximum and candidate region are per group
         const int q = warp & 3;            // TMEM lane quadrant this warp may read
-        const int grp = (warp - 2) >> 2;   // 0 or 1
+        const int grp = (warp - 2) >> 2;   // 0 .. NGROUPS-1
         const float beta = params->beta;
-        uint32_t t_it = 0;
-        long long e_wait = 0, e_work = 0, e_ld = 0;
-        (void)e_wait; (void)e_work; (void)e_ld;
+        uint32_t t_it = 0, item_it = 0;
+        long long e_wait = 0, e_work = 0, e_ld = 0, e_max = 0, e_slow = 0;
+        (void)e_wait; (void)e_work; (void)e_ld; (void)e_max; (void)e_slow;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int rb = item / nsplit, cs = item - rb * nsplit;
             const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
@@ -454,43 +491,68 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
             const int64_t region = valid ? (row * nsplit + cs) * NGROUPS + grp : 0;
             int *slots = cand + region * CAND;
             int cnt = 0;
-            for (int t = t_lo; t < t_hi; ++t) {
+            const int rowl = q * 32 + lane;
+            int *my_smax = &sm->smax[item_it % SMAX_BUFS][rowl];
+            if (grp == 0) sm->smax[(item_it + 1) % SMAX_BUFS][rowl] = KEY_NEG_INF;  // for the next item
+            ++item_it;
+            const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl);
+            for (int sidx = 0; sidx < nseed + ntl; ++sidx) {
+                const int t = tile_at(sidx, nseed, t_lo, ntl);
+                const bool seed = sidx < nseed;
+                if (nseed > 0 && sidx == nseed) {
+                    // end of the seed phase: its columns are visited again by the sweep, so the local
+                    // running maxima restart (a revisited column must not count twice towards the
+                    // second maximum); what the seed established lives on in the shared threshold base
+                    const float mine = WANT2 ? m2 : m1;
+                    atomicMax(my_smax, fkey(mine));
+                    m1 = -INFINITY;
+                    m2 = -INFINITY;
+                    thr = -INFINITY;
+                }
                 const int acc = t_it & 1;
                 { TC_T0(); mbar_wait(&sm->t_full[acc], (t_it >> 1) & 1); TC_ACC(e_wait); }
                 tc_fence_after();
                 TC_T0();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TN;
-                // tcgen05.ld is latency-bound (~600 cycles per ld/wait round trip, measured with
-                // tools/micro_b200.cu): keep four 32-column loads in flight per warp and let the two
-                // epilogue groups interleave, which brings TMEM reads to ~100 B/clk/SM
-#ifdef LR_TC_SKIP_EPI
-                if (false)
-#endif
-#pragma unroll 1
-                for (int h = grp; h < TN / 128; h += NGROUPS) {  // with two groups: group g scans columns [128 g, 128 g + 128)
-                    uint32_t va[32], vb[32], vc[32], vd[32];
-                    const uint32_t ta = taddr + h * 128;
+                // every group drains its CPG = 8 / NGROUPS chunks of 32 columns of this tile: all loads
+                // in flight first (tcgen05.ld is latency-bound), then the independent max trees, then
+                // the (rare) candidate paths
+                {
+                    constexpr int CPG = (TN / 32) / NGROUPS;
+                    uint32_t v[CPG][32];
+                    const uint32_t ta = taddr + grp * (CPG * 32);
 #ifdef LR_TC_TIMING
                     const long long tl0 = clock64();
 #endif
-                    tmem_ld32_issue(ta, va);
-                    tmem_ld32_issue(ta + 32, vb);
-                    tmem_ld32_issue(ta + 64, vc);
-                    tmem_ld32_issue(ta + 96, vd);
-                    tmem_ld32_wait(va);
-                    tmem_ld32_wait(vb);
-                    tmem_ld32_wait(vc);
-                    tmem_ld32_wait(vd);
+#pragma unroll
+                    for (int c = 0; c < CPG; ++c) tmem_ld32_issue(ta + c * 32, v[c]);
+#pragma unroll
+                    for (int c = 0; c < CPG; ++c) tmem_ld32_wait(v[c]);
 #ifdef LR_TC_TIMING
                     e_ld += clock64() - tl0;
 #endif
-                    const int col0 = t * TN + h * 128;
-                    // the four max trees are independent: issue them back to back (ILP), then branch
-                    const float xa = max32(va), xb = max32(vb), xc = max32(vc), xd = max32(vd);
-                    scan_chunk<WANT2>(va, xa, col0, (int)M, valid, beta, m1, m2, thr, slots, cnt);
-                    scan_chunk<WANT2>(vb, xb, col0 + 32, (int)M, valid, beta, m1, m2, thr, slots, cnt);
-                    scan_chunk<WANT2>(vc, xc, col0 + 64, (int)M, valid, beta, m1, m2, thr, slots, cnt);
-                    scan_chunk<WANT2>(vd, xd, col0 + 96, (int)M, valid, beta, m1, m2, thr, slots, cnt);
+                    const int col0 = t * TN + grp * (CPG * 32);
+                    float mx[CPG];
+#pragma unroll
+                    for (int c = 0; c < CPG; ++c) mx[c] = max32(v[c]);
+#ifdef LR_TC_TIMING
+                    const long long tm0 = clock64();
+                    e_max += tm0 - tl0;
+#endif
+                    // what the other groups (and the seed phase) have established for this row
+                    const float shared_base = fkey_inv(*reinterpret_cast<volatile int *>(my_smax));
+                    thr = fmaxf(thr, shared_base - beta);
+#pragma unroll
+                    for (int c = 0; c < CPG; ++c)
+                        scan_chunk<WANT2>(v[c], mx[c], col0 + c * 32, (int)M, valid, seed, beta, shared_base, m1, m2, thr,
+                                          slots, cnt);
+                    // publish this thread's running maximum (2-NN: running second maximum): any group's value
+                    // is a lower bound of the row's true one, so thresholds derived from it stay safe
+                    const float mine = WANT2 ? m2 : m1;
+                    if (mine > shared_base) atomicMax(my_smax, fkey(mine));
+#ifdef LR_TC_TIMING
+                    e_slow += clock64() - tm0;
+#endif
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -505,6 +567,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
             atomicAdd(&g_tc_timing[5], (unsigned long long)e_wait);
             atomicAdd(&g_tc_timing[6], (unsigned long long)e_work);
             atomicAdd(&g_tc_timing[7], (unsigned long long)e_ld);
+            atomicAdd(&g_tc_timing[8], (unsigned long long)e_max);
+            atomicAdd(&g_tc_timing[9], (unsigned long long)e_slow);
         }
 #endif
     }
@@ -685,8 +749,8 @@ int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float 
     const int sms = lr::sm_count();
     // Persistent CTAs take (row block, column split) items round-robin.  Pick the number of column
     // splits that wastes the least of the last wave (391 row blocks on 148 SMs: 1 split = 3 waves
-    // for 2.64 waves of work, 3 splits = 8 waves for 7.93); every extra split costs one more
-    // candidate region per row and one more pass over the query tile, hence the small penalty.
+    // for 2.64 waves of work, 3 splits = 8 waves for 7.93); every extra split restarts the running
+    // maxima (ln(columns) more candidates per row, more slow-path visits), hence the penalty.
     const int64_t region_cap = region_budget(N > M ? N : M) / (Na * NGROUPS);
     int nsplit = 1;
     double best_cost = 1e30;
@@ -696,7 +760,7 @@ int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float 
         const int ns = (n_coltiles + tps_c - 1) / tps_c;
         const long long items = (long long)n_rowblocks * ns;
         const long long waves = (items + sms - 1) / sms;
-        const double cost = (double)waves * tps_c * (1.0 + 0.02 * (ns - 1));
+        const double cost = (double)waves * tps_c * (1.0 + 0.12 * (ns - 1));
         if (cost < best_cost) {
             best_cost = cost;
             nsplit = ns;
@@ -738,7 +802,7 @@ void timing_dump()
     cudaMemcpyFromSymbol(h, g_tc_timing, sizeof(h));
     const double t = (double)(h[4] ? h[4] : 1);
     fprintf(stderr, "[tc timing] tiles %llu | MMA per tile: wait b_full %.0f, wait t_empty %.0f, issue %.0f, total %.0f | "
-            "epilogue per tile: wait t_full %.0f, work %.0f (of which tcgen05.ld+wait %.0f)\n", h[4], h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[5] / t, h[6] / t, h[7] / t);
+            "epilogue per tile: wait t_full %.0f, work %.0f (tcgen05.ld+wait %.0f, ld..max %.0f, compare+slow %.0f)\n", h[4], h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[5] / t, h[6] / t, h[7] / t, h[8] / t, h[9] / t);
     memset(h, 0, sizeof(h));
     cudaMemcpyToSymbol(g_tc_timing, h, sizeof(h));
 }
