@@ -531,6 +531,11 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
 #ifdef LR_TC_TIMING
                     e_ld += clock64() - tl0;
 #endif
+                    // the accumulator now lives in registers: hand the TMEM buffer back to the MMA warp
+                    // BEFORE scanning, so the next tile's MMA overlaps this tile's epilogue
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm->t_empty[acc]);
                     const int col0 = t * TN + grp * (CPG * 32);
                     float mx[CPG];
 #pragma unroll
@@ -554,9 +559,6 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                     e_slow += clock64() - tm0;
 #endif
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm->t_empty[acc]);
                 TC_ACC(e_work);
                 ++t_it;
             }
