@@ -98,19 +98,27 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
 
     # 3. Perform RANSAC
     if args.codebase == "GC":
-        A_ = xyz0_np[corres_idx0, :].astype(np.float32)
-        B_ = xyz1_np[corres_idx1, :].astype(np.float32)
+        # Same steps as the reference (FR.py:70-87 -> GC_RANSAC.py:8-55): gather the filtered
+        # correspondences, PROSAC quality = -ratio, sort best first, native call, None -> identity.
+        # Everything stays in HBM: the gathers, the ratio and the (stable) sort run on the device and
+        # lr_ransac_rigid is called directly instead of round-tripping through numpy.
+        src = engine.gather_xyz(xyz0.detach(), corres_idx0)
+        tgt = engine.gather_xyz(xyz1.detach(), corres_idx1)
         if args.prosac:
             if mode == 'GPF':
-                feat_dist = norm_feat_dist.detach().cpu().numpy()
+                feat_dist = engine.to_dev_f32(norm_feat_dist)
             else:
-                feat_dist = calc_distance_ratio_in_feature_space(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
-                                                                 idx1_2nd).detach().cpu().numpy()
-            match_quality = -feat_dist
-        else:
-            match_quality = None
-        T, _ = GC_RANSAC(A_, B_, distance_threshold=2 * voxel_size, num_iterations=ransac_iters, args=args,
-                         match_quality=match_quality)
+                feat_dist = engine.match_ratio(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd)
+            order = torch.argsort(feat_dist, stable=True)  # == argsort(-match_quality), match_quality = -ratio
+            src, tgt = src[order].contiguous(), tgt[order].contiguous()
+        if args.fast_rejection == "SPRT":
+            raise NotImplementedError("SPRT pre-verification is not part of the B200 hot path (use ELC or NONE)")
+        params = engine.make_params(threshold=2 * voxel_size, confidence=args.GC_conf, max_iters=ransac_iters,
+                                    seed=getattr(args, "seed", 51), sample_size=3,
+                                    sampler=engine.SAMPLER_PROSAC if args.prosac else engine.SAMPLER_UNIFORM,
+                                    use_elc=args.fast_rejection != "NONE", elc_ratio=0.9, refit=True)
+        res = engine.ransac_rigid(src, tgt, params)
+        T = res["T_refit"] if res["best_count"] > 0 else np.eye(4)
 
     elif args.codebase == "open3D":
         T = RANSAC_registration(pcd0, pcd1, corres_idx0, corres_idx1, 2 * voxel_size, num_iterations=ransac_iters,

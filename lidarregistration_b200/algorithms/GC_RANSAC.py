@@ -60,7 +60,7 @@ def GC_RANSAC(A, B, distance_threshold, num_iterations, args, match_quality):
         'neighborhood_size': 20,
     }
     if args.prosac:
-        order = np.argsort(-match_quality)  # best quality first
+        order = np.argsort(-match_quality, kind="stable")  # best quality first
         x1y1z1_ = x1y1z1_[order, :]
         x2y2z2_ = x2y2z2_[order, :]
 

@@ -108,3 +108,26 @@ def test_batch_metrics_match_oracle_pipeline():
     assert r["max_abs_rotation_entry_diff"] < 1e-5 and r["max_abs_translation_diff_m"] < 1e-4
     assert abs(r["gpu"]["RRE"] - r["cpu_oracle"]["RRE"]) < 1e-3 * max(r["cpu_oracle"]["RRE"], 1e-6) + 1e-6
     assert abs(r["gpu"]["RTE"] - r["cpu_oracle"]["RTE"]) < 1e-3 * max(r["cpu_oracle"]["RTE"], 1e-6) + 1e-4
+
+
+def test_cfg1_20k_pair_50k_iters_equals_oracle_pipeline():
+    """BASELINE.json cfg 1: --algo RANSAC --mode MMN --iters 50000 on one synthetic 20k-point pair,
+    both codebases, against the CPU oracle pipeline on the same inputs."""
+    p = synthetic.make_pair(20000, seed=51 + 1000, overlap=0.5)
+    t = tensors(p)
+    _, o1, o2 = O.find_nn(p["feat0"], p["feat1"], return_2nd=True)
+    mi, mj = O.nn_to_mutual(p["feat0"], p["feat1"], o1)
+    # GC codebase (default): PROSAC order by ratio, ELC, conf 0.9995, refit
+    q = O.ratio(p["feat0"], p["feat1"], mi, mj, o2[mi])
+    order = np.argsort(q, kind="stable")
+    ref = O.ransac(p["xyz0"][mi][order], p["xyz1"][mj][order], m=3, sampler=O.PROSAC, use_elc=True, thr=0.6, conf=0.9995,
+                   max_iters=50000, round_size=65536, seed=51)
+    T = FR(*t, make_args(mode="MMN", iters=50000, codebase="GC", prosac=True, GC_conf=0.9995), p["T_gt"])[0]
+    assert np.abs(T - ref["T_refit"]).max() < 1e-5
+    # Open3D codebase: ransac_n = 4 with replacement, conf 0.9995, refit on the unfiltered NN inliers
+    ref4 = O.ransac(p["xyz0"][mi], p["xyz1"][mj], m=4, sampler=O.REPLACE, use_elc=True, thr=0.6, conf=0.9995,
+                    max_iters=50000, round_size=65536, seed=51)
+    Tref, _ = O.refit_indexed(p["xyz0"], p["xyz1"], np.arange(20000), o1, ref4["T"], 0.6)
+    T4 = FR(*t, make_args(mode="MMN", iters=50000, codebase="open3D"), p["T_gt"])[0]
+    assert np.abs(T4[:3, :3] - Tref[:3, :3]).max() < 1e-5 and np.abs(T4[:3, 3] - Tref[:3, 3]).max() < 1e-4
+    assert metrics.registration_success(T, p["T_gt"]) and metrics.registration_success(T4, p["T_gt"])

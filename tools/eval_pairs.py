@@ -29,7 +29,7 @@ def oracle_fr(d, iters, conf, prosac):
     sampler = O.UNIFORM
     if prosac:
         q = -O.ratio(d["feat0"], d["feat1"], m0, m1, i2[m0])
-        order = np.argsort(-q)
+        order = np.argsort(-q, kind="stable")
         A, B = A[order], B[order]
         sampler = O.PROSAC
     r = O.ransac(A, B, m=3, sampler=sampler, use_elc=True, thr=0.6, conf=conf, max_iters=iters, round_size=65536, seed=51)
