@@ -282,7 +282,11 @@ def run_ours(args):
             "peak_source": "FFMA probe measured in this run (lr_peak_fp32 mode 0); packed fma.rn.f32x2 probe: "
                            "%.1f TFLOP/s; nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f" %
                            (peak2, clocks["sm_max_mhz"] or 1965, 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965) / 1e6),
-            "traffic": None, "avg_launch_ms": avg_ms, "launches": score_launches,
+            "traffic": ncu_traffic("r1_ncu_k_score.txt"),
+            "traffic_note": "DRAM bytes of one ncu --set full launch (profiles/r1_ncu_k_score.txt); the kernel is not "
+                            "memory bound: algorithmic bytes per launch = n x 48 B of correspondences + H_scored x 64 B of "
+                            "models",
+            "avg_launch_ms": avg_ms, "launches": score_launches,
             "share_of_step": score_ms / (ms_res * args.steps) if ms_res else None,
             "gen_share_of_step": gen_ms / (ms_res * args.steps) if ms_res else None,
             "algorithmic_flops_per_launch": flops_per_launch}
@@ -301,6 +305,19 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(summary):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) from a committed ncu summary, else None"""
+    try:
+        tot, unit = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(os.path.join(ROOT, "profiles", summary)):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * unit.get(f[2], 1.0)
+        return tot or None
+    except Exception:
+        return None
 
 
 def bench_other_regime(engine, torch, resident, use_elc):
@@ -376,8 +393,8 @@ def bench_matching(engine, torch, dev):
             "mutual_pairs": int(mi.shape[0]), "sweep_ms": nn_ms / max(nn_l, 1),
             "roofline": {"kernel": "k_nn_tc (tcgen05 fp16 -> fp32 sweep + exact fp32 re-rank)", "bound": "tensor", "achieved": ach,
                          "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if ach else None,
-                         "peak_source": "bf16_tflops of MEASURED_PEAKS.json" if peaks else "fallback 1590",
-                         "traffic": None}}
+                         "peak_source": "bf16_tflops of MEASURED_PEAKS.json (burst)" if peaks else "fallback 1590",
+                         "traffic": ncu_traffic("r1_ncu_k_nn_tc.txt")}}
 
 
 def main():
