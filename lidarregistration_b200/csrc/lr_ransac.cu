@@ -533,6 +533,15 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+// same instruction, but `volatile`: ptxas keeps these in source order, which is written so that
+// three consecutive FMAs share their B operand (register-reuse cache; tools/micro_ffma2.cu:
+// 100 instead of 87 FMA/clk/SM)
+__device__ __forceinline__ u64 fma2v(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 __device__ __forceinline__ u64 add2(u64 a, u64 b)
 {
     u64 d;
@@ -656,15 +665,27 @@ k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *_
             const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&sP[buf][0]);
 #pragma unroll 2
             for (int i = 0; i < kChunk; i += kGroup) {
+                // two points at a time; for each coordinate the three rows' FMAs are issued back to
+                // back so they share the point operand (z, then y, then x)
 #pragma unroll
-                for (int g = 0; g < kGroup; ++g) {
-                    const ulonglong2 A = sp[3 * (i + g) + 0], B = sp[3 * (i + g) + 1], C = sp[3 * (i + g) + 2];
-                    u64 d0 = add2(fma2(R00, A.x, fma2(R01, A.y, fma2(R02, B.x, T0))), B.y);
-                    u64 d1 = add2(fma2(R10, A.x, fma2(R11, A.y, fma2(R12, B.x, T1))), C.x);
-                    u64 d2 = add2(fma2(R20, A.x, fma2(R21, A.y, fma2(R22, B.x, T2))), C.y);
-                    u64 rr = fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
+                for (int g = 0; g < kGroup; g += 2) {
+                    const ulonglong2 A0 = sp[3 * (i + g) + 0], B0 = sp[3 * (i + g) + 1], C0 = sp[3 * (i + g) + 2];
+                    const ulonglong2 A1 = sp[3 * (i + g) + 3], B1 = sp[3 * (i + g) + 4], C1 = sp[3 * (i + g) + 5];
+                    u64 p0 = fma2v(R02, B0.x, T0), p1 = fma2v(R12, B0.x, T1), p2 = fma2v(R22, B0.x, T2);
+                    u64 s0 = fma2v(R02, B1.x, T0), s1 = fma2v(R12, B1.x, T1), s2 = fma2v(R22, B1.x, T2);
+                    p0 = fma2v(R01, A0.y, p0); p1 = fma2v(R11, A0.y, p1); p2 = fma2v(R21, A0.y, p2);
+                    s0 = fma2v(R01, A1.y, s0); s1 = fma2v(R11, A1.y, s1); s2 = fma2v(R21, A1.y, s2);
+                    p0 = fma2v(R00, A0.x, p0); p1 = fma2v(R10, A0.x, p1); p2 = fma2v(R20, A0.x, p2);
+                    s0 = fma2v(R00, A1.x, s0); s1 = fma2v(R10, A1.x, s1); s2 = fma2v(R20, A1.x, s2);
+                    p0 = add2(p0, B0.y); p1 = add2(p1, C0.x); p2 = add2(p2, C0.y);
+                    s0 = add2(s0, B1.y); s1 = add2(s1, C1.x); s2 = add2(s2, C1.y);
+                    const u64 rr0 = fma2(p2, p2, fma2(p1, p1, mul2(p0, p0)));
+                    const u64 rr1 = fma2(s2, s2, fma2(s1, s1, mul2(s0, s0)));
                     float ra, rb;
-                    upk2(rr, ra, rb);
+                    upk2(rr0, ra, rb);
+                    count2(ra, loA, hiA, loCntA, hiCntA);
+                    count2(rb, loB, hiB, loCntB, hiCntB);
+                    upk2(rr1, ra, rb);
                     count2(ra, loA, hiA, loCntA, hiCntA);
                     count2(rb, loB, hiB, loCntB, hiCntB);
                 }

@@ -123,3 +123,21 @@ def test_candidate_overflow_falls_back_to_exact_scan():
     _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
     assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2)
     assert np.all(o1[20:30] == 1000) and np.all(o2[20:30] == 1001)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tiny_shapes(mode):
+    engine.match_set_mode(mode)
+    try:
+        rng = np.random.default_rng(1)
+        for (N, M) in [(1, 1), (1, 5), (7, 1), (2, 2), (128, 256), (129, 257)]:
+            f0 = rng.standard_normal((N, 32)).astype(np.float32)
+            f1 = rng.standard_normal((M, 32)).astype(np.float32)
+            i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+            _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
+            assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2), (N, M)
+            mi, mj = engine.match_mutual(f0, f1, i1)
+            oi, oj = O.nn_to_mutual(f0, f1, o1)
+            assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mj.cpu().numpy(), oj), (N, M)
+    finally:
+        engine.match_set_mode(0)
