@@ -13,9 +13,14 @@
 //              4-stage ring of 256-row target tiles, double-buffered 128-row query tile
 //   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N 256, K 16) x 3
 //              into one of two 256-column fp32 accumulators in TMEM
-//   epilogue   4 warps read their TMEM lane quadrant with tcgen05.ld.32x32b.x32; a thread owns a
-//              query row, keeps its running maximum and collects every column whose v is within
-//              `beta` of it (3-input FMNMX tree per 32 columns, one compare, rare slow path)
+//   epilogue   four groups of 4 warps (one TMEM lane quadrant each) share every tile, 64 columns
+//              per group: tcgen05.ld.32x32b.x32 x2, the TMEM buffer is released as soon as the
+//              values are in registers, then a 3-input FMNMX tree per 32 columns and one compare.
+//              A thread owns a query row; when a chunk reaches the row's threshold the columns
+//              within `beta` of the running maximum are appended to the thread's private
+//              candidate region (mask built with saturating FMAs, no atomics).  The running
+//              maximum of a row is shared by the groups through shared memory, and every work
+//              item starts with a short seed phase (maxima only) so thresholds are tight early.
 //
 // `beta` bounds the fp16/tensor-core error, so the collected set provably contains the argmin
 // of the reference's fp32 expression; k_rerank then evaluates that expression exactly (same
@@ -28,8 +33,8 @@
 
 namespace lr_tc {
 
-static inline float __uint_as_float_host(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 #ifdef LR_TC_TIMING
+static inline float __uint_as_float_host(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 extern Prepared g_last; extern int g_last_regions; extern int64_t g_last_rows;
 #endif
 

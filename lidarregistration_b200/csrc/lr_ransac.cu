@@ -520,12 +520,6 @@ __device__ __forceinline__ void cp_async_wait()
 
 typedef unsigned long long u64;
 
-__device__ __forceinline__ u64 pk2(float a, float b)
-{
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
 __device__ __forceinline__ void upk2(u64 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
 {
