@@ -634,6 +634,8 @@ k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *_
         float loA, loB, hiA, hiB;
         upk2(q6.x, loA, loB);
         upk2(q6.y, hiA, hiB);
+        if (!vA) loA = hiA = -1.f;  // slots past the survivor count hold stale models: count nothing
+        if (!vB) loB = hiB = -1.f;
         // running #(rr < lo), #(rr < hi) per hypothesis; their difference grows only when a residual
         // lands inside the error band, which sends the group to the fp64 recheck
         int loCntA = 0, hiCntA = 0, loCntB = 0, hiCntB = 0, seenA = 0, seenB = 0, exactA = 0, exactB = 0;
@@ -934,22 +936,23 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
 {
     ws.n_pad = ((n + kChunk - 1) / kChunk) * kChunk;
     if (ws.n_pad == 0) ws.n_pad = kChunk;
+    // the sweep walks slots in blocks of kHypPerItem: size the per-slot arrays for the padded count
+    const int64_t slots = round + kHypPerItem;
     size_t bytes = lr::padded(sizeof(Ctl)) + lr::padded(sizeof(float4) * 3 * ws.n_pad) +
-                   lr::padded(sizeof(int32_t) * 4 * round) +
-                   lr::padded(sizeof(uint32_t) * round) + lr::padded(sizeof(float4) * 4 * (round + kHypPerItem)) +
-                   lr::padded(sizeof(double) * 12 * round) + lr::padded(sizeof(int) * round) +
-                   lr::padded(sizeof(int) * (nrounds + 1)) + lr::padded(sizeof(double) * 16) +
-                   lr::padded(sizeof(uint32_t) * (prosac ? n : 1));
+                   lr::padded(sizeof(int32_t) * 4 * slots) + lr::padded(sizeof(uint32_t) * slots) +
+                   lr::padded(sizeof(float4) * 4 * slots) + lr::padded(sizeof(double) * 12 * slots) +
+                   lr::padded(sizeof(int) * slots) + lr::padded(sizeof(int) * (nrounds + 1)) +
+                   lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1));
     void *base = lr::arena_get(lr::SLOT_RANSAC, bytes);
     if (!base) return LR_ERR_ALLOC;
     lr::Carver cv(base);
     ws.ctl = cv.take<Ctl>(1);
     ws.P12 = cv.take<float4>(3 * ws.n_pad);
-    ws.samp = cv.take<int32_t>(4 * round);
-    ws.slot_id = cv.take<uint32_t>(round);
-    ws.m32 = cv.take<float4>(4 * (round + kHypPerItem));
-    ws.m64 = cv.take<double>(12 * round);
-    ws.cnt = cv.take<int>(round);
+    ws.samp = cv.take<int32_t>(4 * slots);
+    ws.slot_id = cv.take<uint32_t>(slots);
+    ws.m32 = cv.take<float4>(4 * slots);
+    ws.m64 = cv.take<double>(12 * slots);
+    ws.cnt = cv.take<int>(slots);
     ws.need = cv.take<int>(nrounds + 1);
     ws.scratchT = cv.take<double>(16);
     ws.growth = prosac ? cv.take<uint32_t>(n) : nullptr;
