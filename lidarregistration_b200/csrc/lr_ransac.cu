@@ -619,6 +619,8 @@ k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *_
     nps = (nchunks + cpp - 1) / cpp;
     const int nitems = nhb * nps;
     unsigned long long *n_rechecked = reinterpret_cast<unsigned long long *>(&ctl->n_rechecked);
+    int buf = 0;             // staging buffer of the chunk about to be consumed (runs across items)
+    bool prefetched = false;  // the first chunk of this item was staged during the previous item's last chunk
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int hb = item / nps, ps = item - hb * nps;
@@ -648,14 +650,21 @@ k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *_
             cp_async_commit();
         };
 
-        stage(c_lo, 0);
+        if (!prefetched) stage(c_lo, buf);
         for (int c = c_lo; c < c_hi; ++c) {
-            const int buf = (c - c_lo) & 1;
             if (c + 1 < c_hi) {
                 stage(c + 1, buf ^ 1);
                 cp_async_wait<1>();
             } else {
-                cp_async_wait<0>();
+                // last chunk of the item: stage the first chunk of this CTA's next item behind it
+                const int nxt = item + gridDim.x;
+                prefetched = nxt < nitems;
+                if (prefetched) {
+                    stage((nxt - (nxt / nps) * nps) * cpp, buf ^ 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
             }
             __syncthreads();
             const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(&sP[buf][0]);
@@ -695,6 +704,7 @@ k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *_
                 }
             }
             __syncthreads();
+            buf ^= 1;
         }
         const int cntA = loCntA + exactA, cntB = loCntB + exactB;
         if (nps == 1) {
