@@ -93,7 +93,27 @@ def kabsch_cases():
     print("kabsch_ref.npz:", len(ks), "cases")
 
 
+def gpf_case():
+    """--mode GPF (matching.py:100-205) on an FCGF-shaped pair, RANSAC variant (BB_first=False)."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(53)
+    N, M, D = 3000, 3200, 32
+    f0 = unit(rng.standard_normal((N, D)))
+    f1 = unit(rng.standard_normal((M, D)))
+    f1[:1800] = unit(f0[:1800] + 0.1 * rng.standard_normal((1800, D)).astype(np.float32))
+    xyz0 = rng.uniform(-60, 60, (N, 3)).astype(np.float32)
+    xyz0[:, 2] = rng.uniform(-2, 4, N)
+    t0, t1 = torch.from_numpy(f0), torch.from_numpy(f1)
+    i0, i1, i2 = RM.find_nn(t0, t1, return_2nd=True)
+    args = SimpleNamespace(GPF_factor=2.0, GPF_grid_wid=10, GPF_max_matches=10 ** 9)
+    k0, k1, k2, o0, o1, o2, nfd = RM.Grid_Prioritized_Filter(t0, t1, i0, i1, i2, torch.from_numpy(xyz0), args)
+    np.savez_compressed(os.path.join(OUT, "gpf_ref.npz"), f0=f0, f1=f1, xyz0=xyz0, keep0=k0.numpy(), keep1=k1.numpy(),
+                        keep2=k2.numpy(), nfd=nfd.numpy())
+    print("gpf_ref.npz:", len(k0), "of", N, "pairs kept")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     matching_cases()
     kabsch_cases()
+    gpf_case()
