@@ -100,7 +100,7 @@ def gpf_case():
     N, M, D = 3000, 3200, 32
     f0 = unit(rng.standard_normal((N, D)))
     f1 = unit(rng.standard_normal((M, D)))
-    f1[:1800] = unit(f0[:1800] + 0.1 * rng.standard_normal((1800, D)).astype(np.float32))
+    f1[:600] = unit(f0[:600] + 0.1 * rng.standard_normal((600, D)).astype(np.float32))  # few best buddies: the filter bites
     xyz0 = rng.uniform(-60, 60, (N, 3)).astype(np.float32)
     xyz0[:, 2] = rng.uniform(-2, 4, N)
     t0, t1 = torch.from_numpy(f0), torch.from_numpy(f1)
