@@ -105,7 +105,7 @@ def gpf_case():
     xyz0[:, 2] = rng.uniform(-2, 4, N)
     t0, t1 = torch.from_numpy(f0), torch.from_numpy(f1)
     i0, i1, i2 = RM.find_nn(t0, t1, return_2nd=True)
-    args = SimpleNamespace(GPF_factor=2.0, GPF_grid_wid=10, GPF_max_matches=10 ** 9)
+    args = SimpleNamespace(GPF_factor=0.5, GPF_grid_wid=10, GPF_max_matches=10 ** 9)  # phi < 1 so the quota bites
     k0, k1, k2, o0, o1, o2, nfd = RM.Grid_Prioritized_Filter(t0, t1, i0, i1, i2, torch.from_numpy(xyz0), args)
     np.savez_compressed(os.path.join(OUT, "gpf_ref.npz"), f0=f0, f1=f1, xyz0=xyz0, keep0=k0.numpy(), keep1=k1.numpy(),
                         keep2=k2.numpy(), nfd=nfd.numpy())

@@ -140,8 +140,9 @@ def test_gpf_matches_reference_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "gpf_ref.npz"))
     f0, f1, xyz0 = torch.from_numpy(g["f0"]), torch.from_numpy(g["f1"]), torch.from_numpy(g["xyz0"])
     i0, i1, i2 = find_nn(f0, f1, return_2nd=True)
-    args = make_args()
+    args = make_args(GPF_factor=0.5)  # as in make_golden.py: the per-cell quota has to select
     k0, k1, k2, o0, o1, o2, nfd = Grid_Prioritized_Filter(f0, f1, i0, i1, i2, xyz0, args)
+    assert 0 < len(k0) < len(i0)
     assert torch.equal(o0, i0) and torch.equal(o1, i1)
     ref = set(zip(g["keep0"].tolist(), g["keep1"].tolist()))
     got = set(zip(k0.tolist(), k1.tolist()))
