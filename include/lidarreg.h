@@ -158,6 +158,19 @@ int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t id_lo, int
 int lr_refit_indexed(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1, int64_t K,
                      const double *T_in, double threshold, double *T_out, int64_t *count, void *stream);
 
+/* ---- ICP refinement, SURVEY 8(f4) (Experiments/test.py:183-188: open3d registration_icp,
+ * point-to-point, 0.6 m) composed from the path's own kernels ------------------------------ */
+
+/* out[n,8] = (fp32(T_in * xyz[i]), 0, 0, 0, 0, 0): rows for a 3-D nearest-neighbour search with
+ * lr_match_nn(..., D = 8).  T_in[16] [host]. */
+int lr_transform_pad8(const float *xyz, int64_t n, const double *T_in, float *out, void *stream);
+
+/* One ICP update: over the pairs (xyz0[i0[k]], xyz1[i1[k]]) (i0 nullable = identity) keep those with
+ * |T_in p - q| < threshold, return their count, the sum of their squared residuals under T_in and
+ * the Kabsch transform of the kept pairs.  [host] outputs.  Synchronises `stream`. */
+int lr_icp_step(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1, int64_t K,
+                const double *T_in, double threshold, double *T_out, int64_t *count, double *err2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

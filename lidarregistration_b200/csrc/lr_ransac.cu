@@ -47,6 +47,7 @@ struct Ctl {
     double T[12], Tref[12];
     double csum[6];
     double H[9];
+    double err2;  // sum of squared residuals over the inliers (ICP rmse)
 };
 
 struct Ws {
@@ -782,6 +783,7 @@ __global__ void k_model_from_key(const float *__restrict__ src, const float *__r
 #pragma unroll
     for (int k = 0; k < 12; ++k) ctl->T[k] = T[k];
     ctl->refit_count = 0;
+    ctl->err2 = 0.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) ctl->csum[k] = 0.0;
 #pragma unroll
@@ -827,14 +829,17 @@ k_mask_sums(const float *__restrict__ a, const float *__restrict__ b, const int6
 #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = ctl->T[k];
     double s[6] = {0, 0, 0, 0, 0, 0};
+    double e2 = 0.0;
     int cnt = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double p[3], q[3];
         fetch_pair(a, b, ia, ib, i, p, q);
-        bool in = res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]) < thr2;
+        const double r2 = res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]);
+        bool in = r2 < thr2;
         if (mask) mask[i] = in ? 1 : 0;
         if (in) {
             ++cnt;
+            e2 += r2;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 s[c] += p[c];
@@ -849,6 +854,8 @@ k_mask_sums(const float *__restrict__ a, const float *__restrict__ b, const int6
     }
     double c = block_sum((double)cnt, sh);
     if (threadIdx.x == 0 && c != 0.0) atomicAdd((unsigned long long *)&ctl->refit_count, (unsigned long long)c);
+    double e = block_sum(e2, sh);
+    if (threadIdx.x == 0 && e != 0.0) atomicAdd(&ctl->err2, e);
 }
 
 // pass 2: centred cross-covariance over the inliers
@@ -913,8 +920,26 @@ __global__ void k_set_T(Ctl *ctl, const double *T12)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int k = 0; k < 12; ++k) ctl->T[k] = T12[k];
     ctl->refit_count = 0;
+    ctl->err2 = 0.0;
     for (int k = 0; k < 6; ++k) ctl->csum[k] = 0.0;
     for (int k = 0; k < 9; ++k) ctl->H[k] = 0.0;
+}
+
+// out[i, 0:3] = fp32(R p_i + t) (canonical fp64 order), out[i, 3:8] = 0: the 8-wide rows the exact
+// nearest-neighbour sweep (lr_match_nn, D = 8) searches in 3-D
+__global__ void k_transform_pad8(const float *__restrict__ xyz, int64_t n, const double *__restrict__ T12,
+                                 float *__restrict__ out)
+{
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = xyz[3 * i], py = xyz[3 * i + 1], pz = xyz[3 * i + 2];
+    float4 lo, hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    lo.x = (float)(((T12[0] * px + T12[1] * py) + T12[2] * pz) + T12[3]);
+    lo.y = (float)(((T12[4] * px + T12[5] * py) + T12[6] * pz) + T12[7]);
+    lo.z = (float)(((T12[8] * px + T12[9] * py) + T12[10] * pz) + T12[11]);
+    lo.w = 0.f;
+    reinterpret_cast<float4 *>(out)[2 * i] = lo;
+    reinterpret_cast<float4 *>(out)[2 * i + 1] = hi;
 }
 
 template <int M>
@@ -1302,6 +1327,58 @@ LR_EXPORT int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t 
     else
         k_sample_only<4><<<blocks, 256, 0, st>>>(params->seed, params->sampler, n, ws.growth, id_lo, H, samples);
     LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+LR_EXPORT int lr_transform_pad8(const float *xyz, int64_t n, const double *T_in, float *out, void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(xyz && T_in && out && n >= 0, "bad arguments");
+    if (n == 0) return LR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws;
+    int rc = ws_setup(1, 1, 1, ws);
+    if (rc) return rc;
+    double T12[12];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) T12[4 * r + c] = T_in[4 * r + c];
+    LR_CUDA_TRY(cudaMemcpyAsync(ws.scratchT, T12, sizeof(T12), cudaMemcpyHostToDevice, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));  // T12 is a local
+    k_transform_pad8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, n, ws.scratchT, out);
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+LR_EXPORT int lr_icp_step(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1, int64_t K,
+                          const double *T_in, double threshold, double *T_out, int64_t *count, double *err2, void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(xyz0 && xyz1 && T_in && T_out, "null pointer");
+    LR_REQUIRE(K >= 0 && threshold > 0.0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws;
+    int rc = ws_setup(1, 1, 1, ws);
+    if (rc) return rc;
+    double T12[12];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) T12[4 * r + c] = T_in[4 * r + c];
+    LR_CUDA_TRY(cudaMemcpyAsync(ws.scratchT, T12, sizeof(T12), cudaMemcpyHostToDevice, st));
+    k_set_T<<<1, 32, 0, st>>>(ws.ctl, ws.scratchT);
+    if (K > 0) {
+        int blocks = (int)((K + 255) / 256);
+        if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
+        const double thr2 = threshold * threshold;
+        k_mask_sums<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl, nullptr);
+        k_refit_H<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl);
+    }
+    k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
+    LR_CUDA_TRY(cudaGetLastError());
+    Ctl h;
+    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    T12_to_16(h.Tref, T_out);
+    if (count) *count = h.refit_count;
+    if (err2) *err2 = h.err2;
     return LR_OK;
 }
 

@@ -229,3 +229,28 @@ def peak_fp32(mode=0):
 def match_set_mode(mode):
     """0 = tensor-core sweep + exact re-rank (D == 32, default); 1 = exact CUDA-core sweep."""
     _lib.check(_lib.lib().lr_match_set_mode(int(mode)), "lr_match_set_mode")
+
+
+# --------------------------------------------------------------------- ICP
+def transform_pad8(xyz, T):
+    """lr_transform_pad8 -> [n, 8] fp32 rows (T * xyz, zero padded) for a 3-D lr_match_nn(D = 8)"""
+    xyz = to_dev_f32(xyz)
+    n = xyz.shape[0]
+    out = torch.empty((n, 8), dtype=torch.float32, device=xyz.device)
+    Tin = (ctypes.c_double * 16)(*np.asarray(T, dtype=np.float64).reshape(-1))
+    rc = _lib.lib().lr_transform_pad8(_lib.ptr(xyz), ctypes.c_int64(n), Tin, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "lr_transform_pad8")
+    return out
+
+
+def icp_step(xyz0, xyz1, i1, T, threshold):
+    """lr_icp_step over the pairs (xyz0[k], xyz1[i1[k]]) -> (T_new, inlier count, sum of squared residuals)"""
+    xyz0, xyz1, i1 = to_dev_f32(xyz0), to_dev_f32(xyz1), to_dev_i64(i1)
+    Tin = (ctypes.c_double * 16)(*np.asarray(T, dtype=np.float64).reshape(-1))
+    Tout = (ctypes.c_double * 16)()
+    cnt, err2 = ctypes.c_int64(0), ctypes.c_double(0.0)
+    rc = _lib.lib().lr_icp_step(_lib.ptr(xyz0), _lib.ptr(xyz1), None, _lib.ptr(i1), ctypes.c_int64(i1.shape[0]), Tin,
+                                ctypes.c_double(threshold), Tout, ctypes.byref(cnt), ctypes.byref(err2),
+                                _lib.stream_ptr())
+    _lib.check(rc, "lr_icp_step")
+    return _lib.T_from16(Tout), int(cnt.value), float(err2.value)

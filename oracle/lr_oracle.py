@@ -216,3 +216,40 @@ def refit_indexed(xyz0, xyz1, i0, i1, T, thr):
     k = lib().lro_refit_indexed(_p(xyz0, c_f32p), _p(xyz1, c_f32p), _p(i0, c_i64p), _p(i1, c_i64p),
                                 ctypes.c_int64(len(i0)), _p(T12, c_f64p), ctypes.c_double(thr), _p(out, c_f64p))
     return _T44(out), int(k)
+
+
+def icp(src, tgt, max_dist, init=None, max_iteration=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """Point-to-point ICP (Experiments/test.py:183-188 / Open3D registration_icp semantics) from the oracle's
+    own primitives: exact NN of the transformed source in the target (canonical fp32 distance on zero-padded
+    8-vectors), pairs closer than max_dist, Kabsch.  -> (T, fitness, inlier_rmse, iterations)"""
+    src, tgt = _f32(src), _f32(tgt)
+    T = np.eye(4) if init is None else np.asarray(init, dtype=np.float64).copy()
+    n = len(src)
+    tgt8 = np.zeros((len(tgt), 8), np.float32)
+    tgt8[:, :3] = tgt
+
+    def evaluate(T):
+        p = src.astype(np.float64)
+        moved = np.stack([((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3] for r in range(3)], 1)
+        src8 = np.zeros((n, 8), np.float32)
+        src8[:, :3] = moved.astype(np.float32)
+        _, idx, _ = find_nn(src8, tgt8)
+        q = tgt[idx].astype(np.float64)
+        d = moved - q
+        r2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        keep = r2 < max_dist * max_dist
+        cnt = int(keep.sum())
+        T_new, k = refit_indexed(src, tgt, np.arange(n), idx, T, max_dist)
+        assert k == cnt
+        return T_new, cnt / n, float(np.sqrt(r2[keep].sum() / cnt)) if cnt else 0.0
+
+    T_next, fitness, rmse = evaluate(T)
+    it = 0
+    for it in range(1, max_iteration + 1):
+        T = T_next
+        T_next, f2, r2 = evaluate(T)
+        done = abs(fitness - f2) < rel_fitness and abs(rmse - r2) < rel_rmse
+        fitness, rmse = f2, r2
+        if done:
+            break
+    return T, fitness, rmse, it

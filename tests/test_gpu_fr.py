@@ -151,3 +151,26 @@ def test_gpf_matches_reference_golden(golden_dir):
     assert len(got) == len(ref) and len(got ^ ref) <= 4, (len(got), len(ref), len(got ^ ref))
     common = np.isin(k0.numpy(), g["keep0"])
     assert np.allclose(np.sort(nfd.numpy()[common])[:50], np.sort(g["nfd"])[:50], atol=1e-6)
+
+
+def test_icp_refinement_matches_oracle_and_improves():
+    """point-to-point ICP (test.py:183-188) built from the path's kernels vs the oracle's composition."""
+    from lidarregistration_b200.algorithms import registration_icp
+    p = synthetic.make_pair(4000, seed=321, overlap=0.8)
+    T0 = p["T_gt"].copy()
+    ang = np.deg2rad(1.5)
+    dR = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    T0[:3, :3] = dR @ T0[:3, :3]
+    T0[:3, 3] += [0.25, -0.2, 0.1]  # a coarse RANSAC-like initial guess
+    res = registration_icp(p["xyz0"], p["xyz1"], 0.6, T0)
+    To, fo, ro, ito = O.icp(p["xyz0"], p["xyz1"], 0.6, T0)
+    assert res.iterations == ito and abs(res.fitness - fo) < 1e-9 and abs(res.inlier_rmse - ro) < 1e-7
+    assert np.abs(res.transformation - To).max() < 1e-6
+    before = (metrics.rotation_error_deg(T0, p["T_gt"]), metrics.translation_error_cm(T0, p["T_gt"]))
+    after = (metrics.rotation_error_deg(res.transformation, p["T_gt"]),
+             metrics.translation_error_cm(res.transformation, p["T_gt"]))
+    assert after[0] < 0.2 * before[0] and after[1] < 0.2 * before[1]
+    assert res.fitness > 0.7
+    # accepts the PointCloud objects FR() returns
+    res2 = registration_icp(PointCloud(p["xyz0"]), PointCloud(p["xyz1"]), 0.6, T0)
+    assert np.abs(res2.transformation - res.transformation).max() < 1e-9  # fp64 atomics: order-dependent last bits
