@@ -90,7 +90,8 @@ int lr_match_nn(const float *f0, int64_t N, const float *f1, int64_t M, int D, i
 
 /* Implementation switch for lr_match_nn / lr_match_mutual (both give identical indices):
  * 0 = tensor-core sweep (tcgen05, fp16 operands) + exact fp32 re-rank when D == 32 [default];
- * 1 = exact fp32 CUDA-core sweep for every D. */
+ * 1 = exact fp32 CUDA-core sweep for every D;
+ * 2 / 3 = the tensor-core sweep with fp32 / fp16 accumulators in TMEM, explicitly (A/B tests). */
 int lr_match_set_mode(int mode);
 
 /* nn_to_mutual (matching.py:222-239) incl. torch_intersect (:67-87): keeps

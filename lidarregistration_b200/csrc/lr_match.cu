@@ -24,7 +24,9 @@
 
 namespace {
 
-int g_match_mode = 0;  // 0: tensor-core sweep when D == 32; 1: always the exact CUDA-core sweep
+int g_match_mode = 0;  // 0: auto; 1: always the exact CUDA-core sweep; 2 / 3: tensor-core sweep, fp32 / fp16 accumulators
+constexpr bool kAutoAcc16 = false;  // what mode 0 picks for D == 32
+inline bool tc_acc16() { return g_match_mode == 3 || (g_match_mode == 0 && kAutoAcc16); }
 
 
 constexpr int BM = 128, BN = 128, NT = 256;  // block tile and threads (8 x 8 outputs per thread)
@@ -464,13 +466,13 @@ LR_EXPORT int lr_match_nn(const float *f0, int64_t N, const float *f1, int64_t M
     LR_REQUIRE(f0 && f1 && idx1, "null pointer");
     LR_REQUIRE(N > 0 && M > 0 && N < ((int64_t)1 << 31) && M < ((int64_t)1 << 31), "N/M out of range");
     cudaStream_t st = (cudaStream_t)stream;
-    if (D == 32 && g_match_mode == 0) {
+    if (D == 32 && g_match_mode != 1) {
         char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH, lr_tc::scratch_bytes(N, M));
         if (!scratch) return LR_ERR_ALLOC;
         lr_tc::Prepared P;
         int rc = lr_tc::prepare(f0, N, f1, M, scratch, P, st);
         if (rc) return rc;
-        return lr_tc::sweep(P, false, f0, N, f1, M, idx1, idx1_2nd, st);
+        return lr_tc::sweep(P, false, tc_acc16(), f0, N, f1, M, idx1, idx1_2nd, st);
     }
     char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH, nn_scratch_bytes(N, M));
     if (!scratch) return LR_ERR_ALLOC;
@@ -480,7 +482,7 @@ LR_EXPORT int lr_match_nn(const float *f0, int64_t N, const float *f1, int64_t M
 LR_EXPORT int lr_match_set_mode(int mode)
 {
     lr::Lock lock;
-    LR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (auto) or 1 (exact CUDA-core sweep)");
+    LR_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (auto), 1 (exact CUDA-core sweep), 2 / 3 (tensor-core sweep, fp32 / fp16 accumulators)");
     g_match_mode = mode;
     return LR_OK;
 }
@@ -497,7 +499,7 @@ LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64
     // set are never consulted by the intersection, so the result is identical.
     const int nblocks = (int)((N + kCompactBlock - 1) / kCompactBlock);
     const size_t rev_bytes = lr::padded(sizeof(int64_t) * M) + lr::padded(sizeof(int) * nblocks);
-    const bool tc = D == 32 && g_match_mode == 0;
+    const bool tc = D == 32 && g_match_mode != 1;
     char *scratch = (char *)lr::arena_get(lr::SLOT_MATCH,
                                           rev_bytes + (tc ? lr_tc::scratch_bytes(N, M) : nn_scratch_bytes(M, N)));
     if (!scratch) return LR_ERR_ALLOC;
@@ -508,7 +510,7 @@ LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64
         lr_tc::Prepared P;
         rc = lr_tc::prepare(f0, N, f1, M, scratch + rev_bytes, P, st);
         if (rc) return rc;
-        rc = lr_tc::sweep(P, true, f0, N, f1, M, rev, nullptr, st);
+        rc = lr_tc::sweep(P, true, tc_acc16(), f0, N, f1, M, rev, nullptr, st);
     } else {
         rc = nn_sweep(f1, M, f0, N, D, rev, nullptr, scratch + rev_bytes, st);
     }

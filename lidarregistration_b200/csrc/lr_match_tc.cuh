@@ -16,7 +16,8 @@ struct Prepared {
 size_t scratch_bytes(int64_t N, int64_t M);
 int prepare(const float *f0, int64_t N, const float *f1, int64_t M, char *scratch, Prepared &P, cudaStream_t st);
 // swap = false: neighbours of f0's rows in f1; swap = true: neighbours of f1's rows in f0
-int sweep(const Prepared &P, bool swap, const float *f0, int64_t N, const float *f1, int64_t M, int64_t *idx1,
-          int64_t *idx2, cudaStream_t st);
+// acc16: fp16 accumulators in TMEM (packed tcgen05.ld, half the epilogue work, wider candidate band)
+int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, const float *f1, int64_t M,
+          int64_t *idx1, int64_t *idx2, cudaStream_t st);
 
 }  // namespace lr_tc

@@ -88,9 +88,10 @@ def test_gather_and_errors():
         engine.match_nn(torch.zeros(4, 20), torch.zeros(4, 20))  # unsupported D
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_both_sweep_implementations_agree_with_oracle(mode):
-    """mode 0 = tcgen05 sweep + exact re-rank, mode 1 = exact CUDA-core sweep: identical indices."""
+    """mode 0 = default, 1 = exact CUDA-core sweep, 2 / 3 = tcgen05 sweep with fp32 / fp16 accumulators
+    + exact re-rank: identical indices."""
     engine.match_set_mode(mode)
     try:
         for (N, M, seed) in [(1000, 777, 1), (300, 5000, 2), (2500, 260, 3)]:
@@ -111,8 +112,17 @@ def test_both_sweep_implementations_agree_with_oracle(mode):
         engine.match_set_mode(0)
 
 
-def test_candidate_overflow_falls_back_to_exact_scan():
+@pytest.mark.parametrize("mode", [2, 3])
+def test_candidate_overflow_falls_back_to_exact_scan(mode):
     """More near-ties than candidate slots: the tensor-core path must hand the row to the exact scan."""
+    engine.match_set_mode(mode)
+    try:
+        _overflow_case()
+    finally:
+        engine.match_set_mode(0)
+
+
+def _overflow_case():
     rng = np.random.default_rng(9)
     f1 = rng.standard_normal((3000, 32)).astype(np.float32)
     f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
@@ -125,7 +135,7 @@ def test_candidate_overflow_falls_back_to_exact_scan():
     assert np.all(o1[20:30] == 1000) and np.all(o2[20:30] == 1001)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_tiny_shapes(mode):
     engine.match_set_mode(mode)
     try:
