@@ -25,7 +25,7 @@
 namespace {
 
 int g_match_mode = 0;  // 0: auto; 1: always the exact CUDA-core sweep; 2 / 3: tensor-core sweep, fp32 / fp16 accumulators
-constexpr bool kAutoAcc16 = false;  // what mode 0 picks for D == 32
+constexpr bool kAutoAcc16 = true;   // what mode 0 picks for D == 32
 inline bool tc_acc16() { return g_match_mode == 3 || (g_match_mode == 0 && kAutoAcc16); }
 
 

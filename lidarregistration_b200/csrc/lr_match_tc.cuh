@@ -9,7 +9,10 @@ struct Prepared {
     uint4 *op0, *op1;   // fp16 operand images of f0 / f1
     float *n0, *n1;     // canonical squared norms
     Params *params;
-    int *cand, *cand_cnt, *ovf_rows;
+    int2 *cand;         // events: (32-column chunk id, chunk maximum bits)
+    int *cand_cnt, *ovf_rows;
+    char *partial;      // partial top-2 lists of the overflow scan
+    int64_t partial_cap;
     int64_t pad0, pad1;
 };
 

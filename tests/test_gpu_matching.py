@@ -135,6 +135,31 @@ def _overflow_case():
     assert np.all(o1[20:30] == 1000) and np.all(o2[20:30] == 1001)
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+def test_event_overflow_falls_back_to_exact_scan(mode):
+    """Targets that get steadily closer to the query along the column order make every 32-column chunk a new
+    running-maximum record: more events than slots, so the tensor-core path must hand the rows to the exact scan."""
+    rng = np.random.default_rng(11)
+    M = 40000
+    base = rng.standard_normal((8, 32)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    f1 = rng.standard_normal((M, 32)).astype(np.float32)
+    f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+    w = np.linspace(0.0, 1.0, M, dtype=np.float32)[:, None]
+    f1 = (1.0 - w) * f1 + w * base[0]          # approaches base[0] monotonically
+    f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+    f0 = np.concatenate([base, f1[::997][:40]]).copy()
+    engine.match_set_mode(mode)
+    try:
+        i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+        j1, _ = engine.match_nn(f0, f1, want_2nd=False)
+    finally:
+        engine.match_set_mode(0)
+    _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
+    assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2)
+    assert np.array_equal(j1.cpu().numpy(), o1)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_tiny_shapes(mode):
     engine.match_set_mode(mode)
