@@ -273,6 +273,33 @@ __device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t adesc
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+// One tile's tensor-core work from one elected lane, as a single block: 2 (uniform-norm path) or 3 chained MMAs
+// with the K-step descriptor adds, then the two commits.
+__device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool k48,
+                                              uint32_t bar_stage, uint32_t bar_acc)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e, e3, t, f;\n\t"
+        ".reg .b64 a1, b1, a2, b2;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 e3, %4, 0;\n\t"
+        "and.pred e3, e3, e;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "setp.ne.b32 f, 0, 0;\n\t"
+        "add.u64 a1, %1, 16;\n\t"
+        "add.u64 b1, %2, 16;\n\t"
+        "add.u64 a2, %1, 32;\n\t"
+        "add.u64 b2, %2, 48;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%7, %7, %7, %7}, f;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, {%7, %7, %7, %7}, t;\n\t"
+        "@e3 tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, {%7, %7, %7, %7}, t;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)k48), "r"(bar_stage), "r"(bar_acc), "r"(0u)
+        : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar_addr)
 {
     asm volatile(
@@ -394,49 +421,61 @@ __global__ void k_params_reset(Params *p)
     }
 }
 
-// canonical squared norms (8-lane order, == oracle) + their maximum
-__global__ void k_sqnorms_max(const float *__restrict__ F, int64_t N, float *__restrict__ out, unsigned *maxbits,
-                              unsigned *minbits)
+// canonical squared norm of one 32-d row (8 strided lanes added in order, == oracle)
+__device__ __forceinline__ float sqnorm32_canonical(const float *__restrict__ f)
 {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const float4 *x = reinterpret_cast<const float4 *>(f);
+    float lane[8];
+    float4 a = x[0], b = x[1];
+    lane[0] = a.x * a.x; lane[1] = a.y * a.y; lane[2] = a.z * a.z; lane[3] = a.w * a.w;
+    lane[4] = b.x * b.x; lane[5] = b.y * b.y; lane[6] = b.z * b.z; lane[7] = b.w * b.w;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        a = x[2 * k];
+        b = x[2 * k + 1];
+        lane[0] = lane[0] + a.x * a.x; lane[1] = lane[1] + a.y * a.y;
+        lane[2] = lane[2] + a.z * a.z; lane[3] = lane[3] + a.w * a.w;
+        lane[4] = lane[4] + b.x * b.x; lane[5] = lane[5] + b.y * b.y;
+        lane[6] = lane[6] + b.z * b.z; lane[7] = lane[7] + b.w * b.w;
+    }
+    float s = lane[0];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) s = s + lane[l];
+    return s;
+}
+
+// both feature sets in one launch: the first nb0 blocks take f0, the rest f1
+__global__ void k_sqnorms_both(const float *__restrict__ F0, int64_t N, float *__restrict__ out0, const float *__restrict__ F1,
+                               int64_t M, float *__restrict__ out1, int nb0, Params *p)
+{
+    const bool second = (int)blockIdx.x >= nb0;
+    const float *F = second ? F1 : F0;
+    const int64_t n = second ? M : N;
+    float *out = second ? out1 : out0;
+    const int64_t i = (int64_t)(blockIdx.x - (second ? nb0 : 0)) * blockDim.x + threadIdx.x;
     float s = 0.f;
-    if (i < N) {
-        const float4 *x = reinterpret_cast<const float4 *>(F + i * 32);
-        float lane[8];
-        float4 a = x[0], b = x[1];
-        lane[0] = a.x * a.x; lane[1] = a.y * a.y; lane[2] = a.z * a.z; lane[3] = a.w * a.w;
-        lane[4] = b.x * b.x; lane[5] = b.y * b.y; lane[6] = b.z * b.z; lane[7] = b.w * b.w;
-#pragma unroll
-        for (int k = 1; k < 4; ++k) {
-            a = x[2 * k];
-            b = x[2 * k + 1];
-            lane[0] = lane[0] + a.x * a.x; lane[1] = lane[1] + a.y * a.y;
-            lane[2] = lane[2] + a.z * a.z; lane[3] = lane[3] + a.w * a.w;
-            lane[4] = lane[4] + b.x * b.x; lane[5] = lane[5] + b.y * b.y;
-            lane[6] = lane[6] + b.z * b.z; lane[7] = lane[7] + b.w * b.w;
-        }
-        s = lane[0];
-#pragma unroll
-        for (int l = 1; l < 8; ++l) s = s + lane[l];
+    if (i < n) {
+        s = sqnorm32_canonical(F + i * 32);
         out[i] = s;
     }
-    float m = s;
+    float m = s, lo = i < n ? s : INFINITY;  // non-negative floats order like their bit patterns
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits, __float_as_uint(m));
-    float lo = i < N ? s : INFINITY;  // non-negative floats order like their bit patterns
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    if ((threadIdx.x & 31) == 0) atomicMin(minbits, __float_as_uint(lo));
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m > 0.f) atomicMax(second ? &p->maxn1_bits : &p->maxn0_bits, __float_as_uint(m));
+        atomicMin(second ? &p->minn1_bits : &p->minn0_bits, __float_as_uint(lo));
+    }
 }
 
 // scale = 2^-ceil(log2 sqrt(max |f|^2)): every scaled element and row norm is <= 1.
 // beta (v units): fp16 rounding of both operands 2^-10 |a'||b'|, hi/lo split of the norm term,
 // tensor-core accumulation (2^-20 of the term magnitudes, generous), rounding of the canonical
 // fp32 expression itself (2^-18); doubled because the maximum and the true argmin both move.
-__global__ void k_params_finish(Params *p)
+__device__ __forceinline__ float params_scale(const Params *p)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float mx = fmaxf(__uint_as_float(p->maxn0_bits), __uint_as_float(p->maxn1_bits));
     float scale = 1.f;
     if (mx > 0.f) {
@@ -445,6 +484,11 @@ __global__ void k_params_finish(Params *p)
         e = e < -60 ? -60 : (e > 60 ? 60 : e);
         scale = ldexpf(1.f, -e);
     }
+    return scale;
+}
+__device__ void params_finish(Params *p)
+{
+    const float scale = params_scale(p);
     const float an = scale * sqrtf(__uint_as_float(p->maxn0_bits)) * 1.000001f;
     const float bn = scale * sqrtf(__uint_as_float(p->maxn1_bits)) * 1.000001f;
     const float nm = fmaxf(an, bn);  // either side can play the B role (reverse sweep)
@@ -474,14 +518,21 @@ __global__ void k_params_finish(Params *p)
 }
 
 // fp32 [N,32] -> fp16 core-matrix image (128 B per row), padded to n_pad rows
-__global__ void k_prep16(const float *__restrict__ F, const float *__restrict__ nsq, int64_t N, int64_t n_pad,
-                         const Params *__restrict__ p, uint4 *__restrict__ out)
+// both sides in one launch (the first nb0 blocks take f0); thread 0 also derives the band parameters
+__global__ void k_prep16(const float *__restrict__ F0, const float *__restrict__ nsq0, int64_t N0, int64_t n_pad0,
+                         uint4 *__restrict__ out0, const float *__restrict__ F1, const float *__restrict__ nsq1, int64_t N1,
+                         int64_t n_pad1, uint4 *__restrict__ out1, int nb0, Params *p)
 {
-    const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool second = (int)blockIdx.x >= nb0;
+    const float *F = second ? F1 : F0, *nsq = second ? nsq1 : nsq0;
+    const int64_t N = second ? N1 : N0, n_pad = second ? n_pad1 : n_pad0;
+    uint4 *out = second ? out1 : out0;
+    const float s = params_scale(p);  // (p->scale itself is written below, by one thread, for the later kernels)
+    if (blockIdx.x == 0 && threadIdx.x == 0) params_finish(p);
+    const int64_t gid = (int64_t)(blockIdx.x - (second ? nb0 : 0)) * blockDim.x + threadIdx.x;
     const int64_t row = gid >> 3;
     const int core = (int)(gid & 7);
     if (row >= n_pad) return;
-    const float s = p->scale;
     union {
         __half h[8];
         uint4 u;
@@ -537,7 +588,10 @@ __device__ long long g_tc_trace[18][32][4];
 
 constexpr int SMAX_BUFS = 4;  // rotating per item; buffer (i + 1) % 4 is reset during item i (last used by item i - 3)
 struct __align__(8) Smem {
-    uint64_t a_full[2], a_empty[2], b_full[STAGES], b_empty[STAGES], t_full[2], t_empty[2];
+    // go[s]: tile `it` (stage s = it % 4, accumulator buffer s & 1) may be issued -- its operand tile has landed
+    // (one arrive.expect_tx + the bytes) AND the warps that drain buffer s & 1 have released tile it - 2.  One
+    // barrier, so the MMA warp waits once per tile.
+    uint64_t a_full[2], a_empty[2], go[STAGES], b_empty[STAGES], t_full[2];
     uint32_t tmem_base;
     int smax[SMAX_BUFS][TM];  // running maximum (2-NN variant: running second maximum) of every query row of the
                               // tile, shared by the epilogue groups, as order-preserving integer keys
@@ -660,19 +714,50 @@ template <> struct Chunk<true> {
 // Maxima are tracked per chunk: the second largest CHUNK maximum is a lower bound of the row's
 // second largest value, so thresholds derived from it stay safe.  The threshold never exceeds
 // (final [second] maximum - beta), so the recorded set covers every column the re-rank has to see.
-template <bool WANT2>
+// An event also carries a 6-bit mask of the chunk's column sub-groups (columns 6k .. 6k+5 for k < 5, then 30-31)
+// whose maximum exceeds the threshold as it stands after the event: only those can hold a column within
+// beta of the final maximum, and the re-rank reads only them (its cost is the L2 traffic of target rows).
+template <bool WANT2, class MaskFn>
 __device__ __forceinline__ void note_chunk(float mx, int chunk, bool record, float beta, float shared_base, float &m1,
-                                           float &m2, float &thr, int2 *__restrict__ slots, int &cnt)
+                                           float &m2, float &thr, int2 *__restrict__ slots, int &cnt, MaskFn &&submask)
 {
     if (mx > thr) {
         if (WANT2) m2 = fmaxf(m2, fminf(m1, mx));
         m1 = fmaxf(m1, mx);
         thr = fmaxf(WANT2 ? m2 : m1, shared_base) - beta;
         if (record) {
-            if (cnt < CAND) slots[cnt] = make_int2(chunk, __float_as_int(mx));
+            if (cnt < CAND) slots[cnt] = make_int2((int)(((unsigned)chunk << 6) | submask(thr)), __float_as_int(mx));
             ++cnt;
         }
     }
+}
+// sub-group masks of a chunk held as 32 fp32 registers / as 16 packed f16x2 registers starting at r[o]
+__device__ __forceinline__ unsigned submask32(const uint32_t (&v)[32], float thr)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float x = __uint_as_float(v[6 * k]);
+#pragma unroll
+        for (int i = 1; i < 6; ++i) x = fmaxf(x, __uint_as_float(v[6 * k + i]));
+        m |= x > thr ? 1u << k : 0u;
+    }
+    m |= fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31])) > thr ? 32u : 0u;
+    return m;
+}
+__device__ __forceinline__ unsigned submask16p(const uint32_t (&r)[32], int o, float thr)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const __half2 x = __hmax2(__hmax2(*reinterpret_cast<const __half2 *>(&r[o + 3 * k]),
+                                          *reinterpret_cast<const __half2 *>(&r[o + 3 * k + 1])),
+                                  *reinterpret_cast<const __half2 *>(&r[o + 3 * k + 2]));
+        m |= fmaxf(__low2float(x), __high2float(x)) > thr ? 1u << k : 0u;
+    }
+    const __half2 y = *reinterpret_cast<const __half2 *>(&r[o + 15]);
+    m |= fmaxf(__low2float(y), __high2float(y)) > thr ? 32u : 0u;
+    return m;
 }
 
 template <bool WANT2, bool ACC16>
@@ -695,10 +780,9 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 mbar_init(&sm->a_full[k], 1);
                 mbar_init(&sm->a_empty[k], 1);
                 mbar_init(&sm->t_full[k], 1);
-                mbar_init(&sm->t_empty[k], ACC16 ? 2 * NGROUPS : 4 * NGROUPS);  // warps that drain a buffer
             }
             for (int k = 0; k < STAGES; ++k) {
-                mbar_init(&sm->b_full[k], 1);
+                mbar_init(&sm->go[k], 1 + (ACC16 ? 2 * NGROUPS : 4 * NGROUPS));  // producer + warps that drain a buffer
                 mbar_init(&sm->b_empty[k], 1);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -733,11 +817,11 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                     const int t = tile_at(sidx, nseed, t_lo, ntl);
                     const int s = b_it % STAGES;
                     mbar_wait(&sm->b_empty[s], ((b_it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&sm->b_full[s], B_TILE_BYTES);
+                    mbar_expect_tx(&sm->go[s], B_TILE_BYTES);
                     const uint8_t *src = reinterpret_cast<const uint8_t *>(Bop) + (size_t)t * B_TILE_BYTES;
-                    bulk_g2s(sB + s * B_TILE_BYTES, src, B_TILE_BYTES / 2, &sm->b_full[s]);
+                    bulk_g2s(sB + s * B_TILE_BYTES, src, B_TILE_BYTES / 2, &sm->go[s]);
                     bulk_g2s(sB + s * B_TILE_BYTES + B_TILE_BYTES / 2, src + B_TILE_BYTES / 2, B_TILE_BYTES / 2,
-                             &sm->b_full[s]);
+                             &sm->go[s]);
                     ++b_it;
                 }
             }
@@ -746,8 +830,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         // ===== MMA issuer =====
         // The whole warp runs the loop (warp-uniform control flow, no divergence scaffolding around the
         // tcgen05 instructions); elect.sync picks the lane that issues.  The loop is unrolled over the four
-        // smem stages, so stage, accumulator buffer, barrier addresses and the t_empty parity are static and
-        // a tile costs the two waits, three descriptor adds and the issues.  Measured on B200: the previous
+        // smem stages, so stage, accumulator buffer, barrier addresses are static and
+        // a tile costs one wait, the descriptor adds and one block of issues.  Measured on B200: the previous
         // one-thread loop (~110 instructions per tile) was the sweep's bottleneck at ~660 cycles per tile.
         // (Tried and dropped: two issuing warps on alternate tiles -- their instruction streams interleave in
         // the tensor pipe and both tiles complete late; awaiting the next tile's barriers before the current
@@ -760,8 +844,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 return ntl + seed_tiles(ntl);
             };
             const uint32_t a_full = smem_u32(&sm->a_full[0]), a_empty = smem_u32(&sm->a_empty[0]);
-            const uint32_t b_full = smem_u32(&sm->b_full[0]), b_empty = smem_u32(&sm->b_empty[0]);
-            const uint32_t t_full = smem_u32(&sm->t_full[0]), t_empty = smem_u32(&sm->t_empty[0]);
+            const uint32_t go = smem_u32(&sm->go[0]), b_empty = smem_u32(&sm->b_empty[0]);
+            const uint32_t t_full = smem_u32(&sm->t_full[0]);
             // the 14-bit address field of a descriptor counts 16-byte units: tiles and K steps are plain adds
             const uint64_t adesc0 = smem_desc(smem_u32(sA)), bdesc0 = smem_desc(smem_u32(sB));
             constexpr uint32_t idesc = ACC16 ? (IDESC & ~(1u << 4)) /*D = f16*/ : IDESC;
@@ -779,17 +863,18 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
             while (!done) {
 #pragma unroll
                 for (int s = 0; s < STAGES; ++s) {
-                    mbar_wait_addr(b_full + s * 8u, pb);
-                    mbar_wait_addr(t_empty + (s & 1) * 8u, ((s >> 1) & 1) ^ 1u);
+                    const uint32_t t_it = ntiles;  // (the trace macro's tile index)
+                    (void)t_it;
+                    TC_TRACE(16, 0);
+                    mbar_wait_addr(go + s * 8u, pb);
+                    TC_TRACE(16, 2);
                     tc_fence_after();
                     const uint64_t bdesc = bdesc0 + (uint64_t)(s * (B_TILE_BYTES >> 4));
                     const uint32_t d = tmem_base + (uint32_t)(s & 1) * TN;
-                    // K = 16 per instruction = two 16-byte cores: features 0-15, 16-31, then the extension
-                    tc_mma_f16_elect(d, adesc, bdesc, idesc, 0u);
-                    tc_mma_f16_elect(d, adesc + (2 * 128 >> 4), bdesc + (2 * 128 >> 4), idesc, 1u);
-                    if (k48) tc_mma_f16_elect(d, adesc + (4 * 128 >> 4), bdesc + (6 * 128 >> 4), idesc, 1u);
-                    tc_commit_elect(b_empty + s * 8u);        // smem stage reusable once these MMAs have read it
-                    tc_commit_elect(t_full + (s & 1) * 8u);   // accumulator ready for the epilogue
+                    // K = 16 per instruction = two 16-byte cores: features 0-15, 16-31, then (k48) the extension;
+                    // then: smem stage reusable once these MMAs have read it, accumulator ready for the epilogue
+                    tc_issue_tile(d, adesc, bdesc, idesc, k48, b_empty + s * 8u, t_full + (s & 1) * 8u);
+                    TC_TRACE(16, 3);
                     ++ntiles;
                     if (--left == 0) {
                         tc_commit_elect(a_empty + (a_it & 1u) * 8u);
@@ -831,7 +916,10 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         const float beta = ACC16 ? params->beta16_k32[role] : params->beta_k32[role];
         using CH = Chunk<ACC16>;
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 64;
-        const uint32_t full_addr = smem_u32(&sm->t_full[0]), empty_addr = smem_u32(&sm->t_empty[0]);
+        const uint32_t full_addr = smem_u32(&sm->t_full[0]), go_addr = smem_u32(&sm->go[0]);
+        // the accumulator buffers start out free: the release of "tile -2" and "tile -1"
+        if (lane == 0 && (!ACC16 || (warp >> 3) == 0)) mbar_arrive_addr(go_addr);
+        if (lane == 0 && (!ACC16 || (warp >> 3) == 1)) mbar_arrive_addr(go_addr + 8u);
         const int rowl = q * 32 + lane;
         uint32_t t_it = 0, item_it = 0;
         const int trole = warp;
@@ -864,16 +952,20 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 const uint32_t acc = t_it & 1u;
                 mbar_wait_addr(full_addr + acc * 8u, (t_it >> 1) & 1u);
                 TC_TRACE(trole, 0);
+#if !defined(LR_TC_EXP_NOFENCE) || LR_TC_EXP_NOFENCE < 2
                 tc_fence_after();
+#endif
                 const uint32_t ta = tbase + acc * (uint32_t)TN;
                 tmem_ld32_issue(ta, va);
                 tmem_ld32_issue(ta + 32, vb);
                 tmem_ld32_wait(va);  // waits for every outstanding load of the thread
                 pin32(vb);           // ... so the second chunk only needs its uses ordered behind the wait
                 TC_TRACE(trole, 1);
+#ifndef LR_TC_EXP_NOFENCE
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_addr(empty_addr + acc * 8u);
+#endif
+                if (lane == 0) mbar_arrive_addr(go_addr + ((t_it + 2u) % STAGES) * 8u);  // the tile that reuses the buffer
                 TC_TRACE(trole, 2);
                 if (t == n_coltiles - 1) {
                     mask_tail32(va, t * TN + grp * 64, (int)M);
@@ -886,8 +978,10 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 if (fmaxf(mxa, mxb) > thr) {
                     const int chunk0 = t * (TN / 32) + grp * 2;
                     const bool record = valid && !seed;
-                    note_chunk<WANT2>(mxa, chunk0, record, beta, shared_base, m1, m2, thr, slots, cnt);
-                    note_chunk<WANT2>(mxb, chunk0 + 1, record, beta, shared_base, m1, m2, thr, slots, cnt);
+                    note_chunk<WANT2>(mxa, chunk0, record, beta, shared_base, m1, m2, thr, slots, cnt,
+                                      [&](float th) { return submask32(va, th); });
+                    note_chunk<WANT2>(mxb, chunk0 + 1, record, beta, shared_base, m1, m2, thr, slots, cnt,
+                                      [&](float th) { return submask32(vb, th); });
                     // publish this thread's running maximum (2-NN: running second maximum): any group's value
                     // is a lower bound of the row's true one, so thresholds derived from it stay safe
                     const float mine = WANT2 ? m2 : m1;
@@ -901,7 +995,9 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 const uint32_t acc = my_set;
                 mbar_wait_addr(full_addr + acc * 8u, (t_it >> 1) & 1u);
                 TC_TRACE(trole, 0);
+#if !defined(LR_TC_EXP_NOFENCE) || LR_TC_EXP_NOFENCE < 2
                 tc_fence_after();
+#endif
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)TN + my_half * 128u;
                 tmem_ld32p_issue(ta, va);
                 tmem_ld32p_issue(ta + 64, vb);
@@ -909,9 +1005,11 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 tmem_ld32_wait(va);
                 pin32(vb);
                 TC_TRACE(trole, 1);
+#ifndef LR_TC_EXP_NOFENCE
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_addr(empty_addr + acc * 8u);
+#endif
+                if (lane == 0) mbar_arrive_addr(go_addr + ((t_it + 2u) % STAGES) * 8u);  // the tile that reuses the buffer
                 TC_TRACE(trole, 2);
                 if (t == n_coltiles - 1) {
                     mask_tail32p(va, t * TN + (int)my_half * 128, (int)M);
@@ -925,9 +1023,14 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 if (fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) > thr) {
                     const int chunk0 = t * (TN / 32) + (int)my_half * 4;
                     const bool record = valid && !seed;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        note_chunk<WANT2>(mx[c], chunk0 + c, record, beta, shared_base, m1, m2, thr, slots, cnt);
+                    note_chunk<WANT2>(mx[0], chunk0, record, beta, shared_base, m1, m2, thr, slots, cnt,
+                                      [&](float th) { return submask16p(va, 0, th); });
+                    note_chunk<WANT2>(mx[1], chunk0 + 1, record, beta, shared_base, m1, m2, thr, slots, cnt,
+                                      [&](float th) { return submask16p(va, 16, th); });
+                    note_chunk<WANT2>(mx[2], chunk0 + 2, record, beta, shared_base, m1, m2, thr, slots, cnt,
+                                      [&](float th) { return submask16p(vb, 0, th); });
+                    note_chunk<WANT2>(mx[3], chunk0 + 3, record, beta, shared_base, m1, m2, thr, slots, cnt,
+                                      [&](float th) { return submask16p(vb, 16, th); });
                     const float mine = WANT2 ? m2 : m1;
                     if (mine > shared_base) atomicMax(my_smax, fkey(mine));
                 }
@@ -1011,43 +1114,25 @@ __device__ __forceinline__ void warp_lexmin(float &s, int &j)
     }
 }
 
-// One warp per query row.  Pass 1 reads the row's events (chunk id, chunk maximum) of every region and
-// finds the largest (2-NN: the two largest) recorded chunk maximum; pass 2 evaluates, with the canonical
-// fp32 expression, the 32 columns (lane = column) of every event whose maximum is within beta of it --
-// on cfg 2 about 1.2 of the ~3.4 events a row records.  Per-lane lexicographic top-2, merged by shuffles.
+// One warp per query row.  The event counts of the row's regions are read lane-parallel (one round trip),
+// a warp scan turns them into a flat event numbering, and every lane fetches "its" event (second round
+// trip): (chunk id, chunk maximum).  The largest (2-NN: the two largest) recorded chunk maximum gives the
+// cut: only events within beta of it can hold a (second) nearest neighbour -- on cfg 2 about 1.2 of the
+// ~3.4 events a row records.  Their 32 columns (lane = column) are evaluated with the canonical fp32
+// expression; per-lane lexicographic top-2, merged by shuffles.
 __global__ void __launch_bounds__(256)
 k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float *__restrict__ n0,
-         const float *__restrict__ n1, int64_t N, int64_t M, int nregions, bool acc16, int role, const int2 *__restrict__ cand,
-         const int *__restrict__ cand_cnt, Params *p, int *__restrict__ ovf_rows, int64_t *__restrict__ idx1,
-         int64_t *__restrict__ idx2)
+         const float *__restrict__ n1, int64_t N, int64_t M, int nregions, bool acc16, int role,
+         const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, Params *p, int *__restrict__ ovf_rows,
+         int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
 {
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;  // warp-uniform
-    const float beta = acc16 ? p->beta16_k32[role] : p->beta_k32[role];
-    // pass 1: the two largest chunk maxima among the row's events
-    float e1 = -INFINITY, e2 = -INFINITY;
-    bool overflow = false;
-    for (int g = 0; g < nregions; ++g) {
-        const int cnt = cand_cnt[row * nregions + g];
-        overflow |= cnt > CAND;
-        if (lane < cnt && lane < CAND) {
-            const float mx = __int_as_float(cand[(row * nregions + g) * CAND + lane].y);
-            e2 = fmaxf(e2, fminf(e1, mx));
-            e1 = fmaxf(e1, mx);
-        }
-    }
-    if (overflow) {  // more events than slots in some region: exact scan of the whole row instead
-        if (lane == 0) ovf_rows[atomicAdd(&p->ovf_count, 1)] = (int)row;
-        return;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float o1 = __shfl_xor_sync(0xffffffffu, e1, o), o2 = __shfl_xor_sync(0xffffffffu, e2, o);
-        e2 = fmaxf(fmaxf(e2, o2), fminf(e1, o1));
-        e1 = fmaxf(e1, o1);
-    }
-    const float keep = (idx2 ? e2 : e1) - beta;  // events below this cannot hold a (second) nearest neighbour
+    const int *cc = cand_cnt + row * nregions;
+    const int c0 = lane < nregions ? cc[lane] : 0;
+    const int c1 = lane + 32 < nregions ? cc[lane + 32] : 0;
+    // the query row, early: its latency hides behind the event bookkeeping
     float a[32];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -1055,30 +1140,81 @@ k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float
         a[4 * k] = x.x; a[4 * k + 1] = x.y; a[4 * k + 2] = x.z; a[4 * k + 3] = x.w;
     }
     const float na = n0[row];
+    const float beta = acc16 ? p->beta16_k32[role] : p->beta_k32[role];
+    if (__any_sync(0xffffffffu, c0 > CAND || c1 > CAND)) {  // more events than slots somewhere: exact scan instead
+        if (lane == 0) ovf_rows[atomicAdd(&p->ovf_count, 1)] = (int)row;
+        return;
+    }
+    // exclusive scans of the counts: regions 0-31 first, then 32-63
+    int s0 = c0, s1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u0 = __shfl_up_sync(0xffffffffu, s0, o), u1 = __shfl_up_sync(0xffffffffu, s1, o);
+        if (lane >= o) {
+            s0 += u0;
+            s1 += u1;
+        }
+    }
+    const int tot0 = __shfl_sync(0xffffffffu, s0, 31), total = tot0 + __shfl_sync(0xffffffffu, s1, 31);
+    s0 -= c0;
+    s1 += tot0 - c1;
+    const int rounds = (total + 31) >> 5;  // almost always 1
     Top2 c;
     c.s1 = INFINITY; c.j1 = 0x7fffffff; c.s2 = INFINITY; c.j2 = 0x7fffffff;
-    // pass 2
-    for (int g = 0; g < nregions; ++g) {
-        const int cnt = cand_cnt[row * nregions + g];
-        int2 ev = make_int2(0, 0);
-        bool take = false;
-        if (lane < cnt) {
-            ev = cand[(row * nregions + g) * CAND + lane];
-            take = __int_as_float(ev.y) >= keep;
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, take);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t j = (int64_t)__shfl_sync(0xffffffffu, ev.x, src) * 32 + lane;
-            if (j < M) {
-                float b[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 x = reinterpret_cast<const float4 *>(F1 + j * 32)[q];
-                    b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+    float e1 = -INFINITY, e2 = -INFINITY;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: the cut; pass 1: evaluate what survives it
+        const float keep = (idx2 ? e2 : e1) - beta;
+        for (int r = 0; r < rounds; ++r) {
+            const int e = r * 32 + lane;
+            // which (region, slot) is flat event e?
+            int g = -1, k = 0;
+            const int ng = nregions < 32 ? nregions : 32;
+            for (int src = 0; src < ng; ++src) {
+                const int b0 = __shfl_sync(0xffffffffu, s0, src), n0c = __shfl_sync(0xffffffffu, c0, src);
+                if (e >= b0 && e < b0 + n0c) {
+                    g = src;
+                    k = e - b0;
                 }
-                top2_put(c, canon_dist(a, b, na, n1[j]), (int)j);
+            }
+            for (int src = 0; src + 32 < nregions; ++src) {
+                const int b1 = __shfl_sync(0xffffffffu, s1, src), n1c = __shfl_sync(0xffffffffu, c1, src);
+                if (e >= b1 && e < b1 + n1c) {
+                    g = src + 32;
+                    k = e - b1;
+                }
+            }
+            int2 ev = make_int2(0, 0);
+            if (g >= 0) ev = cand[(row * nregions + g) * CAND + k];
+            const float mx = g >= 0 ? __int_as_float(ev.y) : -INFINITY;
+            if (pass == 0) {
+                e2 = fmaxf(e2, fminf(e1, mx));
+                e1 = fmaxf(e1, mx);
+            } else {
+                unsigned todo = __ballot_sync(0xffffffffu, g >= 0 && mx >= keep);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned cx = (unsigned)__shfl_sync(0xffffffffu, ev.x, src);
+                    const int64_t j = (int64_t)(cx >> 6) * 32 + lane;
+                    const int sub = lane >= 30 ? 5 : lane / 6;  // the lane's column sub-group
+                    if (j < M && ((cx >> sub) & 1u)) {
+                        float b[32];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 x = reinterpret_cast<const float4 *>(F1 + j * 32)[q];
+                            b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+                        }
+                        top2_put(c, canon_dist(a, b, na, n1[j]), (int)j);
+                    }
+                }
+            }
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float o1 = __shfl_xor_sync(0xffffffffu, e1, o), o2 = __shfl_xor_sync(0xffffffffu, e2, o);
+                e2 = fmaxf(fmaxf(e2, o2), fminf(e1, o1));
+                e1 = fmaxf(e1, o1);
             }
         }
     }
@@ -1150,8 +1286,8 @@ k_row_exact(const float *__restrict__ F0, const float *__restrict__ F1, const fl
     }
 }
 
-__global__ void __launch_bounds__(128)
-k_row_merge(const Params *__restrict__ p, const int *__restrict__ ovf_rows, const Top2 *__restrict__ partial,
+__global__ void __launch_bounds__(1024)
+k_row_merge(Params *__restrict__ p, const int *__restrict__ ovf_rows, const Top2 *__restrict__ partial,
             int64_t partial_cap, int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
 {
     const int novf = p->ovf_count;
@@ -1168,6 +1304,8 @@ k_row_merge(const Params *__restrict__ p, const int *__restrict__ ovf_rows, cons
         idx1[row] = m.j1 == 0x7fffffff ? 0 : m.j1;
         if (idx2) idx2[row] = m.j2 == 0x7fffffff ? 0 : m.j2;
     }
+    __syncthreads();  // single block: everyone has read the count
+    if (threadIdx.x == 0) p->ovf_count = 0;
 }
 
 // ---------------------------------------------------------------- host side
@@ -1209,11 +1347,10 @@ int prepare(const float *f0, int64_t N, const float *f1, int64_t M, char *scratc
     P.partial = cv.take<char>(sizeof(Top2) * partial_cap(mx));
     P.partial_cap = partial_cap(mx);
     k_params_reset<<<1, 32, 0, st>>>(P.params);
-    k_sqnorms_max<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f0, N, P.n0, &P.params->maxn0_bits, &P.params->minn0_bits);
-    k_sqnorms_max<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(f1, M, P.n1, &P.params->maxn1_bits, &P.params->minn1_bits);
-    k_params_finish<<<1, 32, 0, st>>>(P.params);
-    k_prep16<<<(unsigned)((P.pad0 * 8 + 255) / 256), 256, 0, st>>>(f0, P.n0, N, P.pad0, P.params, P.op0);
-    k_prep16<<<(unsigned)((P.pad1 * 8 + 255) / 256), 256, 0, st>>>(f1, P.n1, M, P.pad1, P.params, P.op1);
+    const int nbs0 = (int)((N + 255) / 256), nbs1 = (int)((M + 255) / 256);
+    k_sqnorms_both<<<nbs0 + nbs1, 256, 0, st>>>(f0, N, P.n0, f1, M, P.n1, nbs0, P.params);
+    const int nbp0 = (int)((P.pad0 * 8 + 255) / 256), nbp1 = (int)((P.pad1 * 8 + 255) / 256);
+    k_prep16<<<nbp0 + nbp1, 256, 0, st>>>(f0, P.n0, N, P.pad0, P.op0, f1, P.n1, M, P.pad1, P.op1, nbp0, P.params);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1253,8 +1390,8 @@ int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, 
     const int nitems = n_rowblocks * nsplit;
     const int grid = nitems < sms ? nitems : sms;
     const size_t smem = 2 * A_TILE_BYTES + STAGES * B_TILE_BYTES + sizeof(Smem) + 1024 + 64;
-    LR_CUDA_TRY(cudaMemsetAsync(P.cand_cnt, 0, sizeof(int) * Na * nsplit * NGROUPS, st));
-    LR_CUDA_TRY(cudaMemsetAsync(&P.params->ovf_count, 0, sizeof(int), st));
+    // (no clearing of cand_cnt: the sweep writes the count of every region of every valid row; ovf_count is zero
+    // from k_params_reset and k_row_merge puts it back to zero)
     const int tok = lr::prof_begin(lr::PROF_NN, st);
     auto launch = [&](auto kern) -> int {
         LR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1274,7 +1411,7 @@ int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, 
                                                        P.params, P.ovf_rows, idx1, idx2);
     k_row_exact<<<sms * 2, 256, 0, st>>>(fa, fb, na, nb, Nb, P.params, P.ovf_rows, reinterpret_cast<Top2 *>(P.partial),
                                          P.partial_cap);
-    k_row_merge<<<8, 128, 0, st>>>(P.params, P.ovf_rows, reinterpret_cast<const Top2 *>(P.partial), P.partial_cap, idx1,
+    k_row_merge<<<1, 1024, 0, st>>>(P.params, P.ovf_rows, reinterpret_cast<const Top2 *>(P.partial), P.partial_cap, idx1,
                                    idx2);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
@@ -1307,7 +1444,7 @@ LR_EXPORT int lr_tc_trace_dump(void)
     fprintf(stderr, "[tc trace] epilogue warp w (group w/4, sub-partition w%%4): t_full seen, chunks landed, released, scan done | "
                     "mma thread: top, b_full, t_empty, issued+committed\n");
     for (int t = 8; t < 20; ++t) {
-        for (int r = 16; r < 18; ++r)
+        for (int r = 16; r < 17; ++r)
             if (h[r][t][0])
                 fprintf(stderr, "tile %2d mma%d : %6lld %6lld %6lld %6lld\n", t, r - 16, h[r][t][0] - t0, h[r][t][1] - t0,
                         h[r][t][2] - t0, h[r][t][3] - t0);
