@@ -391,7 +391,7 @@ def bench_matching(engine, torch, dev):
                                        "sample": "oracle find_nn, %d of %d query rows x all targets (%.2f s), scaled to "
                                                  "two full sweeps" % (rows, MATCH_N, cpu_s)}, "unit": "ms per mutual-NN match (forward + reverse sweep + intersection), N=M=50000, D=32",
             "mutual_pairs": int(mi.shape[0]), "sweep_ms": nn_ms / max(nn_l, 1),
-            "roofline": {"kernel": "k_nn_tc (tcgen05 fp16 -> fp32 sweep + exact fp32 re-rank)", "bound": "tensor", "achieved": ach,
+            "roofline": {"kernel": "k_nn_tc (tcgen05 sweep: fp16 operands, fp16 accumulators in TMEM, chunk-maximum events) + k_rerank (exact fp32)", "bound": "tensor", "achieved": ach,
                          "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if ach else None,
                          "peak_source": "bf16_tflops of MEASURED_PEAKS.json (burst)" if peaks else "fallback 1590",
                          "traffic": ncu_traffic("r1_ncu_k_nn_tc.txt")}}

@@ -1114,9 +1114,8 @@ __device__ __forceinline__ void warp_lexmin(float &s, int &j)
     }
 }
 
-// One warp per query row.  The event counts of the row's regions are read lane-parallel (one round trip),
-// a warp scan turns them into a flat event numbering, and every lane fetches "its" event (second round
-// trip): (chunk id, chunk maximum).  The largest (2-NN: the two largest) recorded chunk maximum gives the
+// One warp per query row.  Lane L reads the event counts of regions L and L + 32 (one round trip) and walks
+// their few events itself: (chunk id | sub-group mask, chunk maximum).  The largest (2-NN: the two largest) recorded chunk maximum gives the
 // cut: only events within beta of it can hold a (second) nearest neighbour -- on cfg 2 about 1.2 of the
 // ~3.4 events a row records.  Their 32 columns (lane = column) are evaluated with the canonical fp32
 // expression; per-lane lexicographic top-2, merged by shuffles.
@@ -1145,77 +1144,69 @@ k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float
         if (lane == 0) ovf_rows[atomicAdd(&p->ovf_count, 1)] = (int)row;
         return;
     }
-    // exclusive scans of the counts: regions 0-31 first, then 32-63
-    int s0 = c0, s1 = c1;
+    // lane L owns regions L and L + 32: it walks their (few) events itself, no cross-lane search
+    int maxc = c0 > c1 ? c0 : c1;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u0 = __shfl_up_sync(0xffffffffu, s0, o), u1 = __shfl_up_sync(0xffffffffu, s1, o);
-        if (lane >= o) {
-            s0 += u0;
-            s1 += u1;
+    for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
+    const int2 *ev0 = cand + (row * nregions + lane) * CAND, *ev1 = cand + (row * nregions + lane + 32) * CAND;
+    // pass 0: the two largest chunk maxima among the row's events
+    float e1 = -INFINITY, e2 = -INFINITY;
+    for (int k = 0; k < maxc; ++k) {
+        if (k < c0) {
+            const float mx = __int_as_float(ev0[k].y);
+            e2 = fmaxf(e2, fminf(e1, mx));
+            e1 = fmaxf(e1, mx);
+        }
+        if (k < c1) {
+            const float mx = __int_as_float(ev1[k].y);
+            e2 = fmaxf(e2, fminf(e1, mx));
+            e1 = fmaxf(e1, mx);
         }
     }
-    const int tot0 = __shfl_sync(0xffffffffu, s0, 31), total = tot0 + __shfl_sync(0xffffffffu, s1, 31);
-    s0 -= c0;
-    s1 += tot0 - c1;
-    const int rounds = (total + 31) >> 5;  // almost always 1
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, e1, o), o2 = __shfl_xor_sync(0xffffffffu, e2, o);
+        e2 = fmaxf(fmaxf(e2, o2), fminf(e1, o1));
+        e1 = fmaxf(e1, o1);
+    }
+    const float keep = (idx2 ? e2 : e1) - beta;  // events below this cannot hold a (second) nearest neighbour
+    // pass 1: the flagged columns of the surviving events, lane = column
     Top2 c;
     c.s1 = INFINITY; c.j1 = 0x7fffffff; c.s2 = INFINITY; c.j2 = 0x7fffffff;
-    float e1 = -INFINITY, e2 = -INFINITY;
-    for (int pass = 0; pass < 2; ++pass) {  // pass 0: the cut; pass 1: evaluate what survives it
-        const float keep = (idx2 ? e2 : e1) - beta;
-        for (int r = 0; r < rounds; ++r) {
-            const int e = r * 32 + lane;
-            // which (region, slot) is flat event e?
-            int g = -1, k = 0;
-            const int ng = nregions < 32 ? nregions : 32;
-            for (int src = 0; src < ng; ++src) {
-                const int b0 = __shfl_sync(0xffffffffu, s0, src), n0c = __shfl_sync(0xffffffffu, c0, src);
-                if (e >= b0 && e < b0 + n0c) {
-                    g = src;
-                    k = e - b0;
-                }
-            }
-            for (int src = 0; src + 32 < nregions; ++src) {
-                const int b1 = __shfl_sync(0xffffffffu, s1, src), n1c = __shfl_sync(0xffffffffu, c1, src);
-                if (e >= b1 && e < b1 + n1c) {
-                    g = src + 32;
-                    k = e - b1;
-                }
-            }
-            int2 ev = make_int2(0, 0);
-            if (g >= 0) ev = cand[(row * nregions + g) * CAND + k];
-            const float mx = g >= 0 ? __int_as_float(ev.y) : -INFINITY;
-            if (pass == 0) {
-                e2 = fmaxf(e2, fminf(e1, mx));
-                e1 = fmaxf(e1, mx);
-            } else {
-                unsigned todo = __ballot_sync(0xffffffffu, g >= 0 && mx >= keep);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const unsigned cx = (unsigned)__shfl_sync(0xffffffffu, ev.x, src);
-                    const int64_t j = (int64_t)(cx >> 6) * 32 + lane;
-                    const int sub = lane >= 30 ? 5 : lane / 6;  // the lane's column sub-group
-                    if (j < M && ((cx >> sub) & 1u)) {
-                        float b[32];
+    auto evaluate = [&](int2 ev, bool take) {
+        unsigned todo = __ballot_sync(0xffffffffu, take);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned cx = (unsigned)__shfl_sync(0xffffffffu, ev.x, src);
+            const int64_t j = (int64_t)(cx >> 6) * 32 + lane;
+            const int sub = lane >= 30 ? 5 : lane / 6;  // the lane's column sub-group
+            if (j < M && ((cx >> sub) & 1u)) {
+                float b[32];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 x = reinterpret_cast<const float4 *>(F1 + j * 32)[q];
-                            b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
-                        }
-                        top2_put(c, canon_dist(a, b, na, n1[j]), (int)j);
-                    }
+                for (int q = 0; q < 8; ++q) {
+                    const float4 x = reinterpret_cast<const float4 *>(F1 + j * 32)[q];
+                    b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
                 }
+                top2_put(c, canon_dist(a, b, na, n1[j]), (int)j);
             }
         }
-        if (pass == 0) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float o1 = __shfl_xor_sync(0xffffffffu, e1, o), o2 = __shfl_xor_sync(0xffffffffu, e2, o);
-                e2 = fmaxf(fmaxf(e2, o2), fminf(e1, o1));
-                e1 = fmaxf(e1, o1);
+    };
+    for (int k = 0; k < maxc; ++k) {
+        int2 ev = make_int2(0, 0);
+        bool take = false;
+        if (k < c0) {
+            ev = ev0[k];
+            take = __int_as_float(ev.y) >= keep;
+        }
+        evaluate(ev, take);
+        if (nregions > 32) {
+            take = false;
+            if (k < c1) {
+                ev = ev1[k];
+                take = __int_as_float(ev.y) >= keep;
             }
+            evaluate(ev, take);
         }
     }
     // merge the per-lane top-2 lists

@@ -176,3 +176,47 @@ def test_tiny_shapes(mode):
             assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(mj.cpu().numpy(), oj), (N, M)
     finally:
         engine.match_set_mode(0)
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_uniform_norm_path_with_negative_scores_and_padding(mode):
+    """Unit-norm features take the K = 32 path (no norm-extension MMA), where padding rows would score v = 0.
+    Queries anti-correlated with every target have only negative scores: the padded columns of the last tile
+    must not win or raise thresholds.  M is chosen so that the last tile is mostly padding."""
+    rng = np.random.default_rng(21)
+    for M in (257, 300, 1000, 5121):
+        f1 = np.abs(rng.standard_normal((M, 32))).astype(np.float32) + 0.1   # all-positive targets
+        f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+        f0 = -np.abs(rng.standard_normal((700, 32))).astype(np.float32) - 0.1  # all-negative queries
+        f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+        engine.match_set_mode(mode)
+        try:
+            i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+            r1, _ = engine.match_nn(f1, f0)
+        finally:
+            engine.match_set_mode(0)
+        _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
+        assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2), M
+        _, p1, _ = O.find_nn(f1, f0)
+        assert np.array_equal(r1.cpu().numpy(), p1), M
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_dense_near_ties_within_the_band(mode):
+    """Clusters of targets a few 1e-4 apart (inside the fp16 band): many events and flagged sub-groups per row,
+    first and second neighbour often in the same 32-column chunk; indices must still be the oracle's."""
+    rng = np.random.default_rng(22)
+    centres = rng.standard_normal((400, 32)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    f1 = np.repeat(centres, 12, axis=0) + 2e-4 * rng.standard_normal((4800, 32)).astype(np.float32)
+    f1 = f1[rng.permutation(len(f1))]
+    f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+    f0 = centres + 1e-4 * rng.standard_normal(centres.shape).astype(np.float32)
+    f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+    engine.match_set_mode(mode)
+    try:
+        i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+    finally:
+        engine.match_set_mode(0)
+    _, o1, o2 = O.find_nn(f0, f1, return_2nd=True)
+    assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2)

@@ -116,6 +116,20 @@ __global__ void __launch_bounds__(512) k_maxrate(uint32_t *out, int iters)
             if (MODE == 2) a[i] = __vimax3_s16x2(a[i], x, y);
             if (MODE == 3) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(x));
             if (MODE == 4) asm volatile("max.f32 %0, %0, %1;" : "+r"(a[i]) : "r"(x));
+            // pipe-sharing probes: alternate two instruction kinds on independent registers
+            if (MODE == 5) {  // VHMNMX + HMNMX2
+                if (i & 1) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(x));
+                else asm volatile("{\n\t.reg .b32 t;\n\tmax.f16x2 t, %0, %1;\n\tmax.f16x2 %0, t, %2;\n\t}" : "+r"(a[i]) : "r"(x), "r"(y));
+            }
+            if (MODE == 6) {  // HMNMX2 + HFMA2 (fma pipe)
+                if (i & 1) asm volatile("max.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(x));
+                else asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(x), "r"(y));
+            }
+            if (MODE == 7) {  // VHMNMX + HFMA2
+                if (i & 1) asm volatile("{\n\t.reg .b32 t;\n\tmax.f16x2 t, %0, %1;\n\tmax.f16x2 %0, t, %2;\n\t}" : "+r"(a[i]) : "r"(x), "r"(y));
+                else asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(x), "r"(y));
+            }
+            if (MODE == 8) asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(x), "r"(y));
         }
         x += 0x00010001u;
         if (MODE == 2) y ^= a[0] & 1;
@@ -203,8 +217,9 @@ int main()
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
     uint32_t *out; cudaMalloc(&out, sizeof(uint32_t) * sms * 512);
     cudaEvent_t ea, eb; cudaEventCreate(&ea); cudaEventCreate(&eb);
-    const char *names[5] = {"FMNMX3 (max.f32 x3)", "VHMNMX (max.f16x2 x3)", "VIMNMX3.S16x2", "HMNMX2 (max.f16x2 x2)", "FMNMX (max.f32 x2)"};
-    for (int mode = 0; mode < 5; ++mode) {
+    const char *names[9] = {"FMNMX3 (max.f32 x3)", "VHMNMX (max.f16x2 x3)", "VIMNMX3.S16x2", "HMNMX2 (max.f16x2 x2)", "FMNMX (max.f32 x2)",
+                             "VHMNMX + HMNMX2 mix", "HMNMX2 + HFMA2 mix", "VHMNMX + HFMA2 mix", "HFMA2"};
+    for (int mode = 0; mode < 9; ++mode) {
         const int iters = 20000;
         for (int rep = 0; rep < 2; ++rep) {
             cudaEventRecord(ea);
@@ -213,6 +228,10 @@ int main()
             if (mode == 2) k_maxrate<2><<<sms, 512>>>(out, iters);
             if (mode == 3) k_maxrate<3><<<sms, 512>>>(out, iters);
             if (mode == 4) k_maxrate<4><<<sms, 512>>>(out, iters);
+            if (mode == 5) k_maxrate<5><<<sms, 512>>>(out, iters);
+            if (mode == 6) k_maxrate<6><<<sms, 512>>>(out, iters);
+            if (mode == 7) k_maxrate<7><<<sms, 512>>>(out, iters);
+            if (mode == 8) k_maxrate<8><<<sms, 512>>>(out, iters);
             cudaEventRecord(eb);
             cudaEventSynchronize(eb);
         }
