@@ -8,26 +8,33 @@
 //              K-major "core matrix" layout, 128 B per row: 4 cores of 8 features, 2 cores of
 //              A-role extension (1, 1, 0..) and 2 cores of B-role extension (c_hi, c_lo, 0..)
 //              with c = -s^2 |b|^2 / 2, so that one K = 48 MMA chain yields
-//              v_ij = s^2 (a_i . b_j - |b_j|^2 / 2)  =  -s^2 (d2_ij - |a_i|^2) / 2
+//              v_ij = s^2 (a_i . b_j - |b_j|^2 / 2)  =  -s^2 (d2_ij - |a_i|^2) / 2;
+//              when the B side's norms are uniform (L2-normalised FCGF features) the extension
+//              step is skipped (K = 32) and the band is widened by the norm spread
 //   staging    cp.async.bulk (UBLKCP, the TMA engine) global -> shared, completion on mbarriers,
 //              4-stage ring of 256-row target tiles, double-buffered 128-row query tile
-//   MMA        one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128, N 256, K 16) x 3
-//              into one of two 256-column fp32 accumulators in TMEM
-//   epilogue   four groups of 4 warps (one TMEM lane quadrant each) share every tile, 64 columns
-//              per group: tcgen05.ld.32x32b.x32 x2, the TMEM buffer is released as soon as the
-//              values are in registers, then a 3-input FMNMX tree per 32 columns and one compare.
-//              A thread owns a query row; when a chunk reaches the row's threshold the columns
-//              within `beta` of the running maximum are appended to the thread's private
-//              candidate region (mask built with saturating FMAs, no atomics).  The running
-//              maximum of a row is shared by the groups through shared memory, and every work
-//              item starts with a short seed phase (maxima only) so thresholds are tight early.
+//   MMA        a warp-uniform issue loop, elect.sync picks the lane: tcgen05.mma.cta_group::1
+//              .kind::f16 (M 128, N 256, K 16) x 2-3 into one of two 256-column accumulators
+//              in TMEM; fp16 accumulators by default (fp32 kept for A/B), one mbarrier per tile
+//   epilogue   16 warps (TMEM lane quadrant = warp % 4).  fp16 accumulators: groups 0-1 drain
+//              the even tiles, groups 2-3 the odd ones, 128 columns per warp and tile through
+//              tcgen05.ld.32x32b.x32.pack::16b x 2; the TMEM buffer is released as soon as the
+//              values are in registers; 3-input VHMNMX trees per 32-column chunk, ONE compare.
+//              A chunk whose maximum reaches the row's threshold becomes an event
+//              (chunk id | 6-bit column sub-group mask, chunk maximum) in the warp's private
+//              region -- no atomics.  The running maximum of a row is shared by the groups
+//              through shared memory, and every work item starts with a short seed phase
+//              (maxima only) so thresholds are tight early.
+//   re-rank    k_rerank (one warp per row) keeps the events within `beta` of the final
+//              (second) maximum and evaluates their flagged columns with the reference's fp32
+//              expression, same operation order as oracle/lr_oracle.c
 //
-// `beta` bounds the fp16/tensor-core error, so the collected set provably contains the argmin
-// of the reference's fp32 expression; k_rerank then evaluates that expression exactly (same
-// operation order as oracle/lr_oracle.c) on the few candidates, which makes the indices
-// bit-exact.  Rows whose candidate list overflows are redone by an exact scan.
+// `beta` bounds the fp16 operand / accumulator error, so the evaluated set provably contains the
+// argmin of the reference's fp32 expression, which makes the indices bit-exact.  Rows with more
+// events than slots are redone by an exact scan.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "lr_match_tc.cuh"
 
@@ -38,9 +45,6 @@ static inline float __uint_as_float_host(unsigned u) { float f; memcpy(&f, &u, 4
 extern Prepared g_last; extern int g_last_regions; extern int64_t g_last_rows;
 #endif
 
-#ifndef LR_TC_WAITSTYLE
-#define LR_TC_WAITSTYLE 0
-#endif
 constexpr int TM = 128;                      // query rows per tile (UMMA M)
 constexpr int TN = 256;                      // target rows per tile (UMMA N)
 constexpr int KCORES = 8;                    // 16-byte K cores per row (4 data + 2 A-ext + 2 B-ext)
@@ -80,97 +84,11 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-#if LR_TC_WAITSTYLE == 2
-    uint32_t ok = 0;
-    while (!ok)
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-#elif LR_TC_WAITSTYLE == 1
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(addr), "r"(parity)
-        : "memory");
-#else
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(addr), "r"(parity), "r"(0x989680u)  // suspend-time hint (ns): sleep in hardware instead of
-        : "memory");                                   // burning issue slots the epilogue warps need
-#endif
-}
-// the same with the wait style as a template parameter: 0 = try_wait with a suspend-time hint, 1 = plain
-// try_wait, 2 = test_wait spin
-template <int STYLE>
-__device__ __forceinline__ void mbar_wait_style(uint32_t addr, uint32_t parity)
-{
-    if (STYLE == 2) {
-        uint32_t ok = 0;
-        while (!ok)
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p;\n\t"
-                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t"
-                "}"
-                : "=r"(ok)
-                : "r"(addr), "r"(parity)
-                : "memory");
-    } else if (STYLE == 1) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "WAIT_LOOP:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@p bra.uni WAIT_DONE;\n\t"
-            "bra.uni WAIT_LOOP;\n\t"
-            "WAIT_DONE:\n\t"
-            "}" ::"r"(addr), "r"(parity)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "WAIT_LOOP:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-            "@p bra.uni WAIT_DONE;\n\t"
-            "bra.uni WAIT_LOOP;\n\t"
-            "WAIT_DONE:\n\t"
-            "}" ::"r"(addr), "r"(parity), "r"(0x989680u)
-            : "memory");
-    }
-}
-#ifndef LR_TC_MMAWAIT
-#define LR_TC_MMAWAIT 0
-#endif
-#ifndef LR_TC_EPIWAIT
-#define LR_TC_EPIWAIT 0
-#endif
-// the same on a precomputed shared-space address (keeps address arithmetic out of the hot loop)
+// Blocking wait on a phase, on a precomputed shared-space address (keeps address arithmetic out of the hot
+// loops).  try_wait with a suspend-time hint: the thread sleeps in hardware instead of burning issue slots
+// the epilogue warps need.  (Plain try_wait and a test_wait spin were measured: no difference / slower.)
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity)
 {
-    mbar_wait_style<LR_TC_EPIWAIT>(addr, parity);
-    return;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -182,20 +100,7 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity)
         "}" ::"r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
 }
-__device__ __forceinline__ bool mbar_test_addr(uint32_t addr, uint32_t parity)  // non-blocking
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t addr)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
@@ -205,25 +110,6 @@ __device__ __forceinline__ int lds_volatile_s32(uint32_t addr)
     int v;
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
-}
-// one non-blocking probe of a phase
-__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-#ifdef LR_TC_TESTWAIT
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#else
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -243,36 +129,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-// the same issued by one elected lane of a converged warp
-__device__ __forceinline__ void tc_mma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p, e;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
 // One tile's tensor-core work from one elected lane, as a single block: 2 (uniform-norm path) or 3 chained MMAs
 // with the K-step descriptor adds, then the two commits.
 __device__ __forceinline__ void tc_issue_tile(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool k48,
@@ -343,19 +199,9 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32])
                  : "memory");
 }
 
-// fp16 accumulators: .pack::16b puts two adjacent 16-bit columns in one register (lower column in the low
-// half), so 16 registers carry a 32-column chunk
-__device__ __forceinline__ void tmem_ld16p_issue(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32p_issue(uint32_t taddr, uint32_t (&r)[32])  // 64 columns of 16-bit data
+// fp16 accumulators: .pack::16b puts two adjacent 16-bit columns in one register (lower column in the low half,
+// tools/micro_acc16.cu), so 32 registers carry 64 columns
+__device__ __forceinline__ void tmem_ld32p_issue(uint32_t taddr, uint32_t (&r)[32])
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
@@ -368,33 +214,6 @@ __device__ __forceinline__ void tmem_ld32p_issue(uint32_t taddr, uint32_t (&r)[3
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_wait2(uint32_t (&r)[16], uint32_t (&s)[16])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                   "+r"(s[0]), "+r"(s[1]), "+r"(s[2]), "+r"(s[3]), "+r"(s[4]), "+r"(s[5]), "+r"(s[6]), "+r"(s[7]),
-                   "+r"(s[8]), "+r"(s[9]), "+r"(s[10]), "+r"(s[11]), "+r"(s[12]), "+r"(s[13]), "+r"(s[14]), "+r"(s[15])
-                 :
-                 : "memory");
-}
-__device__ __forceinline__ void pin16(uint32_t (&r)[16])
-{
-    asm volatile(""
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
-
 // Scheduling fence for 32 live registers: the compiler may not move their uses above this point
 // (used to keep a tcgen05.ld issue ahead of the ALU work on the previous chunk).
 __device__ __forceinline__ void pin32(uint32_t (&r)[32])
@@ -609,7 +428,7 @@ constexpr int KEY_NEG_INF = (int)(0xff800000u ^ 0x7fffffffu);
 // tile sequence of one work item: a short seed phase over tiles spread across the item's range
 // (running maxima only, no candidates) and then the full sweep.  Seeding makes the thresholds
 // tight before the sweep starts: ~ln(columns) prefix-maximum records per row become ~ln(16).
-__device__ __forceinline__ int seed_tiles(int ntl) { return ntl >= 32 ? 8 : 0; }
+__device__ __forceinline__ int seed_tiles(int ntl, int seed_cfg) { return ntl >= 32 ? seed_cfg : 0; }
 __device__ __forceinline__ int tile_at(int sidx, int nseed, int t_lo, int ntl)
 {
     return sidx < nseed ? t_lo + (int)(((unsigned)sidx * (unsigned)ntl) / (unsigned)nseed) : t_lo + (sidx - nseed);
@@ -627,20 +446,6 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32])
     return fmaxf(fmaxf(a, b), fmaxf(c, d));
 }
 
-// the same for a chunk held as 16 packed f16x2 registers: 3-input VHMNMX tree, then the two halves
-__device__ __forceinline__ float max16p(const uint32_t (&r)[16])
-{
-    __half2 h[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) h[k] = *reinterpret_cast<const __half2 *>(&r[k]);
-    __half2 m[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) m[k] = __hmax2(__hmax2(h[3 * k], h[3 * k + 1]), h[3 * k + 2]);
-    const __half2 a = __hmax2(__hmax2(m[0], m[1]), m[2]);
-    const __half2 b = __hmax2(__hmax2(m[3], m[4]), h[15]);
-    const __half2 c = __hmax2(a, b);
-    return fmaxf(__low2float(c), __high2float(c));
-}
 // 64 packed columns (32 f16x2 registers) -> the maxima of their two 32-column chunks
 __device__ __forceinline__ float max16p_at(const uint32_t (&r)[32], int o)
 {
@@ -679,29 +484,6 @@ __device__ __forceinline__ void mask_tail32p(uint32_t (&r)[32], int col0, int M)
         if (col0 + 2 * k + 1 >= M) r[k] = (r[k] & 0x0000ffffu) | 0xfc000000u;
     }
 }
-
-// chunk = 32 columns of one query row in registers: 32 fp32 values, or 16 packed f16x2 (fp16 accumulators)
-template <bool ACC16> struct Chunk;
-template <> struct Chunk<false> {
-    static constexpr int NR = 32;
-    static __device__ __forceinline__ void issue(uint32_t ta, uint32_t (&r)[32]) { tmem_ld32_issue(ta, r); }
-    static __device__ __forceinline__ void wait(uint32_t (&r)[32]) { tmem_ld32_wait(r); }
-    static __device__ __forceinline__ void wait2(uint32_t (&r)[32], uint32_t (&s)[32])
-    {
-        tmem_ld32_wait(r);  // waits for every outstanding load of the thread
-        pin32(s);           // ... so the second chunk only needs its uses ordered behind the wait
-    }
-    static __device__ __forceinline__ void pin(uint32_t (&r)[32]) { pin32(r); }
-    static __device__ __forceinline__ float max(const uint32_t (&r)[32]) { return max32(r); }
-};
-template <> struct Chunk<true> {
-    static constexpr int NR = 16;
-    static __device__ __forceinline__ void issue(uint32_t ta, uint32_t (&r)[16]) { tmem_ld16p_issue(ta, r); }
-    static __device__ __forceinline__ void wait(uint32_t (&r)[16]) { tmem_ld16_wait(r); }
-    static __device__ __forceinline__ void wait2(uint32_t (&r)[16], uint32_t (&s)[16]) { tmem_ld16_wait2(r, s); }
-    static __device__ __forceinline__ void pin(uint32_t (&r)[16]) { pin16(r); }
-    static __device__ __forceinline__ float max(const uint32_t (&r)[16]) { return max16p(r); }
-};
 
 // A 32-column chunk whose maximum reaches the row's threshold (running maximum, or running second
 // maximum for the 2-NN variant, minus beta) is an EVENT: the running maxima absorb the chunk maximum
@@ -760,11 +542,36 @@ __device__ __forceinline__ unsigned submask16p(const uint32_t (&r)[32], int o, f
     return m;
 }
 
+// Work items of the persistent CTAs, taken round-robin: the first `full_rb` row blocks sweep all column tiles
+// (whole waves of full items), the remaining row blocks -- the last, partial wave -- are cut into `nsplit`
+// column ranges each so that the tail fills the machine too.
+struct Sched {
+    int full_rb, nsplit, tiles_per_split, nitems;
+};
+struct Item {
+    int rb, cs, t_lo, t_hi, nsp;
+};
+__device__ __forceinline__ Item item_of(int item, const Sched &sc, int n_coltiles)
+{
+    Item it;
+    if (item < sc.full_rb) {
+        it.rb = item; it.cs = 0; it.t_lo = 0; it.t_hi = n_coltiles; it.nsp = 1;
+    } else {
+        const int j = item - sc.full_rb;
+        it.rb = sc.full_rb + j / sc.nsplit;
+        it.cs = j - (j / sc.nsplit) * sc.nsplit;
+        it.t_lo = it.cs * sc.tiles_per_split;
+        it.t_hi = min(n_coltiles, it.t_lo + sc.tiles_per_split);
+        it.nsp = sc.nsplit;
+    }
+    return it;
+}
+
 template <bool WANT2, bool ACC16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N, int64_t M, int n_rowblocks,
-        int n_coltiles, int tiles_per_split, int nsplit, const Params *__restrict__ params, int role,
-        int2 *__restrict__ cand, int *__restrict__ cand_cnt)
+        int n_coltiles, Sched sc, const Params *__restrict__ params, int role,
+        int seed_cfg, int2 *__restrict__ cand, int *__restrict__ cand_cnt)
 {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -772,7 +579,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
     uint8_t *sB = smem_raw + 2 * A_TILE_BYTES;         // STAGES x 32 KB
     Smem *sm = reinterpret_cast<Smem *>(smem_raw + 2 * A_TILE_BYTES + STAGES * B_TILE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nitems = n_rowblocks * nsplit;
+    const int nitems = sc.nitems, nsplit = sc.nsplit;  // nsplit = region sets per row
+    (void)n_rowblocks;
 
     if (warp == WARP_MMA) {
         if (lane == 0) {
@@ -804,15 +612,15 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int rb = item / nsplit, cs = item - rb * nsplit;
-                const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
+                const Item wi = item_of(item, sc, n_coltiles);
+                const int rb = wi.rb, t_lo = wi.t_lo, t_hi = wi.t_hi;
                 const int ab = a_it & 1;
                 mbar_wait(&sm->a_empty[ab], ((a_it >> 1) & 1) ^ 1);
                 mbar_expect_tx(&sm->a_full[ab], A_TILE_BYTES);
                 bulk_g2s(sA + ab * A_TILE_BYTES, reinterpret_cast<const uint8_t *>(Aop) + (size_t)rb * A_TILE_BYTES,
                          A_TILE_BYTES, &sm->a_full[ab]);
                 ++a_it;
-                const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl);
+                const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl, seed_cfg);
                 for (int sidx = 0; sidx < nseed + ntl; ++sidx) {
                     const int t = tile_at(sidx, nseed, t_lo, ntl);
                     const int s = b_it % STAGES;
@@ -839,9 +647,9 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         static_assert(STAGES == 4, "the issue loop is unrolled over four stages / two accumulator buffers");
         if ((int)blockIdx.x < nitems) {
             auto tiles_of = [&](int item) {
-                const int cs = item % nsplit;
-                const int ntl = min(n_coltiles, (cs + 1) * tiles_per_split) - cs * tiles_per_split;
-                return ntl + seed_tiles(ntl);
+                const Item wi = item_of(item, sc, n_coltiles);
+                const int ntl = wi.t_hi - wi.t_lo;
+                return ntl + seed_tiles(ntl, seed_cfg);
             };
             const uint32_t a_full = smem_u32(&sm->a_full[0]), a_empty = smem_u32(&sm->a_empty[0]);
             const uint32_t go = smem_u32(&sm->go[0]), b_empty = smem_u32(&sm->b_empty[0]);
@@ -914,7 +722,6 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         const int q = warp & 3;            // TMEM lane quadrant this warp may read
         const int grp = warp >> 2;         // 0 .. NGROUPS-1
         const float beta = ACC16 ? params->beta16_k32[role] : params->beta_k32[role];
-        using CH = Chunk<ACC16>;
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 64;
         const uint32_t full_addr = smem_u32(&sm->t_full[0]), go_addr = smem_u32(&sm->go[0]);
         // the accumulator buffers start out free: the release of "tile -2" and "tile -1"
@@ -932,8 +739,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
         const uint32_t my_set = (uint32_t)(grp >> 1), my_half = (uint32_t)(grp & 1);
         (void)my_set; (void)my_half;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int rb = item / nsplit, cs = item - rb * nsplit;
-            const int t_lo = cs * tiles_per_split, t_hi = min(n_coltiles, t_lo + tiles_per_split);
+            const Item wi = item_of(item, sc, n_coltiles);
+            const int rb = wi.rb, cs = wi.cs, t_lo = wi.t_lo, t_hi = wi.t_hi;
             const int64_t row = (int64_t)rb * TM + rowl;
             const bool valid = row < N;
             float m1 = -INFINITY, m2 = -INFINITY, thr = -INFINITY;
@@ -944,7 +751,7 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
             const uint32_t smax_addr = smem_u32(my_smax);
             if (grp == 0) sm->smax[(item_it + 1) % SMAX_BUFS][rowl] = KEY_NEG_INF;  // for the next item
             ++item_it;
-            const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl);
+            const int ntl = t_hi - t_lo, nseed = seed_tiles(ntl, seed_cfg);
 
             // fp32 accumulators: load the tile's two chunks, hand the TMEM buffer back, scan
             auto tile32 = [&](const int t, const bool seed) {
@@ -952,19 +759,15 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 const uint32_t acc = t_it & 1u;
                 mbar_wait_addr(full_addr + acc * 8u, (t_it >> 1) & 1u);
                 TC_TRACE(trole, 0);
-#if !defined(LR_TC_EXP_NOFENCE) || LR_TC_EXP_NOFENCE < 2
                 tc_fence_after();
-#endif
                 const uint32_t ta = tbase + acc * (uint32_t)TN;
                 tmem_ld32_issue(ta, va);
                 tmem_ld32_issue(ta + 32, vb);
                 tmem_ld32_wait(va);  // waits for every outstanding load of the thread
                 pin32(vb);           // ... so the second chunk only needs its uses ordered behind the wait
                 TC_TRACE(trole, 1);
-#ifndef LR_TC_EXP_NOFENCE
                 tc_fence_before();
                 __syncwarp();
-#endif
                 if (lane == 0) mbar_arrive_addr(go_addr + ((t_it + 2u) % STAGES) * 8u);  // the tile that reuses the buffer
                 TC_TRACE(trole, 2);
                 if (t == n_coltiles - 1) {
@@ -995,9 +798,7 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 const uint32_t acc = my_set;
                 mbar_wait_addr(full_addr + acc * 8u, (t_it >> 1) & 1u);
                 TC_TRACE(trole, 0);
-#if !defined(LR_TC_EXP_NOFENCE) || LR_TC_EXP_NOFENCE < 2
                 tc_fence_after();
-#endif
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)TN + my_half * 128u;
                 tmem_ld32p_issue(ta, va);
                 tmem_ld32p_issue(ta + 64, vb);
@@ -1005,10 +806,8 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
                 tmem_ld32_wait(va);
                 pin32(vb);
                 TC_TRACE(trole, 1);
-#ifndef LR_TC_EXP_NOFENCE
                 tc_fence_before();
                 __syncwarp();
-#endif
                 if (lane == 0) mbar_arrive_addr(go_addr + ((t_it + 2u) % STAGES) * 8u);  // the tile that reuses the buffer
                 TC_TRACE(trole, 2);
                 if (t == n_coltiles - 1) {
@@ -1057,7 +856,11 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
             }
 #pragma unroll 1
             for (int t = t_lo; t < t_hi; ++t) tile(t, false);
-            if (valid) cand_cnt[region] = cnt;
+            if (valid) {
+                cand_cnt[region] = cnt;
+                // a full item stands for all column ranges of its rows: the other region sets stay empty
+                for (int c = wi.nsp; c < nsplit; ++c) cand_cnt[(row * nsplit + c) * NGROUPS + grp] = 0;
+            }
         }
     }
 
@@ -1357,28 +1160,41 @@ int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, 
     const int n_rowblocks = (int)((Na + TM - 1) / TM);
     const int n_coltiles = (int)((Nb + TN - 1) / TN);
     const int sms = lr::sm_count();
-    // Persistent CTAs take (row block, column split) items round-robin.  Pick the number of column
-    // splits that wastes the least of the last wave (391 row blocks on 148 SMs: 1 split = 3 waves
-    // for 2.64 waves of work, 3 splits = 8 waves for 7.93); every extra split restarts the running
-    // maxima (ln(columns) more candidates per row, more slow-path visits), hence the penalty.
+    // Persistent CTAs take items round-robin (Sched): whole waves of full row blocks, then the row blocks of the
+    // last partial wave cut into S column ranges.  S minimises rounds x (tiles per range + a per-item overhead of
+    // ~12 tiles: pipeline fill, query tile, seed phase); 391 row blocks on 148 SMs: 296 full + 95 x 3 ranges =
+    // 2.67 full-item times instead of 3 (one split for everything) or 8 x (1/3 + overhead) (three for everything).
     const int64_t region_cap = region_budget(N > M ? N : M) / (Na * NGROUPS);
-    int nsplit = 1;
-    double best_cost = 1e30;
-    for (int cand_split = 1; cand_split <= 16; ++cand_split) {
-        if (cand_split > n_coltiles || cand_split > region_cap) break;
-        const int tps_c = (n_coltiles + cand_split - 1) / cand_split;
-        const int ns = (n_coltiles + tps_c - 1) / tps_c;
-        const long long items = (long long)n_rowblocks * ns;
-        const long long waves = (items + sms - 1) / sms;
-        const double cost = (double)waves * tps_c * (1.0 + 0.12 * (ns - 1));
-        if (cost < best_cost) {
-            best_cost = cost;
-            nsplit = ns;
+    Sched sc;
+    sc.full_rb = n_rowblocks / sms * sms;
+    const int tail = n_rowblocks - sc.full_rb;
+    sc.nsplit = 1;
+    if (tail > 0) {
+        double best_cost = 1e30;
+        for (int S = 1; S <= 16; ++S) {
+            if (S > n_coltiles || S > region_cap) break;
+            const int tps_c = (n_coltiles + S - 1) / S;
+            if (S > 1 && tps_c < 8) break;
+            const int ns = (n_coltiles + tps_c - 1) / tps_c;
+            const long long rounds = ((long long)tail * ns + sms - 1) / sms;
+            const double cost = (double)rounds * (tps_c + 12.0);
+            if (cost < best_cost - 1e-9) {
+                best_cost = cost;
+                sc.nsplit = ns;
+            }
         }
     }
-    const int tps = (n_coltiles + nsplit - 1) / nsplit;
-    nsplit = (n_coltiles + tps - 1) / tps;
-    const int nitems = n_rowblocks * nsplit;
+    if (const char *e = getenv("LR_TC_NSPLIT")) {  // experiments only
+        const int v = atoi(e);
+        if (v >= 1 && v <= n_coltiles && v <= region_cap) sc.nsplit = v;
+    }
+    if (getenv("LR_TC_NOFULL")) sc.full_rb = 0;  // experiments only: every row block split alike
+    sc.tiles_per_split = (n_coltiles + sc.nsplit - 1) / sc.nsplit;
+    sc.nsplit = (n_coltiles + sc.tiles_per_split - 1) / sc.tiles_per_split;
+    sc.nitems = sc.full_rb + (n_rowblocks - sc.full_rb) * sc.nsplit;
+    const int nsplit = sc.nsplit, nitems = sc.nitems;
+    int seed_cfg = 8;
+    if (const char *e = getenv("LR_TC_SEEDS")) seed_cfg = atoi(e);
     const int grid = nitems < sms ? nitems : sms;
     const size_t smem = 2 * A_TILE_BYTES + STAGES * B_TILE_BYTES + sizeof(Smem) + 1024 + 64;
     // (no clearing of cand_cnt: the sweep writes the count of every region of every valid row; ovf_count is zero
@@ -1386,7 +1202,7 @@ int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, 
     const int tok = lr::prof_begin(lr::PROF_NN, st);
     auto launch = [&](auto kern) -> int {
         LR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHREADS, smem, st>>>(opa, opb, Na, Nb, n_rowblocks, n_coltiles, tps, nsplit, P.params, swap ? 1 : 0, P.cand,
+        kern<<<grid, NTHREADS, smem, st>>>(opa, opb, Na, Nb, n_rowblocks, n_coltiles, sc, P.params, swap ? 1 : 0, seed_cfg, P.cand,
                                            P.cand_cnt);
         return LR_OK;
     };
