@@ -121,6 +121,17 @@ int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, v
 int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
                     double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
 
+/* The same for `count` independent pairs (the reference's per-pair loop over a registration set,
+ * Experiments/test.py:108-167, sharded by rank as in data_loaders.py:111-116): src[i] / tgt[i] are device
+ * pointers to [n[i],3] fp32 correspondences.  Two pairs are in flight at a time on two internal streams with
+ * separate scratch, so one pair's single-block tail kernels run under the next pair's chip-filling ones and
+ * there is no host round trip between pairs.  T_out[16*count] [host], T_refit[16*count] [host, nullable],
+ * stats[count] [host, nullable]; results are those of `count` lr_ransac_rigid calls.  The work is ordered
+ * after what `stream` holds at the call; synchronises before returning. */
+int lr_ransac_rigid_batch(const float *const *src, const float *const *tgt, const int64_t *n, int count,
+                          const LrRansacParams *params, double *T_out, double *T_refit, LrRansacStats *stats,
+                          void *stream);
+
 /* Fed-sample parity hook (BASELINE.json: "same fed hypothesis triplets").
  * samples[H,m] int32 (m = 3 or 4).  counts[H] = exact inlier count of each
  * sample's Kabsch model, -1 where ELC rejects it; models[H,12] (nullable) =

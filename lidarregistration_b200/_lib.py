@@ -45,7 +45,7 @@ SAMPLER_UNIFORM, SAMPLER_PROSAC, SAMPLER_REPLACE = 0, 1, 2
 # every symbol include/lidarreg.h declares (tests check the .so exports them all)
 SYMBOLS = [
     "lr_last_error", "lr_version", "lr_device_info", "lr_shutdown", "lr_match_nn", "lr_match_mutual",
-    "lr_match_ratio", "lr_gather_xyz", "lr_ransac_rigid", "lr_ransac_score_samples", "lr_ransac_shard",
+    "lr_match_ratio", "lr_gather_xyz", "lr_ransac_rigid", "lr_ransac_rigid_batch", "lr_ransac_score_samples", "lr_ransac_shard",
     "lr_ransac_finalize", "lr_ransac_conf_iters", "lr_ransac_sample", "lr_refit_indexed",
     "lr_prof_enable", "lr_prof_read", "lr_peak_fp32", "lr_match_set_mode", "lr_transform_pad8", "lr_icp_step",
 ]

@@ -35,7 +35,7 @@ void set_error(const char *fmt, ...);
 // nothing else on the device.  Not shared between concurrent calls: every entry
 // point takes the arena lock for its duration (the reference path is called
 // from one Python thread per process, Experiments/test.py:108-167).
-enum Slot { SLOT_RANSAC = 0, SLOT_MATCH = 1, SLOT_MISC = 2, SLOT_COUNT = 3 };
+enum Slot { SLOT_RANSAC = 0, SLOT_MATCH = 1, SLOT_MISC = 2, SLOT_RANSAC_B = 3, SLOT_COUNT = 4 };
 
 struct Arena {
     void *ptr = nullptr;

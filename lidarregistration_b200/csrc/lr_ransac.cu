@@ -967,7 +967,7 @@ __global__ void k_scatter_models(const Ctl *ctl, const uint32_t *slot_id, const 
 // host side
 // ------------------------------------------------------------------------
 
-int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false)
+int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false, int slot = lr::SLOT_RANSAC)
 {
     ws.n_pad = ((n + kChunk - 1) / kChunk) * kChunk;
     if (ws.n_pad == 0) ws.n_pad = kChunk;
@@ -978,7 +978,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
                    lr::padded(sizeof(float4) * 4 * slots) + lr::padded(sizeof(double) * 12 * slots) +
                    lr::padded(sizeof(int) * slots) + lr::padded(sizeof(int) * (nrounds + 1)) +
                    lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1));
-    void *base = lr::arena_get(lr::SLOT_RANSAC, bytes);
+    void *base = lr::arena_get(slot, bytes);
     if (!base) return LR_ERR_ALLOC;
     lr::Carver cv(base);
     ws.ctl = cv.take<Ctl>(1);
@@ -1093,17 +1093,16 @@ void identity16(double *T)
     for (int k = 0; k < 16; ++k) T[k] = (k % 5 == 0) ? 1.0 : 0.0;
 }
 
-// model from key + mask + refit + D2H
-int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
-           uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st)
+// model from key + mask + refit (launches only)
+int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
+                  uint64_t key, bool want_refit, uint8_t *mask, bool want_stats, cudaStream_t st)
 {
     const double thr2 = p.threshold * p.threshold;
     if (p.sample_size == 3)
         k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
     else
         k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
-    const bool want_refit = (T_refit != nullptr) && p.refit;
-    if (want_refit || mask || stats) {
+    if (want_refit || mask || want_stats) {
         int blocks = (int)((n + 255) / 256);
         if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
         if (blocks < 1) blocks = 1;
@@ -1114,9 +1113,12 @@ int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &
         }
     }
     LR_CUDA_TRY(cudaGetLastError());
-    Ctl h;
-    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
-    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    return LR_OK;
+}
+
+// host copy of the control block -> the caller's outputs
+void finish_read(const Ctl &h, bool want_refit, double *T_out, double *T_refit, LrRansacStats *stats)
+{
     if (T_out) T12_to_16(h.T, T_out);
     if (T_refit) {
         if (want_refit) T12_to_16(h.Tref, T_refit);
@@ -1136,6 +1138,95 @@ int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &
         }
         stats->refit_count = h.refit_count;
     }
+}
+
+// model from key + mask + refit + D2H
+int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
+           uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st)
+{
+    const bool want_refit = (T_refit != nullptr) && p.refit;
+    int rc = finish_launch(src, tgt, n, p, ws, use_ctl_key, key, want_refit, mask, stats != nullptr, st);
+    if (rc) return rc;
+    Ctl h;
+    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    finish_read(h, want_refit, T_out, T_refit, stats);
+    return LR_OK;
+}
+
+// everything of one lr_ransac_rigid run up to (not including) the model read-back, enqueued on `st`
+int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, int slot, Ws &ws, cudaStream_t st)
+{
+    // With the confidence exit the round length is part of the result's
+    // definition (the exit is evaluated at round ends); with a fixed budget the
+    // result is a plain arg-max, so hypotheses are batched as large as the
+    // scratch allows to keep every launch chip-filling.
+    const bool use_conf = p.confidence < 1.0 && p.max_iters > 0;
+    const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
+    const int64_t nrounds = (p.max_iters + R - 1) / R;
+    int rc = ws_setup(n, R, nrounds, ws, p.sampler == LR_SAMPLER_PROSAC, slot);
+    if (rc) return rc;
+    rc = upload_growth(ws, n, p.sample_size, st);
+    if (rc) return rc;
+    rc = launch_pack(src, tgt, n, ws, st);
+    if (rc) return rc;
+    // confidence exit: need[r] = smallest best-count that lets the loop stop
+    // after round r (conf_iters is non-increasing in the count)
+    if (use_conf) {
+        std::vector<int> need((size_t)nrounds);
+        for (int64_t r = 0; r < nrounds; ++r) {
+            int64_t done = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
+            int64_t lo = 1, hi = n + 1;  // smallest c in [1, n] with conf_iters(c) <= done, else n + 1
+            while (lo < hi) {
+                int64_t mid = lo + (hi - lo) / 2;
+                if (lr_ransac_conf_iters(mid, n, p.sample_size, p.confidence, p.max_iters) <= done) hi = mid;
+                else lo = mid + 1;
+            }
+            need[r] = (int)lo;
+        }
+        // pageable source: the runtime stages it before returning, `need` may go out of scope
+        LR_CUDA_TRY(cudaMemcpyAsync(ws.need, need.data(), sizeof(int) * nrounds, cudaMemcpyHostToDevice, st));
+    }
+    for (int64_t r = 0; r < nrounds; ++r) {
+        int64_t lo = r * R, hi = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
+        rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
+        if (rc) return rc;
+        k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, nullptr);
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    return LR_OK;
+}
+
+// two internal streams + pinned staging for lr_ransac_rigid_batch, per device
+struct BatchCtx {
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+    Ctl *host = nullptr;
+    int host_cap = 0;
+};
+BatchCtx g_batch[64];
+
+int batch_ctx(int count, BatchCtx **out)
+{
+    int dev = 0;
+    LR_CUDA_TRY(cudaGetDevice(&dev));
+    LR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    BatchCtx &c = g_batch[dev];
+    if (!c.lane[0]) {
+        for (int l = 0; l < 2; ++l) {
+            LR_CUDA_TRY(cudaStreamCreateWithFlags(&c.lane[l], cudaStreamNonBlocking));
+            LR_CUDA_TRY(cudaEventCreateWithFlags(&c.done[l], cudaEventDisableTiming));
+        }
+        LR_CUDA_TRY(cudaEventCreateWithFlags(&c.start, cudaEventDisableTiming));
+    }
+    if (c.host_cap < count) {
+        if (c.host) cudaFreeHost(c.host);
+        c.host = nullptr;
+        c.host_cap = 0;
+        LR_CUDA_TRY(cudaMallocHost(&c.host, sizeof(Ctl) * (size_t)(count + 16)));
+        c.host_cap = count + 16;
+    }
+    *out = &c;
     return LR_OK;
 }
 
@@ -1172,45 +1263,73 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
         LR_CUDA_TRY(cudaStreamSynchronize(st));
         return LR_OK;
     }
-    // With the confidence exit the round length is part of the result's
-    // definition (the exit is evaluated at round ends); with a fixed budget the
-    // result is a plain arg-max, so hypotheses are batched as large as the
-    // scratch allows to keep every launch chip-filling.
-    const bool use_conf = p.confidence < 1.0 && p.max_iters > 0;
-    const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
-    const int64_t nrounds = (p.max_iters + R - 1) / R;
     Ws ws;
-    rc = ws_setup(n, R, nrounds, ws, p.sampler == LR_SAMPLER_PROSAC);
+    rc = enqueue_run(src, tgt, n, p, lr::SLOT_RANSAC, ws, st);
     if (rc) return rc;
-    rc = upload_growth(ws, n, p.sample_size, st);
-    if (rc) return rc;
-    rc = launch_pack(src, tgt, n, ws, st);
-    if (rc) return rc;
-    // confidence exit: need[r] = smallest best-count that lets the loop stop
-    // after round r (conf_iters is non-increasing in the count)
-    std::vector<int> need;
-    if (use_conf) {
-        need.resize(nrounds);
-        for (int64_t r = 0; r < nrounds; ++r) {
-            int64_t done = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
-            int64_t lo = 1, hi = n + 1;  // smallest c in [1, n] with conf_iters(c) <= done, else n + 1
-            while (lo < hi) {
-                int64_t mid = lo + (hi - lo) / 2;
-                if (lr_ransac_conf_iters(mid, n, p.sample_size, p.confidence, p.max_iters) <= done) hi = mid;
-                else lo = mid + 1;
-            }
-            need[r] = (int)lo;
-        }
-        LR_CUDA_TRY(cudaMemcpyAsync(ws.need, need.data(), sizeof(int) * nrounds, cudaMemcpyHostToDevice, st));
-    }
-    for (int64_t r = 0; r < nrounds; ++r) {
-        int64_t lo = r * R, hi = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
-        rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
-        if (rc) return rc;
-        k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, nullptr);
-    }
-    LR_CUDA_TRY(cudaGetLastError());
     return finish(src, tgt, n, p, ws, 1, 0, T_out, T_refit, mask, stats, st);
+}
+
+LR_EXPORT int lr_ransac_rigid_batch(const float *const *src, const float *const *tgt, const int64_t *n, int count,
+                                    const LrRansacParams *params, double *T_out, double *T_refit, LrRansacStats *stats,
+                                    void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(count >= 0 && (count == 0 || (src && tgt && n && T_out)), "null argument");
+    if (count == 0) return LR_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t n_max = 0;
+    for (int i = 0; i < count; ++i) {
+        int rc = check_params(params, n[i]);
+        if (rc) return rc;
+        LR_REQUIRE(n[i] == 0 || (src[i] && tgt[i]), "src/tgt is null");
+        n_max = n[i] > n_max ? n[i] : n_max;
+    }
+    const LrRansacParams &p = *params;
+    const bool want_refit = (T_refit != nullptr) && p.refit;
+    BatchCtx *ctx = nullptr;
+    int rc = batch_ctx(count, &ctx);
+    if (rc) return rc;
+    // Two pairs are in flight at any time, each with its own scratch and stream: the single-block tail of one
+    // pair (round end, model, refit) runs under the other pair's chip-filling kernels, and there is no host
+    // round trip between pairs.  Grow both arenas for the largest pair first: growing frees the old block.
+    {
+        const bool use_conf = p.confidence < 1.0 && p.max_iters > 0;
+        const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
+        Ws tmp;
+        for (int slot : {(int)lr::SLOT_RANSAC, (int)lr::SLOT_RANSAC_B}) {
+            rc = ws_setup(n_max, R, (p.max_iters + R - 1) / R, tmp, p.sampler == LR_SAMPLER_PROSAC, slot);
+            if (rc) return rc;
+        }
+    }
+    LR_CUDA_TRY(cudaEventRecord(ctx->start, st));
+    for (int l = 0; l < 2; ++l) LR_CUDA_TRY(cudaStreamWaitEvent(ctx->lane[l], ctx->start, 0));
+    for (int i = 0; i < count; ++i) {
+        if (n[i] < p.sample_size) continue;  // identity, filled in below
+        const int l = i & 1;
+        Ws ws;
+        rc = enqueue_run(src[i], tgt[i], n[i], p, l ? lr::SLOT_RANSAC_B : lr::SLOT_RANSAC, ws, ctx->lane[l]);
+        if (rc) return rc;
+        rc = finish_launch(src[i], tgt[i], n[i], p, ws, 1, 0, want_refit, nullptr, stats != nullptr, ctx->lane[l]);
+        if (rc) return rc;
+        LR_CUDA_TRY(cudaMemcpyAsync(&ctx->host[i], ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->lane[l]));
+    }
+    for (int l = 0; l < 2; ++l) {
+        LR_CUDA_TRY(cudaEventRecord(ctx->done[l], ctx->lane[l]));
+        LR_CUDA_TRY(cudaStreamWaitEvent(st, ctx->done[l], 0));
+    }
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < count; ++i) {
+        double *To = T_out + 16 * (size_t)i, *Tr = T_refit ? T_refit + 16 * (size_t)i : nullptr;
+        LrRansacStats *s = stats ? stats + i : nullptr;
+        if (n[i] < p.sample_size) {  // Open3D: |corres| < ransac_n -> identity (App. B)
+            identity16(To);
+            if (Tr) identity16(Tr);
+            if (s) *s = LrRansacStats{0, 0, 0, -1, -1, 0};
+        } else {
+            finish_read(ctx->host[i], want_refit, To, Tr, s);
+        }
+    }
+    return LR_OK;
 }
 
 LR_EXPORT int lr_ransac_score_samples(const float *src, const float *tgt, int64_t n, const int32_t *samples, int64_t H,

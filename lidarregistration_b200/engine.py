@@ -123,6 +123,30 @@ def ransac_rigid(src, tgt, params, want_mask=False):
     return out
 
 
+def ransac_rigid_batch(pairs, params):
+    """lr_ransac_rigid_batch: `pairs` = [(src, tgt), ...] of CUDA fp32 [n,3] tensors -> list of dicts as
+    ransac_rigid returns (no masks).  Two pairs in flight at a time, one host synchronisation for the batch."""
+    pairs = [(to_dev_f32(a), to_dev_f32(b)) for a, b in pairs]
+    k = len(pairs)
+    if k == 0:
+        return []
+    srcs = (ctypes.c_void_p * k)(*[a.data_ptr() for a, _ in pairs])
+    tgts = (ctypes.c_void_p * k)(*[b.data_ptr() for _, b in pairs])
+    ns = (ctypes.c_int64 * k)(*[a.shape[0] for a, _ in pairs])
+    T = (ctypes.c_double * (16 * k))()
+    Tr = (ctypes.c_double * (16 * k))()
+    st = (LrRansacStats * k)()
+    rc = _lib.lib().lr_ransac_rigid_batch(srcs, tgts, ns, ctypes.c_int(k), ctypes.byref(params), T, Tr, st,
+                                          _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_rigid_batch")
+    out = []
+    for i in range(k):
+        d = dict(T=_lib.T_from16(T[16 * i:16 * i + 16]), T_refit=_lib.T_from16(Tr[16 * i:16 * i + 16]), mask=None)
+        d.update(st[i].as_dict())
+        out.append(d)
+    return out
+
+
 def ransac_score_samples(src, tgt, samples, threshold=0.6, use_elc=True, elc_ratio=0.9, want_models=False):
     """Fed-sample parity hook -> (counts[H] int32 CUDA, best, models[H,12] | None)."""
     src, tgt = to_dev_f32(src), to_dev_f32(tgt)

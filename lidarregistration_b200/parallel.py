@@ -31,6 +31,19 @@ def shard_pairs(num_pairs, rank, world_size):
     return list(range(rank, num_pairs, world_size))
 
 
+def ransac_rigid_pairs(pairs, params, backend=None, group=None):
+    """RANSAC over this rank's share of a registration set: `pairs` is the WHOLE list of (src, tgt)
+    correspondence sets (or callables producing them); rank r runs pairs r, r + G, ... through one batched call
+    (engine.ransac_rigid_batch: two pairs in flight, no host round trip between pairs) and no collective.
+    Returns [(pair index, result dict), ...] for the pairs of this rank."""
+    if backend is None:
+        from . import engine as backend
+    rank, ws = world(group)
+    mine = shard_pairs(len(pairs), rank, ws)
+    data = [pairs[i]() if callable(pairs[i]) else pairs[i] for i in mine]
+    return list(zip(mine, backend.ransac_rigid_batch(data, params)))
+
+
 def shard_range(lo, hi, rank, world_size):
     """contiguous, near-equal slice of the hypothesis ids [lo, hi) owned by `rank`"""
     n = hi - lo

@@ -163,3 +163,23 @@ def test_full_budget_property_1M():
     assert int(res["mask"].sum()) == res["best_count"] == res["refit_count"]
     assert metrics.rotation_error_deg(res["T_refit"], d["T_gt"]) < 0.1
     assert metrics.translation_error_cm(res["T_refit"], d["T_gt"]) < 2.0
+
+
+def test_batch_equals_single_calls():
+    """lr_ransac_rigid_batch (two pairs in flight on internal streams) == one lr_ransac_rigid per pair (selection,
+    counts and model bit for bit, the least-squares refit within the north star's tolerance);
+    pairs of different sizes, a degenerate one (n < sample size) and the confidence exit included."""
+    sets = [synthetic.make_correspondences(n, r, seed=400 + k) for k, (n, r) in
+            enumerate([(3000, 0.3), (12000, 0.5), (2, 0.5), (7000, 0.1), (9000, 0.6)])]
+    pairs = [(torch.from_numpy(d["src"]).cuda(), torch.from_numpy(d["tgt"]).cuda()) for d in sets]
+    for kw in (dict(confidence=1.0, max_iters=60000), dict(confidence=0.999, max_iters=200000, round_size=8192)):
+        params = engine.make_params(threshold=0.6, seed=7, use_elc=True, **kw)
+        single = [engine.ransac_rigid(a, b, params) for a, b in pairs]
+        batch = engine.ransac_rigid_batch(pairs, params)
+        assert len(batch) == len(single)
+        for s1, b1 in zip(single, batch):
+            for key in ("best_id", "best_count", "iters_run", "n_scored", "refit_count"):
+                assert s1[key] == b1[key], key
+            assert np.array_equal(s1["T"], b1["T"])
+            assert close_T(s1["T_refit"], b1["T_refit"])  # the refit sums use fp64 atomics: order-dependent last bits
+    assert engine.ransac_rigid_batch([], params) == []

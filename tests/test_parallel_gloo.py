@@ -34,6 +34,15 @@ class OracleBackend:
             T = O.kabsch(src[s].astype(float), tgt[s].astype(float))
         return dict(T=T, best_id=hid, best_count=cnt)
 
+    @staticmethod
+    def ransac_rigid_batch(pairs, p):
+        out = []
+        for src, tgt in pairs:
+            r = O.ransac(src, tgt, m=p.sample_size, sampler=p.sampler, use_elc=bool(p.use_elc), thr=p.threshold,
+                         conf=p.confidence, max_iters=p.max_iters, round_size=p.round_size, seed=p.seed)
+            out.append(dict(T=r["T"], best_id=r["best_id"], best_count=r["best_count"]))
+        return out
+
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -47,6 +56,11 @@ def _worker(rank, world, port, q):
     rows = np.full((3 + rank, 22), float(rank))
     out["rows"] = parallel.gather_rows(rows).tolist()
     out["pairs"] = parallel.shard_pairs(11, rank, world)
+    # pairs of a set sharded by rank, no collective: every pair is run exactly once, by rank p mod G
+    sets = [synthetic.make_correspondences(400 + 50 * k, inlier_ratio=0.4, seed=900 + k) for k in range(5)]
+    p = engine.make_params(confidence=1.0, max_iters=500, seed=3, use_elc=True)
+    mine = parallel.ransac_rigid_pairs([(d["src"], d["tgt"]) for d in sets], p, backend=OracleBackend)
+    out["set"] = [(i, r["best_id"], r["best_count"]) for i, r in mine]
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -86,3 +100,9 @@ def test_world2_matches_single_process():
     assert rows.shape == (7, 22) and np.all(rows[:3] == 0) and np.all(rows[3:] == 1)
     assert res[0]["rows"] == res[1]["rows"]
     assert sorted(res[0]["pairs"] + res[1]["pairs"]) == list(range(11))
+    got = sorted(res[0]["set"] + res[1]["set"])
+    assert [g[0] for g in got] == list(range(5)) and [g[0] for g in res[1]["set"]] == [1, 3]
+    for k, bid, bcnt in got:
+        d = synthetic.make_correspondences(400 + 50 * k, inlier_ratio=0.4, seed=900 + k)
+        ref = O.ransac(d["src"], d["tgt"], conf=1.0, max_iters=500, seed=3)
+        assert (bid, bcnt) == (ref["best_id"], ref["best_count"]), k
