@@ -80,6 +80,11 @@ def run_reference(args):
     use_elc = not args.no_elc
     pairs = make_pairs(1, CFG_SEED)
     from oracle import lr_oracle as O
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        O.set_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        O.set_threads(os.cpu_count() or 1)
     cores = O.num_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_ransac_rate(pairs, use_elc)
@@ -305,6 +310,11 @@ def run_ours(args):
             line["mnn_match"] = bench_matching(engine, torch, dev)
             other = bench_other_regime(engine, torch, resident, not use_elc)
             line["other_regime"] = other
+            try:
+                from oracle import lr_oracle as _O
+                _O.set_threads(len(os.sched_getaffinity(0)))
+            except Exception:
+                pass
             cpu_pairs = make_pairs(1, CFG_SEED) * 8
             cpu_ransac_rate(cpu_pairs[:1], use_elc)  # warm the thread pool
             v, cores, secs = cpu_ransac_rate(cpu_pairs, use_elc)
