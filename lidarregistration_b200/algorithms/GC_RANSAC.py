@@ -38,8 +38,8 @@ def findRigidTransform(x1y1z1, x2y2z2, threshold, conf, spatial_coherence_weight
                                 sampler=engine.SAMPLER_PROSAC if int(sampler) == 1 else engine.SAMPLER_UNIFORM,
                                 use_elc=bool(use_sprt), elc_ratio=0.9,
                                 round_size=round_size, refit=True)
-    res = engine.ransac_rigid(x1y1z1, x2y2z2, params, want_mask=True)
-    mask = res["mask"].cpu().numpy()
+    res = engine.ransac_rigid(x1y1z1, x2y2z2, params, want_mask=True, mask_on_host=True)
+    mask = res["mask"]
     if res["best_count"] <= 0:  # 0 inliers: Python gets None (gcransac_python.cpp:594-611)
         return None, mask
     return res["T_refit"].T.copy(), mask

@@ -107,18 +107,28 @@ def make_params(threshold=0.6, confidence=1.0, max_iters=500000, seed=51, sample
     return p
 
 
-def ransac_rigid(src, tgt, params, want_mask=False):
-    """lr_ransac_rigid -> dict(T, T_refit, mask (CUDA bool) | None, + LrRansacStats fields)."""
+def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
+    """lr_ransac_rigid -> dict(T, T_refit, mask | None, + LrRansacStats fields).
+
+    mask: CUDA bool tensor, or with mask_on_host a numpy bool array: the kernel then writes the inlier bytes
+    straight into pinned, device-mapped host memory (unified addressing) and the call's own synchronisation
+    covers them -- no conversion kernel, no second copy, no second synchronisation."""
     src, tgt = to_dev_f32(src), to_dev_f32(tgt)
     n = src.shape[0]
     T = (ctypes.c_double * 16)()
     Tr = (ctypes.c_double * 16)()
     st = LrRansacStats()
-    mask = torch.empty(n, dtype=torch.uint8, device=src.device) if want_mask else None
+    mask = None
+    if want_mask:
+        mask = (torch.empty(n, dtype=torch.uint8, pin_memory=True) if mask_on_host
+                else torch.empty(n, dtype=torch.uint8, device=src.device))
+    mask_ptr = None if mask is None else ctypes.c_void_p(mask.data_ptr())
     rc = _lib.lib().lr_ransac_rigid(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), ctypes.byref(params), T, Tr,
-                                    _lib.ptr(mask), ctypes.byref(st), _lib.stream_ptr())
+                                    mask_ptr, ctypes.byref(st), _lib.stream_ptr())
     _lib.check(rc, "lr_ransac_rigid")
-    out = dict(T=_lib.T_from16(T), T_refit=_lib.T_from16(Tr), mask=mask.bool() if want_mask else None)
+    if mask is not None:
+        mask = mask.numpy().astype(bool) if mask_on_host else mask.bool()
+    out = dict(T=_lib.T_from16(T), T_refit=_lib.T_from16(Tr), mask=mask)
     out.update(st.as_dict())
     return out
 

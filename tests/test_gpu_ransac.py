@@ -183,3 +183,17 @@ def test_batch_equals_single_calls():
             assert np.array_equal(s1["T"], b1["T"])
             assert close_T(s1["T_refit"], b1["T_refit"])  # the refit sums use fp64 atomics: order-dependent last bits
     assert engine.ransac_rigid_batch([], params) == []
+
+
+def test_find_rigid_transform_mask_in_pinned_host_memory():
+    """The reference-facing call has its inlier mask written by the kernel straight into pinned host memory:
+    same mask as the device path, pose = the refit in pygcransac's row-vector convention."""
+    from lidarregistration_b200.algorithms import findRigidTransform
+    d = synthetic.make_correspondences(8000, 0.4, seed=77)
+    pose, mask = findRigidTransform(d["src"], d["tgt"], threshold=0.6, conf=1.0, spatial_coherence_weight=0.0,
+                                    max_iters=30000, use_sprt=True, min_inlier_ratio_for_sprt=-1, sampler=0,
+                                    neighborhood=0, neighborhood_size=20, seed=5)
+    params = engine.make_params(threshold=0.6, confidence=1.0, max_iters=30000, seed=5, use_elc=True, refit=True)
+    res = engine.ransac_rigid(d["src"], d["tgt"], params, want_mask=True)
+    assert mask.dtype == bool and np.array_equal(mask, res["mask"].cpu().numpy())
+    assert int(mask.sum()) == res["best_count"] and close_T(pose.T, res["T_refit"])

@@ -9,16 +9,31 @@ for (N, M) in [(300, 700), (1000, 130)]:
     mi, mj = engine.match_mutual(f0, f1, i1)
     _, o1, o2 = O.find_nn(f0, f1, True)
     assert np.array_equal(i1.cpu().numpy(), o1) and np.array_equal(i2.cpu().numpy(), o2)
-engine.match_set_mode(1)
-i1b, _ = engine.match_nn(f0, f1)
+for mode in (1, 2, 3):  # exact CUDA-core sweep, tcgen05 with fp32 / fp16 accumulators
+    engine.match_set_mode(mode)
+    i1b, i2b = engine.match_nn(f0, f1, want_2nd=True)
+    assert np.array_equal(i1b.cpu().numpy(), o1) and np.array_equal(i2b.cpu().numpy(), o2)
 engine.match_set_mode(0)
-assert np.array_equal(i1b.cpu().numpy(), o1)
+# unit-norm features: the K = 32 path with its masked tail; monotone targets: the event-overflow scan
+g0 = f0 / np.linalg.norm(f0, axis=1, keepdims=True); g1 = f1 / np.linalg.norm(f1, axis=1, keepdims=True)
+w = np.linspace(0, 1, 3000, dtype=np.float32)[:, None]
+h1 = (1 - w) * rng.standard_normal((3000, 32)).astype(np.float32) + w * g0[0]
+h1 /= np.linalg.norm(h1, axis=1, keepdims=True)
+for a, b in ((g0, g1), (g0[:40], h1)):
+    j1, j2 = engine.match_nn(a, b, want_2nd=True)
+    _, p1, p2 = O.find_nn(a, b, True)
+    assert np.array_equal(j1.cpu().numpy(), p1) and np.array_equal(j2.cpu().numpy(), p2)
 d = synthetic.make_correspondences(3000, 0.3, seed=4)
 for sampler, m in ((0, 3), (1, 3), (2, 4)):
     p = engine.make_params(max_iters=20000, round_size=4096, sampler=sampler, sample_size=m, confidence=0.999)
     r = engine.ransac_rigid(d["src"], d["tgt"], p, want_mask=True)
     ref = O.ransac(d["src"], d["tgt"], m=m, sampler=sampler, conf=0.999, max_iters=20000, round_size=4096)
     assert r["best_id"] == ref["best_id"] and r["best_count"] == ref["best_count"]
+pairs = [(torch.from_numpy(d["src"]).cuda(), torch.from_numpy(d["tgt"]).cuda())] * 3
+pb = engine.make_params(max_iters=20000, confidence=1.0)
+rb = engine.ransac_rigid_batch(pairs, pb)
+rs = engine.ransac_rigid(*pairs[0], pb)
+assert all(x["best_id"] == rs["best_id"] and x["best_count"] == rs["best_count"] for x in rb)
 s = rng.integers(0, 3000, (5000, 3)).astype(np.int32)
 c, b, _ = engine.ransac_score_samples(d["src"], d["tgt"], s)
 oc, ob = O.score_samples(d["src"], d["tgt"], s, 0.6)
