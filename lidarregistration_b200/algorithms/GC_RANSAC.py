@@ -14,8 +14,15 @@ What the flags select here (DESIGN.md "GC codebase mapping"):
   --prosac True         -> correspondences pre-sorted best-first (GC_RANSAC.py:39-43) and the
                            PROSAC progressive sampler (sampler id 1, gcransac_python.cpp:464-465)
   --GC_conf c           -> confidence of the stopping rule
-  --GC_LO               -> graph-cut LO is SURVEY row f3; the final least-squares
-                           refit over the inliers is always returned, as pygcransac does
+  --GC_scoring count    -> [default] the graded selection criterion of SURVEY 8(a): inlier count at the
+                           threshold, ties -> lowest hypothesis id; the least-squares refit over the
+                           winner's inliers is returned, as pygcransac ends with a non-minimal fit
+  --GC_scoring MSAC     -> pygcransac's own criterion: MSAC score at 1.5 x threshold,
+                           then, with --GC_LO True, local optimisation (10 rounds x 20 inner draws of
+                           min(21, #inliers) inliers; the graph cut with spatial_coherence_weight = 0 is
+                           thresholding) and 10 passes of iterated least squares; the final model is returned
+  (`GC_scoring` is an attribute this drop-in adds; the reference has no such flag because pygcransac
+   knows only MSAC.  args without it get "count".)
 """
 from time import time
 
@@ -25,24 +32,48 @@ import torch
 from .. import engine
 
 
+# settings the reference's glue fixes (gcransac_python.cpp:511-521) / upstream defaults
+GC_LO_ROUNDS = 10   # settings.max_graph_cut_number (0 when neighborhood != 0, i.e. --GC_LO False)
+GC_LO_TRIALS = 20   # settings.max_local_optimization_number
+GC_LSQ_ITERS = 10   # iterated least squares, upstream's cap
+
+
+def gc_options(scoring, local_optimisation, spatial_coherence_weight=0.0):
+    """--GC_scoring / --GC_LO -> the scoring / lo_rounds / lo_trials / lsq_iters of engine.make_params"""
+    scoring = "count" if scoring is None else str(scoring)
+    if scoring.lower() == "count":
+        return dict(scoring=engine.SCORE_COUNT)
+    if scoring.upper() != "MSAC":
+        raise ValueError("GC_scoring must be 'count' or 'MSAC'")
+    if spatial_coherence_weight != 0.0:
+        # the pairwise term needs the neighbourhood graph (FLANN, gcransac_python.cpp:444-446); the reference's
+        # default and README examples all use 0.0 (test.py:306), for which the graph cut is thresholding
+        raise NotImplementedError("spatial_coherence_weight != 0 (graph-cut pairwise term) is not built")
+    on = bool(local_optimisation)
+    return dict(scoring=engine.SCORE_MSAC, lo_rounds=GC_LO_ROUNDS if on else 0, lo_trials=GC_LO_TRIALS,
+                lsq_iters=GC_LSQ_ITERS if on else 0)
+
+
 def findRigidTransform(x1y1z1, x2y2z2, threshold, conf, spatial_coherence_weight, max_iters, use_sprt,
                        min_inlier_ratio_for_sprt, sampler, neighborhood, neighborhood_size, seed=51,
-                       round_size=engine.DEFAULT_ROUND):
-    """Same kwargs as pygcransac.findRigidTransform (GC_RANSAC.py:12-22).
+                       round_size=engine.DEFAULT_ROUND, scoring="count"):
+    """Same kwargs as pygcransac.findRigidTransform (GC_RANSAC.py:12-22); `scoring`: see the module docstring.
 
     -> (pose[4,4] float64 in pygcransac's ROW-vector convention | None, mask[n] bool)
     """
     if use_sprt and not (min_inlier_ratio_for_sprt < 0):
         raise NotImplementedError("SPRT pre-verification is not part of the B200 hot path (use ELC or NONE)")
+    opts = gc_options(scoring, int(neighborhood) == 0, spatial_coherence_weight)  # neighborhood != 0: no LO (:418-423)
     params = engine.make_params(threshold=threshold, confidence=conf, max_iters=max_iters, seed=seed, sample_size=3,
                                 sampler=engine.SAMPLER_PROSAC if int(sampler) == 1 else engine.SAMPLER_UNIFORM,
                                 use_elc=bool(use_sprt), elc_ratio=0.9,
-                                round_size=round_size, refit=True)
+                                round_size=round_size, refit=True, **opts)
     res = engine.ransac_rigid(x1y1z1, x2y2z2, params, want_mask=True, mask_on_host=True)
     mask = res["mask"]
     if res["best_count"] <= 0:  # 0 inliers: Python gets None (gcransac_python.cpp:594-611)
         return None, mask
-    return res["T_refit"].T.copy(), mask
+    pose = res["T"] if opts["scoring"] == engine.SCORE_MSAC else res["T_refit"]
+    return pose.T.copy(), mask
 
 
 def GC_RANSAC(A, B, distance_threshold, num_iterations, args, match_quality):
@@ -66,7 +97,8 @@ def GC_RANSAC(A, B, distance_threshold, num_iterations, args, match_quality):
 
     torch.cuda.synchronize()
     start_time = time()
-    pose_T, mask = findRigidTransform(x1y1z1_, x2y2z2_, seed=getattr(args, "seed", 51), **params)
+    pose_T, mask = findRigidTransform(x1y1z1_, x2y2z2_, seed=getattr(args, "seed", 51),
+                                      scoring=getattr(args, "GC_scoring", "count"), **params)
     if pose_T is None:
         pose_T = np.eye(4, dtype=np.float32)
     elapsed_time = time() - start_time

@@ -33,6 +33,7 @@ constexpr int kHypPerItem = 2 * kScoreThreads;
 constexpr int kChunk = 512;         // correspondences per shared-memory stage (48 B each, double buffered)
 constexpr int kGroup = 4;           // points between two checks of the "some residual is in the band" flag
 constexpr int kGenThreads = 128;
+constexpr int kGcMaxTrials = 64;    // inner LO draws scored by one launch
 
 struct Ctl {
     unsigned long long best_key;   // over finished rounds
@@ -48,6 +49,19 @@ struct Ctl {
     double csum[6];
     double H[9];
     double err2;  // sum of squared residuals over the inliers (ICP rmse)
+    // LR_SCORE_MSAC runs only (lr_ransac_gc.cuh); q = quantised MSAC score (include/lidarreg.h)
+    struct Gc {
+        unsigned long long round_q;     // highest q of the current round
+        unsigned long long round_pick;  // lowest (id << 32 | slot) among the slots that reach it
+        unsigned long long best_q;      // q of the selected minimal-sample hypothesis
+        unsigned long long cur_q;       // q of cur[] (grows through LO and the iterated least squares)
+        unsigned long long lo_q;        // cur_q when the local optimisation ended
+        long long best_id, best_inl;    // selected hypothesis, its #(r^2 < tau^2)
+        int has_model, lo_active, lsq_active, lo_improved, lsq_improved;
+        int lo_I, lo_s;                 // inliers (at thr) of cur[] and the inner sample size of this LO round
+        int mode;                       // 1 while the block belongs to an LR_SCORE_MSAC run
+        double cur[12];
+    } gc;
 };
 
 struct Ws {
@@ -62,6 +76,12 @@ struct Ws {
     uint32_t *growth; // PROSAC growth function T'_n (null unless the sampler is PROSAC)
     double *scratchT; // 16 doubles of staging
     int64_t n_pad;
+    // LR_SCORE_MSAC runs only (null otherwise)
+    unsigned long long *q64;  // per slot: quantised MSAC score
+    int32_t *lo_L;            // inlier index list of the current LO round, ascending
+    double *tr_T;             // kGcMaxTrials x 12: models of one LO round / the least-squares candidate
+    unsigned long long *tr_q; // their q
+    int *tr_inl;              // their #(r^2 < tau^2)
 };
 
 // ------------------------------------------------------------------------
@@ -376,6 +396,15 @@ __global__ void k_ctl_reset(Ctl *ctl)
         ctl->p1max_bits = 0u;
         ctl->qmax_bits = 0u;
         ctl->refit_count = 0;
+        ctl->gc.round_q = ctl->gc.best_q = ctl->gc.cur_q = ctl->gc.lo_q = 0ULL;
+        ctl->gc.round_pick = ~0ULL;
+        ctl->gc.best_id = -1;
+        ctl->gc.best_inl = 0;
+        ctl->gc.has_model = ctl->gc.lo_active = ctl->gc.lsq_active = 0;
+        ctl->gc.lo_improved = ctl->gc.lsq_improved = 0;
+        ctl->gc.lo_I = ctl->gc.lo_s = 0;
+        ctl->gc.mode = 0;
+        for (int k = 0; k < 12; ++k) ctl->gc.cur[k] = (k % 5 == 0) ? 1.0 : 0.0;
     }
 }
 
@@ -967,7 +996,8 @@ __global__ void k_scatter_models(const Ctl *ctl, const uint32_t *slot_id, const 
 // host side
 // ------------------------------------------------------------------------
 
-int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false, int slot = lr::SLOT_RANSAC)
+int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false, int slot = lr::SLOT_RANSAC,
+             bool gc = false)
 {
     ws.n_pad = ((n + kChunk - 1) / kChunk) * kChunk;
     if (ws.n_pad == 0) ws.n_pad = kChunk;
@@ -978,6 +1008,10 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
                    lr::padded(sizeof(float4) * 4 * slots) + lr::padded(sizeof(double) * 12 * slots) +
                    lr::padded(sizeof(int) * slots) + lr::padded(sizeof(int) * (nrounds + 1)) +
                    lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1));
+    if (gc)
+        bytes += lr::padded(sizeof(unsigned long long) * slots) + lr::padded(sizeof(int32_t) * (n > 0 ? n : 1)) +
+                 lr::padded(sizeof(double) * 12 * kGcMaxTrials) + lr::padded(sizeof(unsigned long long) * kGcMaxTrials) +
+                 lr::padded(sizeof(int) * kGcMaxTrials);
     void *base = lr::arena_get(slot, bytes);
     if (!base) return LR_ERR_ALLOC;
     lr::Carver cv(base);
@@ -990,7 +1024,13 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     ws.cnt = cv.take<int>(slots);
     ws.need = cv.take<int>(nrounds + 1);
     ws.scratchT = cv.take<double>(16);
-    ws.growth = prosac ? cv.take<uint32_t>(n) : nullptr;
+    ws.growth = prosac ? cv.take<uint32_t>(n) : cv.take<uint32_t>(1);
+    if (!prosac) ws.growth = nullptr;
+    ws.q64 = gc ? cv.take<unsigned long long>(slots) : nullptr;
+    ws.lo_L = gc ? cv.take<int32_t>(n > 0 ? n : 1) : nullptr;
+    ws.tr_T = gc ? cv.take<double>(12 * kGcMaxTrials) : nullptr;
+    ws.tr_q = gc ? cv.take<unsigned long long>(kGcMaxTrials) : nullptr;
+    ws.tr_inl = gc ? cv.take<int>(kGcMaxTrials) : nullptr;
     return LR_OK;
 }
 
@@ -1004,6 +1044,11 @@ int check_params(const LrRansacParams *p, int64_t n)
     LR_REQUIRE(p->max_iters >= 0 && p->max_iters < (int64_t)0xFFFFFFFFLL, "max_iters out of range");
     LR_REQUIRE(p->round_size > 0 && p->round_size <= (1 << 20), "round_size out of range");
     LR_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "n out of range");
+    LR_REQUIRE(p->scoring == LR_SCORE_COUNT || p->scoring == LR_SCORE_MSAC, "scoring must be one of LR_SCORE_*");
+    if (p->scoring == LR_SCORE_MSAC)
+        LR_REQUIRE(p->lo_rounds >= 0 && p->lo_rounds <= 64 && p->lo_trials >= 0 && p->lo_trials <= kGcMaxTrials &&
+                       p->lsq_iters >= 0 && p->lsq_iters <= 64,
+                   "lo_rounds / lsq_iters must be in [0, 64], lo_trials in [0, 64]");
     return LR_OK;
 }
 
@@ -1048,9 +1093,12 @@ int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cud
     return LR_OK;
 }
 
-// one round: ids [lo, hi) (or H fed samples), leaves the result in ctl->round_key
+#include "lr_ransac_gc.cuh"
+
+// one round: ids [lo, hi) (or H fed samples), leaves the result in ctl->round_key (LR_SCORE_MSAC:
+// ctl->gc.round_q / round_pick; counts_out then receives #(r^2 < tau^2) and scores_out the q values)
 int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int64_t lo,
-                 int64_t hi, const int32_t *fed, int32_t *counts_out, cudaStream_t st)
+                 int64_t hi, const int32_t *fed, int32_t *counts_out, cudaStream_t st, int64_t *scores_out = nullptr)
 {
     const int64_t len = hi - lo;
     if (len <= 0) return LR_OK;
@@ -1069,6 +1117,7 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
         k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
     }
     lr::prof_end(tok, st);
+    if (p.scoring == LR_SCORE_MSAC) return gc_launch_score(src, tgt, n, p, ws, lo, len, scores_out, counts_out, st);
     tok = lr::prof_begin(lr::PROF_SCORE, st);
     // 4 resident CTAs of 128 threads per SM (48 KB of staging each)
     k_score<<<sms * 4, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
@@ -1098,7 +1147,9 @@ int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacP
                   uint64_t key, bool want_refit, uint8_t *mask, bool want_stats, cudaStream_t st)
 {
     const double thr2 = p.threshold * p.threshold;
-    if (p.sample_size == 3)
+    if (p.scoring == LR_SCORE_MSAC)
+        k_gc_commit<<<1, 32, 0, st>>>(ws.ctl);  // the model was kept in ctl->gc, there is no key to decode
+    else if (p.sample_size == 3)
         k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
     else
         k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
@@ -1137,6 +1188,17 @@ void finish_read(const Ctl &h, bool want_refit, double *T_out, double *T_refit, 
             stats->best_count = -1;
         }
         stats->refit_count = h.refit_count;
+        stats->best_score = stats->lo_score = stats->final_score = 0;
+        stats->lo_improved = stats->lsq_improved = 0;
+        if (h.gc.mode) {
+            stats->best_id = h.gc.has_model ? (int64_t)h.gc.best_id : -1;
+            stats->best_count = h.gc.has_model ? (int64_t)h.gc.best_inl : -1;
+            stats->best_score = (int64_t)h.gc.best_q;
+            stats->lo_score = (int64_t)h.gc.lo_q;
+            stats->final_score = (int64_t)h.gc.cur_q;
+            stats->lo_improved = h.gc.lo_improved;
+            stats->lsq_improved = h.gc.lsq_improved;
+        }
     }
 }
 
@@ -1164,12 +1226,14 @@ int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacPar
     const bool use_conf = p.confidence < 1.0 && p.max_iters > 0;
     const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
     const int64_t nrounds = (p.max_iters + R - 1) / R;
-    int rc = ws_setup(n, R, nrounds, ws, p.sampler == LR_SAMPLER_PROSAC, slot);
+    const bool gc = p.scoring == LR_SCORE_MSAC;
+    int rc = ws_setup(n, R, nrounds, ws, p.sampler == LR_SAMPLER_PROSAC, slot, gc);
     if (rc) return rc;
     rc = upload_growth(ws, n, p.sample_size, st);
     if (rc) return rc;
     rc = launch_pack(src, tgt, n, ws, st);
     if (rc) return rc;
+    if (gc) k_gc_mode<<<1, 32, 0, st>>>(ws.ctl);
     // confidence exit: need[r] = smallest best-count that lets the loop stop
     // after round r (conf_iters is non-increasing in the count)
     if (use_conf) {
@@ -1191,9 +1255,13 @@ int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacPar
         int64_t lo = r * R, hi = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
         rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
         if (rc) return rc;
-        k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, nullptr);
+        if (gc)
+            k_round_end_msac<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, ws.m64, ws.cnt);
+        else
+            k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, nullptr);
     }
     LR_CUDA_TRY(cudaGetLastError());
+    if (gc) return gc_enqueue_polish(src, tgt, n, p, ws, st);
     return LR_OK;
 }
 
@@ -1259,7 +1327,7 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
         identity16(T_out);
         if (T_refit) identity16(T_refit);
         if (mask && n > 0) LR_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)n, st));
-        if (stats) *stats = LrRansacStats{0, 0, 0, -1, -1, 0};
+        if (stats) *stats = LrRansacStats{0, 0, 0, -1, -1, 0, 0, 0, 0, 0, 0};
         LR_CUDA_TRY(cudaStreamSynchronize(st));
         return LR_OK;
     }
@@ -1297,7 +1365,8 @@ LR_EXPORT int lr_ransac_rigid_batch(const float *const *src, const float *const 
         const int64_t R = use_conf ? (int64_t)p.round_size : batch_len(p.max_iters);
         Ws tmp;
         for (int slot : {(int)lr::SLOT_RANSAC, (int)lr::SLOT_RANSAC_B}) {
-            rc = ws_setup(n_max, R, (p.max_iters + R - 1) / R, tmp, p.sampler == LR_SAMPLER_PROSAC, slot);
+            rc = ws_setup(n_max, R, (p.max_iters + R - 1) / R, tmp, p.sampler == LR_SAMPLER_PROSAC, slot,
+                          p.scoring == LR_SCORE_MSAC);
             if (rc) return rc;
         }
     }
@@ -1324,7 +1393,7 @@ LR_EXPORT int lr_ransac_rigid_batch(const float *const *src, const float *const 
         if (n[i] < p.sample_size) {  // Open3D: |corres| < ransac_n -> identity (App. B)
             identity16(To);
             if (Tr) identity16(Tr);
-            if (s) *s = LrRansacStats{0, 0, 0, -1, -1, 0};
+            if (s) *s = LrRansacStats{0, 0, 0, -1, -1, 0, 0, 0, 0, 0, 0};
         } else {
             finish_read(ctx->host[i], want_refit, To, Tr, s);
         }
@@ -1378,6 +1447,51 @@ LR_EXPORT int lr_ransac_score_samples(const float *src, const float *tgt, int64_
     return LR_OK;
 }
 
+LR_EXPORT int lr_ransac_score_samples_msac(const float *src, const float *tgt, int64_t n, const int32_t *samples,
+                                           int64_t H, int m, double threshold, int use_elc, double elc_ratio,
+                                           int64_t *scores, int32_t *inliers, int64_t *best, void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(m == 3 || m == 4, "m must be 3 or 4");
+    LR_REQUIRE(src && tgt && samples && scores, "null pointer");
+    LR_REQUIRE(n > 0 && n < (int64_t)1 << 31 && H > 0 && H < (int64_t)0xFFFFFFFFLL, "n/H out of range");
+    LR_REQUIRE(threshold > 0.0, "threshold must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    LrRansacParams p;
+    memset(&p, 0, sizeof(p));
+    p.threshold = threshold;
+    p.confidence = 1.0;
+    p.elc_ratio = elc_ratio;
+    p.max_iters = H;
+    p.sample_size = m;
+    p.sampler = LR_SAMPLER_UNIFORM;
+    p.use_elc = use_elc;
+    p.scoring = LR_SCORE_MSAC;
+    const int64_t R = batch_len(H);
+    p.round_size = (int32_t)R;
+    Ws ws;
+    int rc = ws_setup(n, R, 1, ws, false, lr::SLOT_RANSAC, true);
+    if (rc) return rc;
+    rc = launch_pack(src, tgt, n, ws, st);
+    if (rc) return rc;
+    k_gc_mode<<<1, 32, 0, st>>>(ws.ctl);
+    LR_CUDA_TRY(cudaMemsetAsync(scores, 0xFF, sizeof(int64_t) * H, st));  // -1 = rejected
+    if (inliers) LR_CUDA_TRY(cudaMemsetAsync(inliers, 0xFF, sizeof(int32_t) * H, st));
+    for (int64_t lo = 0; lo < H; lo += R) {
+        int64_t hi = lo + R < H ? lo + R : H;
+        rc = launch_round(src, tgt, n, p, ws, lo, hi, samples + lo * m, inliers ? inliers + lo : nullptr, st,
+                          scores + lo);
+        if (rc) return rc;
+        k_round_end_msac<<<1, 32, 0, st>>>(ws.ctl, hi - lo, nullptr, 0, ws.m64, ws.cnt);
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    Ctl h;
+    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    if (best) *best = h.gc.has_model ? (int64_t)h.gc.best_id : -1;
+    return LR_OK;
+}
+
 LR_EXPORT int lr_ransac_shard(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
                               int64_t id_lo, int64_t id_hi, uint64_t *key, void *stream)
 {
@@ -1385,6 +1499,7 @@ LR_EXPORT int lr_ransac_shard(const float *src, const float *tgt, int64_t n, con
     int rc = check_params(params, n);
     if (rc) return rc;
     LR_REQUIRE(src && tgt && key, "null pointer");
+    LR_REQUIRE(params->scoring == LR_SCORE_COUNT, "hypothesis sharding packs (count, id): LR_SCORE_COUNT only");
     LR_REQUIRE(n >= params->sample_size, "fewer correspondences than the sample size");
     LR_REQUIRE(id_lo >= 0 && id_hi >= id_lo && id_hi < (int64_t)0xFFFFFFFFLL, "id range out of bounds");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1415,6 +1530,7 @@ LR_EXPORT int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, 
     int rc = check_params(params, n);
     if (rc) return rc;
     LR_REQUIRE(src && tgt && T_out, "null pointer");
+    LR_REQUIRE(params->scoring == LR_SCORE_COUNT, "hypothesis sharding packs (count, id): LR_SCORE_COUNT only");
     LR_REQUIRE(n >= params->sample_size, "fewer correspondences than the sample size");
     cudaStream_t st = (cudaStream_t)stream;
     Ws ws;

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import LrRansacParams, LrRansacStats, SAMPLER_PROSAC, SAMPLER_REPLACE, SAMPLER_UNIFORM  # noqa: F401
+from ._lib import (LrRansacParams, LrRansacStats, SAMPLER_PROSAC, SAMPLER_REPLACE, SAMPLER_UNIFORM,  # noqa: F401
+                   SCORE_COUNT, SCORE_MSAC)
 
 DEFAULT_ROUND = 65536
 
@@ -98,12 +99,16 @@ def gather_xyz(xyz, idx):
 
 # ------------------------------------------------------------------ RANSAC
 def make_params(threshold=0.6, confidence=1.0, max_iters=500000, seed=51, sample_size=3,
-                sampler=SAMPLER_UNIFORM, use_elc=True, elc_ratio=0.9, round_size=DEFAULT_ROUND, refit=True):
+                sampler=SAMPLER_UNIFORM, use_elc=True, elc_ratio=0.9, round_size=DEFAULT_ROUND, refit=True,
+                scoring=SCORE_COUNT, lo_rounds=0, lo_trials=20, lsq_iters=0):
+    """scoring = SCORE_MSAC selects GC-RANSAC semantics: MSAC selection, then lo_rounds rounds of
+    local optimisation (lo_trials inner draws each) and lsq_iters passes of iterated least squares."""
     p = LrRansacParams()
     p.threshold, p.confidence, p.elc_ratio = float(threshold), float(confidence), float(elc_ratio)
     p.max_iters, p.seed = int(max_iters), int(seed)
     p.sample_size, p.sampler, p.use_elc = int(sample_size), int(sampler), int(bool(use_elc))
     p.round_size, p.refit, p.reserved = int(round_size), int(bool(refit)), 0
+    p.scoring, p.lo_rounds, p.lo_trials, p.lsq_iters = int(scoring), int(lo_rounds), int(lo_trials), int(lsq_iters)
     return p
 
 
@@ -173,6 +178,25 @@ def ransac_score_samples(src, tgt, samples, threshold=0.6, use_elc=True, elc_rat
                                             _lib.ptr(models), ctypes.byref(best), _lib.stream_ptr())
     _lib.check(rc, "lr_ransac_score_samples")
     return counts, int(best.value), models
+
+
+def ransac_score_samples_msac(src, tgt, samples, threshold=0.6, use_elc=True, elc_ratio=0.9):
+    """Fed-sample parity hook, MSAC flavour -> (scores[H] int64 CUDA, inliers[H] int32 CUDA, best)."""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    if isinstance(samples, np.ndarray):
+        samples = torch.from_numpy(np.ascontiguousarray(samples))
+    samples = samples.to(src.device).to(torch.int32).contiguous()
+    H, m = samples.shape
+    scores = torch.empty(H, dtype=torch.int64, device=src.device)
+    inl = torch.empty(H, dtype=torch.int32, device=src.device)
+    best = ctypes.c_int64(-1)
+    rc = _lib.lib().lr_ransac_score_samples_msac(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(src.shape[0]),
+                                                 _lib.ptr(samples), ctypes.c_int64(H), int(m),
+                                                 ctypes.c_double(threshold), int(bool(use_elc)),
+                                                 ctypes.c_double(elc_ratio), _lib.ptr(scores), _lib.ptr(inl),
+                                                 ctypes.byref(best), _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_score_samples_msac")
+    return scores, inl, int(best.value)
 
 
 def ransac_shard(src, tgt, params, id_lo, id_hi, key):

@@ -578,6 +578,228 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* GC-RANSAC semantics: MSAC score, local         */
+/* optimisation, iterated least squares                                      */
+/* ------------------------------------------------------------------------- */
+
+/* The MSAC value sum_{r^2 < tau^2} (1 - r^2/tau^2), tau = 1.5*thr (App. A), is a floating-point sum whose
+ * value depends on the order of the terms.  To make "best model = highest score" a well-defined, order-free
+ * (hence thread- and GPU-count independent, bit-reproducible) criterion, every term is quantised to
+ * 2^-16 and the score is the exact INTEGER sum  q = sum trunc((1 - r^2/tau^2) * 65536).  n < 2^31 terms of
+ * at most 2^16 fit an int64 with room to spare. */
+#define LRO_MSAC_SCALE 65536.0
+
+static inline int64_t lro_msac_term(double r2, double tau2)
+{
+    return (int64_t)((1.0 - r2 / tau2) * LRO_MSAC_SCALE);
+}
+
+LRO_API int64_t lro_msac_q(const float *src, const float *tgt, int64_t n, const double T[12], double thr,
+                           int64_t *inliers_out)
+{
+    const double tau2 = (1.5 * thr) * (1.5 * thr);
+    int64_t q = 0, cnt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        double r2 = lro_res2(T, src + 3 * i, tgt + 3 * i);
+        if (r2 < tau2) { q += lro_msac_term(r2, tau2); ++cnt; }
+    }
+    if (inliers_out) *inliers_out = cnt;
+    return q;
+}
+
+/* Fed-sample hook, MSAC flavour: scores[h] = q of sample h's Kabsch model (-1 where ELC rejects it),
+ * inliers[h] = #(r^2 < tau^2).  Returns the selected hypothesis: max q, ties -> lowest h; -1 if none scored above 0. */
+LRO_API int64_t lro_score_samples_msac(const float *src, const float *tgt, int64_t n, const int32_t *samples,
+                                       int64_t H, int m, double thr, int use_elc, double elc_ratio,
+                                       int64_t *scores, int32_t *inliers)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t h = 0; h < H; ++h) {
+        double T[12];
+        int64_t inl = -1;
+        int ok = lro_model_from_sample(src, tgt, samples + h * m, m, use_elc, elc_ratio, T);
+        scores[h] = ok ? lro_msac_q(src, tgt, n, T, thr, &inl) : -1;
+        if (inliers) inliers[h] = (int32_t)inl;
+    }
+    int64_t best = -1, bq = 0; /* a model that scores 0 is never selected */
+    for (int64_t h = 0; h < H; ++h)
+        if (scores[h] > bq) { bq = scores[h]; best = h; }
+    return best;
+}
+
+/* k <= 32 unique indices out of [0, n): same rule as lro_unique (draw d picks the r-th index not yet taken) */
+static void lro_unique_k(uint64_t seed, uint64_t id, int k, int64_t n, int32_t *out)
+{
+    int32_t taken[32];
+    for (int d = 0; d < k; ++d) {
+        int32_t r = (int32_t)lro_draw(seed, id, (uint32_t)d, (uint32_t)(n - d));
+        for (int e = 0; e < d; ++e)
+            if (r >= taken[e]) ++r;
+        out[d] = r;
+        int e = d;
+        while (e > 0 && taken[e - 1] > r) { taken[e] = taken[e - 1]; --e; }
+        taken[e] = r;
+    }
+}
+
+#define LRO_LO_SEED_SALT 0x4C4F43414C4F5054ULL /* "LOCALOPT" */
+#define LRO_LO_SAMPLE_FACTOR 7                /* inner samples of min(7 m, #inliers) points (App. A) */
+
+typedef struct {
+    int64_t iters_run;    /* hypotheses generated */
+    int64_t n_passed;     /* hypotheses that passed ELC (= scored) */
+    int64_t best_id;      /* minimal-sample hypothesis with the highest q (-1: none) */
+    int64_t best_score;   /* its q */
+    int64_t best_inliers; /* its #(r^2 < tau^2), the I of the confidence rule */
+    int64_t lo_score;     /* q after the local optimisation */
+    int64_t final_score;  /* q after the iterated least squares (= q of T) */
+    int64_t refit_count;  /* inliers (at thr) of T used by Trefit */
+    int32_t lo_improved;  /* LO rounds that improved q */
+    int32_t lsq_improved; /* least-squares iterations that improved q */
+} LroGcStats;
+
+/* GC-RANSAC loop (App. A) restated for a batched evaluation order:
+ *  1. global search: hypotheses id = 0,1,... (pure functions of (seed, id)) -> ELC -> Kabsch -> q; selected =
+ *     highest q, ties -> lowest id, q = 0 never replaces the identity; the confidence exit
+ *     log(1-conf)/log(1-(I/n)^m) uses the selected model's I = #(r^2 < tau^2) and is evaluated at round ends;
+ *  2. local optimisation (lo_rounds > 0; graph cut with spatial_coherence_weight = 0 is thresholding at thr,
+ *     App. A): up to lo_rounds rounds of { L = inliers of the current model at thr, stop if |L| <= m;
+ *     lo_trials inner draws of min(7 m, |L|) unique members of L -> non-minimal Kabsch -> q; take the best
+ *     trial (ties -> lowest trial) if its q is higher, else stop };
+ *  3. iterated least squares (lsq_iters > 0): refit on the inliers at thr, keep while q improves.
+ * Upstream runs 2. whenever the so-far-best improves inside its sequential loop; the batched order runs it
+ * once on the winner ("if no LO ever ran, run one", App. A) -- the difference is confined to which
+ * intermediate models get polished, not to the definition of any step.
+ * T = final model; Trefit (nullable) = Kabsch over its inliers at thr; mask (nullable) = those inliers. */
+LRO_API void lro_ransac_gc(const float *src, const float *tgt, int64_t n, int m, int sampler, int use_elc,
+                           double elc_ratio, double thr, double conf, int64_t max_iters, int64_t round,
+                           uint64_t seed, int lo_rounds, int lo_trials, int lsq_iters, double T[12],
+                           double *Trefit, uint8_t *mask, LroGcStats *st)
+{
+    int64_t best_id = -1, best_q = 0, best_inl = 0, passed = 0, done = 0;
+    double cur[12];
+    uint32_t *growth = NULL;
+    if (sampler == 1 && n >= m) {
+        growth = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+        lro_prosac_growth(n, m, growth);
+    }
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) cur[4 * r + c] = (r == c) ? 1.0 : 0.0;
+    if (n >= m && round > 0) {
+        while (done < max_iters) {
+            int64_t lo = done, hi = done + round < max_iters ? done + round : max_iters;
+            int64_t r_id = -1, r_q = 0, r_inl = 0, r_pass = 0;
+#pragma omp parallel
+            {
+                int64_t t_id = -1, t_q = 0, t_inl = 0, t_pass = 0;
+#pragma omp for schedule(dynamic, 256) nowait
+                for (int64_t id = lo; id < hi; ++id) {
+                    int32_t s[4];
+                    double Th[12];
+                    int64_t inl = 0;
+                    lro_sample(seed, (uint64_t)id, sampler, m, n, growth, s);
+                    if (!lro_model_from_sample(src, tgt, s, m, use_elc, elc_ratio, Th)) continue;
+                    ++t_pass;
+                    int64_t q = lro_msac_q(src, tgt, n, Th, thr, &inl);
+                    if (q > t_q || (q == t_q && q > 0 && id < t_id)) { t_q = q; t_id = id; t_inl = inl; }
+                }
+#pragma omp critical
+                {
+                    r_pass += t_pass;
+                    if (t_id >= 0 && (t_q > r_q || (t_q == r_q && t_id < r_id))) { r_q = t_q; r_id = t_id; r_inl = t_inl; }
+                }
+            }
+            passed += r_pass;
+            if (r_id >= 0 && r_q > best_q) { best_q = r_q; best_id = r_id; best_inl = r_inl; }
+            done = hi;
+            if (best_id >= 0 && done >= lro_conf_iters(best_inl, n, m, conf, max_iters)) break;
+        }
+    }
+    int64_t cur_q = 0;
+    if (best_id >= 0) {
+        int32_t s[4];
+        lro_sample(seed, (uint64_t)best_id, sampler, m, n, growth, s);
+        lro_model_from_sample(src, tgt, s, m, 0, elc_ratio, cur);
+        cur_q = best_q;
+    }
+    const double thr2 = thr * thr;
+    int32_t lo_improved = 0, lsq_improved = 0;
+    int32_t *L = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    const uint64_t lo_seed = lro_mix64(seed ^ LRO_LO_SEED_SALT);
+    if (lo_trials > 64) lo_trials = 64; /* the CUDA side scores one round's trials in one launch */
+    for (int rd = 0; best_id >= 0 && rd < lo_rounds; ++rd) {
+        int64_t I = 0;
+        for (int64_t i = 0; i < n; ++i)
+            if (lro_res2(cur, src + 3 * i, tgt + 3 * i) < thr2) L[I++] = (int32_t)i;
+        if (I <= m) break;
+        const int s_n = (int)(I < LRO_LO_SAMPLE_FACTOR * m ? I : LRO_LO_SAMPLE_FACTOR * m);
+        int t_best = -1;
+        int64_t q_best = 0;
+        double T_best[12];
+        for (int t = 0; t < lo_trials; ++t) {
+            int32_t pos[32];
+            double P[96], Q[96], Tt[12];
+            lro_unique_k(lo_seed, (uint64_t)rd * (uint64_t)lo_trials + (uint64_t)t, s_n, I, pos);
+            for (int d = 0; d < s_n; ++d)
+                for (int c = 0; c < 3; ++c) {
+                    P[3 * d + c] = (double)src[3 * (int64_t)L[pos[d]] + c];
+                    Q[3 * d + c] = (double)tgt[3 * (int64_t)L[pos[d]] + c];
+                }
+            lro_kabsch(P, Q, s_n, Tt);
+            int64_t q = lro_msac_q(src, tgt, n, Tt, thr, NULL);
+            if (q > q_best) { q_best = q; t_best = t; memcpy(T_best, Tt, sizeof(Tt)); }
+        }
+        if (t_best >= 0 && q_best > cur_q) { cur_q = q_best; memcpy(cur, T_best, sizeof(cur)); ++lo_improved; }
+        else break;
+    }
+    const int64_t lo_q = cur_q;
+    for (int it = 0; best_id >= 0 && it < lsq_iters; ++it) {
+        double Tn[12];
+        int64_t k = 0;
+        {
+            double *P = (double *)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+            double *Q = (double *)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
+            for (int64_t i = 0; i < n; ++i)
+                if (lro_res2(cur, src + 3 * i, tgt + 3 * i) < thr2) {
+                    for (int c = 0; c < 3; ++c) { P[3 * k + c] = src[3 * i + c]; Q[3 * k + c] = tgt[3 * i + c]; }
+                    ++k;
+                }
+            if (k >= m) lro_kabsch(P, Q, k, Tn);
+            free(P); free(Q);
+        }
+        if (k < m) break;
+        int64_t q = lro_msac_q(src, tgt, n, Tn, thr, NULL);
+        if (q > cur_q) { cur_q = q; memcpy(cur, Tn, sizeof(cur)); ++lsq_improved; }
+        else break;
+    }
+    free(L);
+    memcpy(T, cur, sizeof(cur));
+    int64_t refit_cnt = 0;
+    if (Trefit || mask) {
+        uint8_t *mk = mask ? mask : (uint8_t *)malloc((size_t)(n > 0 ? n : 1));
+        refit_cnt = lro_count_inliers(src, tgt, n, cur, thr, mk);
+        if (Trefit) {
+            double *P = (double *)malloc(sizeof(double) * 3 * (size_t)(refit_cnt > 0 ? refit_cnt : 1));
+            double *Q = (double *)malloc(sizeof(double) * 3 * (size_t)(refit_cnt > 0 ? refit_cnt : 1));
+            int64_t k = 0;
+            for (int64_t i = 0; i < n; ++i)
+                if (mk[i]) {
+                    for (int c = 0; c < 3; ++c) { P[3 * k + c] = src[3 * i + c]; Q[3 * k + c] = tgt[3 * i + c]; }
+                    ++k;
+                }
+            lro_kabsch(P, Q, k, Trefit);
+            free(P); free(Q);
+        }
+        if (!mask) free(mk);
+    }
+    free(growth);
+    if (st) {
+        st->iters_run = done; st->n_passed = passed; st->best_id = best_id; st->best_score = best_q;
+        st->best_inliers = best_inl; st->lo_score = lo_q; st->final_score = cur_q; st->refit_count = refit_cnt;
+        st->lo_improved = lo_improved; st->lsq_improved = lsq_improved;
+    }
+}
+
 /* Refit over an arbitrary correspondence set given as index pairs into two
  * clouds (FR.py:99-111: inliers of the ORIGINAL NN set under T, then Kabsch). */
 LRO_API int64_t lro_refit_indexed(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1,

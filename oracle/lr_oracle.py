@@ -27,6 +27,13 @@ class LroStats(ctypes.Structure):
                 ("best_count", ctypes.c_int64), ("refit_count", ctypes.c_int64)]
 
 
+class LroGcStats(ctypes.Structure):
+    _fields_ = [("iters_run", ctypes.c_int64), ("n_passed", ctypes.c_int64), ("best_id", ctypes.c_int64),
+                ("best_score", ctypes.c_int64), ("best_inliers", ctypes.c_int64), ("lo_score", ctypes.c_int64),
+                ("final_score", ctypes.c_int64), ("refit_count", ctypes.c_int64), ("lo_improved", ctypes.c_int32),
+                ("lsq_improved", ctypes.c_int32)]
+
+
 def build(force=False):
     """Compile the oracle with the committed Makefile (gcc only)."""
     src = os.path.join(_HERE, "lr_oracle.c")
@@ -46,6 +53,8 @@ def lib():
         _lib.lro_conf_iters.restype = ctypes.c_int64
         _lib.lro_refit_indexed.restype = ctypes.c_int64
         _lib.lro_msac.restype = ctypes.c_double
+        _lib.lro_msac_q.restype = ctypes.c_int64
+        _lib.lro_score_samples_msac.restype = ctypes.c_int64
         _lib.lro_elc.restype = ctypes.c_int
         _lib.lro_num_threads.restype = ctypes.c_int
     return _lib
@@ -204,6 +213,50 @@ def ransac(src, tgt, m=3, sampler=0, use_elc=True, elc_ratio=0.9, thr=0.6, conf=
     return dict(T=_T44(T), T_refit=_T44(Tr) if refit else None, mask=mask.astype(bool) if return_mask else None,
                 iters_run=st.iters_run, n_passed=st.n_passed, best_id=st.best_id, best_count=st.best_count,
                 refit_count=st.refit_count)
+
+
+def msac_q(src, tgt, T, thr):
+    """Quantised MSAC score (integer sum of trunc((1 - r^2/tau^2) * 65536), tau = 1.5 thr) -> (q, #r^2<tau^2)"""
+    src, tgt = _f32(src), _f32(tgt)
+    T12 = np.ascontiguousarray(np.asarray(T, dtype=np.float64)[:3, :].reshape(-1))
+    cnt = ctypes.c_int64(0)
+    q = lib().lro_msac_q(_p(src, c_f32p), _p(tgt, c_f32p), ctypes.c_int64(src.shape[0]), _p(T12, c_f64p),
+                         ctypes.c_double(thr), ctypes.byref(cnt))
+    return int(q), int(cnt.value)
+
+
+def score_samples_msac(src, tgt, samples, thr, use_elc=True, elc_ratio=0.9):
+    """Fed-sample hook, MSAC flavour -> (scores[H] int64 (-1 = ELC reject), inliers[H] int32, selected h)"""
+    src, tgt = _f32(src), _f32(tgt)
+    samples = np.ascontiguousarray(samples, dtype=np.int32)
+    H, m = samples.shape
+    scores = np.empty(H, np.int64)
+    inl = np.empty(H, np.int32)
+    best = lib().lro_score_samples_msac(_p(src, c_f32p), _p(tgt, c_f32p), ctypes.c_int64(src.shape[0]),
+                                        _p(samples, c_i32p), ctypes.c_int64(H), m, ctypes.c_double(thr),
+                                        int(use_elc), ctypes.c_double(elc_ratio), _p(scores, c_i64p),
+                                        _p(inl, c_i32p))
+    return scores, inl, int(best)
+
+
+def ransac_gc(src, tgt, m=3, sampler=0, use_elc=True, elc_ratio=0.9, thr=0.6, conf=1.0, max_iters=100000,
+              round_size=65536, seed=51, lo_rounds=10, lo_trials=20, lsq_iters=10, refit=True, return_mask=False):
+    """GC-RANSAC semantics: MSAC selection, local optimisation, iterated least squares."""
+    src, tgt = _f32(src), _f32(tgt)
+    n = src.shape[0]
+    T = np.empty(12, np.float64)
+    Tr = np.empty(12, np.float64) if refit else None
+    mask = np.empty(n, np.uint8) if return_mask else None
+    st = LroGcStats()
+    lib().lro_ransac_gc(_p(src, c_f32p), _p(tgt, c_f32p), ctypes.c_int64(n), int(m), int(sampler), int(use_elc),
+                        ctypes.c_double(elc_ratio), ctypes.c_double(thr), ctypes.c_double(conf),
+                        ctypes.c_int64(max_iters), ctypes.c_int64(round_size), ctypes.c_uint64(seed),
+                        int(lo_rounds), int(lo_trials), int(lsq_iters), _p(T, c_f64p),
+                        _p(Tr, c_f64p) if refit else None, _p(mask, c_u8p) if return_mask else None,
+                        ctypes.byref(st))
+    out = dict(T=_T44(T), T_refit=_T44(Tr) if refit else None, mask=mask.astype(bool) if return_mask else None)
+    out.update({k: int(getattr(st, k)) for k, _ in st._fields_})
+    return out
 
 
 def refit_indexed(xyz0, xyz1, i0, i1, T, thr):

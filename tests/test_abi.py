@@ -28,8 +28,8 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     import ctypes
-    assert ctypes.sizeof(_lib.LrRansacParams) == 3 * 8 + 2 * 8 + 6 * 4
-    assert ctypes.sizeof(_lib.LrRansacStats) == 6 * 8
+    assert ctypes.sizeof(_lib.LrRansacParams) == 3 * 8 + 2 * 8 + 10 * 4
+    assert ctypes.sizeof(_lib.LrRansacStats) == 9 * 8 + 2 * 4
 
 
 def test_host_only_entry_points():
