@@ -310,6 +310,7 @@ def run_ours(args):
             line["mnn_match"] = bench_matching(engine, torch, dev)
             other = bench_other_regime(engine, torch, resident, not use_elc)
             line["other_regime"] = other
+            line["gc_semantics"] = bench_gc_semantics(engine, torch, resident, pairs[0], use_elc)
             try:
                 from oracle import lr_oracle as _O
                 _O.set_threads(len(os.sched_getaffinity(0)))
@@ -363,6 +364,46 @@ def bench_other_regime(engine, torch, resident, use_elc):
     flops = res["n_scored"] * reps * N_CORR * FLOPS_PER_TEST
     return {"elc": use_elc, "pairs_per_s": 1e3 / ms, "ms_per_pair": ms, "h_scored_per_pair": res["n_scored"],
             "k_score_tflops": flops / (sms * 1e-3) / 1e12 if sms > 0 else None, "k_score_ms_per_pair": sms / reps}
+
+
+def bench_gc_semantics(engine, torch, resident, pair0, use_elc):
+    """the same cfg-3 pair under pygcransac's own criterion -- quantised MSAC selection in fp64
+    (k_score_msac), 10 x 20 local-optimisation draws, 10 passes of iterated least squares -- with the oracle's
+    lro_ransac_gc timed beside it on one pass."""
+    params = engine.make_params(threshold=THRESH, confidence=1.0, max_iters=ITERS, seed=51, use_elc=use_elc,
+                                scoring=engine.SCORE_MSAC, lo_rounds=10, lo_trials=20, lsq_iters=10)
+    a, b = resident[0]
+    for _ in range(2):
+        engine.ransac_rigid(a, b, params)
+    engine.prof_read(engine.PROF_SCORE)
+    engine.prof_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        res = engine.ransac_rigid(a, b, params)
+    e1.record()
+    torch.cuda.synchronize()
+    engine.prof_enable(False)
+    ms = e0.elapsed_time(e1) / reps
+    sms, _ = engine.prof_read(engine.PROF_SCORE)
+    out = {"scoring": "MSAC at 1.5 x threshold, integer-quantised (include/lidarreg.h LR_SCORE_MSAC)",
+           "pairs_per_s": 1e3 / ms, "ms_per_pair": ms, "k_score_msac_ms_per_pair": sms / reps,
+           "h_scored_per_pair": res["n_scored"],
+           "stats": {k: res[k] for k in ("best_id", "best_count", "best_score", "lo_score", "final_score",
+                                         "lo_improved", "lsq_improved")}}
+    try:
+        from oracle import lr_oracle as O
+        t0 = time.perf_counter()
+        o = O.ransac_gc(pair0["src"], pair0["tgt"], thr=THRESH, conf=1.0, max_iters=ITERS, seed=51, use_elc=use_elc)
+        out["cpu_baseline"] = {"ms_per_pair": (time.perf_counter() - t0) * 1e3, "cores": O.num_threads(),
+                               "kind": "port", "same_selection": bool(o["best_id"] == res["best_id"] and
+                                                                      o["best_score"] == res["best_score"] and
+                                                                      o["lo_score"] == res["lo_score"])}
+    except Exception as e:  # the checker is optional here, the measurement is not
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
 
 
 def bench_matching(engine, torch, dev):

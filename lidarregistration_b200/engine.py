@@ -112,6 +112,16 @@ def make_params(threshold=0.6, confidence=1.0, max_iters=500000, seed=51, sample
     return p
 
 
+_PINNED_MASK = None  # grow-only pinned staging for mask_on_host (cudaHostAlloc per call costs ~0.1 ms)
+
+
+def _pinned_mask(n):
+    global _PINNED_MASK
+    if _PINNED_MASK is None or _PINNED_MASK.numel() < n:
+        _PINNED_MASK = torch.empty(max(n, 1 << 16), dtype=torch.uint8, pin_memory=True)
+    return _PINNED_MASK[:n]
+
+
 def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
     """lr_ransac_rigid -> dict(T, T_refit, mask | None, + LrRansacStats fields).
 
@@ -125,8 +135,7 @@ def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
     st = LrRansacStats()
     mask = None
     if want_mask:
-        mask = (torch.empty(n, dtype=torch.uint8, pin_memory=True) if mask_on_host
-                else torch.empty(n, dtype=torch.uint8, device=src.device))
+        mask = _pinned_mask(n) if mask_on_host else torch.empty(n, dtype=torch.uint8, device=src.device)
     mask_ptr = None if mask is None else ctypes.c_void_p(mask.data_ptr())
     rc = _lib.lib().lr_ransac_rigid(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), ctypes.byref(params), T, Tr,
                                     mask_ptr, ctypes.byref(st), _lib.stream_ptr())

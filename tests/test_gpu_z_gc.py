@@ -150,8 +150,8 @@ def test_gc_batch_entry_equals_single_calls():
 
 def test_reference_interface_with_msac_scoring():
     """findRigidTransform / FR with GC_scoring = MSAC: pygcransac's return convention, GC_LO switch, accuracy."""
-    G = sys.modules["lidarregistration_b200.algorithms.GC_RANSAC"]
     from lidarregistration_b200.algorithms import FR
+    G = sys.modules["lidarregistration_b200.algorithms.GC_RANSAC"]  # the package re-exports the function under this name
     d = synthetic.make_correspondences(6000, inlier_ratio=0.3, seed=41)
     common = dict(threshold=THR, conf=1.0, spatial_coherence_weight=0.0, max_iters=30000, use_sprt=True,
                   min_inlier_ratio_for_sprt=-1, sampler=0, neighborhood_size=20, seed=7)
