@@ -147,6 +147,10 @@ int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, v
 int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
                     double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
 
+/* Implementation switch of the inlier sweep (identical results): 0 = with the warp-uniform early-out on the first
+ * residual component [default], 1 = every residual evaluated in full (A/B measurements). */
+int lr_ransac_set_mode(int mode);
+
 /* The same for `count` independent pairs (the reference's per-pair loop over a registration set,
  * Experiments/test.py:108-167, sharded by rank as in data_loaders.py:111-116): src[i] / tgt[i] are device
  * pointers to [n[i],3] fp32 correspondences.  Two pairs are in flight at a time on two internal streams with

@@ -298,6 +298,11 @@ def match_set_mode(mode):
     _lib.check(_lib.lib().lr_match_set_mode(int(mode)), "lr_match_set_mode")
 
 
+def ransac_set_mode(mode):
+    """0 = inlier sweep with the first-component early-out (default); 1 = every residual in full (A/B)."""
+    _lib.check(_lib.lib().lr_ransac_set_mode(int(mode)), "lr_ransac_set_mode")
+
+
 # --------------------------------------------------------------------- ICP
 def transform_pad8(xyz, T):
     """lr_transform_pad8 -> [n, 8] fp32 rows (T * xyz, zero padded) for a 3-D lr_match_nn(D = 8)"""
