@@ -70,6 +70,7 @@ struct Ctl {
 struct Ws {
     Ctl *ctl;
     float4 *P12;      // 3 x float4 per point: (px,px,py,py) (pz,pz,-qx,-qx) (-qy,-qy,-qz,-qz)
+    float4 *P8;       // 2 x float4 per point: (px,py,pz,qx) (qy,qz,0,0) -- one 32-byte sector per sampled correspondence
     int32_t *samp;    // sample indices of the survivors, 4 per slot
     uint32_t *slot_id;
     float4 *m32;      // fp32 [R|t], lo, hi of two slots interleaved: see m32_index()
@@ -363,7 +364,7 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // far-away points that can never be inliers.  Also the coordinate bound that
 // enters the fp32 error band.
 __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, int64_t n_pad,
-                       float4 *__restrict__ P12, Ctl *ctl)
+                       float4 *__restrict__ P12, float4 *__restrict__ P8, Ctl *ctl)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     float p1 = 0.f;
@@ -373,6 +374,8 @@ __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ 
         P12[3 * i + 0] = make_float4(px, px, py, py);
         P12[3 * i + 1] = make_float4(pz, pz, -qx, -qx);
         P12[3 * i + 2] = make_float4(-qy, -qy, -qz, -qz);
+        P8[2 * i + 0] = make_float4(px, py, pz, qx);
+        P8[2 * i + 1] = make_float4(qy, qz, 0.f, 0.f);
         p1 = fabsf(px) + fabsf(py) + fabsf(pz);
     } else if (i < n_pad) {
         P12[3 * i + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -445,11 +448,19 @@ __device__ __forceinline__ bool elc_pass_fast(const double (&P)[M][3], const dou
     return ok;
 }
 
+// one sampled correspondence = one 32-byte sector of the packed copy (the [n,3] arrays cost 2-4 sectors)
+__device__ __forceinline__ void load_pq(const float4 *__restrict__ P8, int64_t k, double (&P)[3], double (&Q)[3])
+{
+    const float4 a = __ldg(P8 + 2 * k), b = __ldg(P8 + 2 * k + 1);
+    P[0] = (double)a.x, P[1] = (double)a.y, P[2] = (double)a.z;
+    Q[0] = (double)a.w, Q[1] = (double)b.x, Q[2] = (double)b.y;
+}
+
 // one thread per hypothesis id: counter-based sample -> ELC; survivors are
 // compacted (warp-aggregated) as (id, sample indices)
 template <int M>
 __global__ void __launch_bounds__(kGenThreads)
-k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, uint64_t seed, int sampler,
+k_gen(const float4 *__restrict__ P8, int64_t n, uint64_t seed, int sampler,
       int use_elc, double elc_ratio, int64_t id_lo, int64_t id_hi, const int32_t *__restrict__ fed,
       const uint32_t *__restrict__ growth, Ctl *ctl, uint32_t *__restrict__ slot_id, int32_t *__restrict__ samp)
 {
@@ -467,12 +478,7 @@ k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, u
         if (use_elc) {
             double P[M][3], Q[M][3];
 #pragma unroll
-            for (int d = 0; d < M; ++d)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    P[d][c] = (double)src[3 * (int64_t)s[d] + c];
-                    Q[d][c] = (double)tgt[3 * (int64_t)s[d] + c];
-                }
+            for (int d = 0; d < M; ++d) load_pq(P8, (int64_t)s[d], P[d], Q[d]);
             ok = elc_pass_fast<M>(P, Q, elc_ratio);
         }
     }
@@ -492,7 +498,7 @@ k_gen(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, u
 // rigorous fp32 error band of the inlier test (DESIGN.md "fp32 bracket")
 template <int M>
 __global__ void __launch_bounds__(kGenThreads)
-k_kabsch(const float *__restrict__ src, const float *__restrict__ tgt, double thr2, Ctl *ctl,
+k_kabsch(const float4 *__restrict__ P8, double thr2, Ctl *ctl,
          const int32_t *__restrict__ samp, float4 *__restrict__ m32, double *__restrict__ m64,
          int *__restrict__ cnt)
 {
@@ -501,14 +507,7 @@ k_kabsch(const float *__restrict__ src, const float *__restrict__ tgt, double th
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
         double P[M][3], Q[M][3], T[12];
 #pragma unroll
-        for (int d = 0; d < M; ++d) {
-            const int64_t k = samp[(size_t)slot * 4 + d];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                P[d][c] = (double)src[3 * k + c];
-                Q[d][c] = (double)tgt[3 * k + c];
-            }
-        }
+        for (int d = 0; d < M; ++d) load_pq(P8, (int64_t)samp[(size_t)slot * 4 + d], P[d], Q[d]);
         kabsch_small<M>(P, Q, T);
 #pragma unroll
         for (int k = 0; k < 12; ++k) m64[(size_t)slot * 12 + k] = T[k];
@@ -1059,6 +1058,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     // the sweep walks slots in blocks of kHypPerItem: size the per-slot arrays for the padded count
     const int64_t slots = round + kHypPerItem;
     size_t bytes = lr::padded(sizeof(Ctl)) + lr::padded(sizeof(float4) * 3 * ws.n_pad) +
+                   lr::padded(sizeof(float4) * 2 * ws.n_pad) +
                    lr::padded(sizeof(int32_t) * 4 * slots) + lr::padded(sizeof(uint32_t) * slots) +
                    lr::padded(sizeof(float4) * 4 * slots) + lr::padded(sizeof(double) * 12 * slots) +
                    lr::padded(sizeof(int) * slots) + lr::padded(sizeof(int) * (nrounds + 1)) +
@@ -1072,6 +1072,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     lr::Carver cv(base);
     ws.ctl = cv.take<Ctl>(1);
     ws.P12 = cv.take<float4>(3 * ws.n_pad);
+    ws.P8 = cv.take<float4>(2 * ws.n_pad);
     ws.samp = cv.take<int32_t>(4 * slots);
     ws.slot_id = cv.take<uint32_t>(slots);
     ws.m32 = cv.take<float4>(4 * slots);
@@ -1143,7 +1144,7 @@ int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cud
 {
     k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
     int blocks = (int)((ws.n_pad + 255) / 256);
-    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.ctl);
+    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.ctl);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1163,13 +1164,13 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     int kblocks = gblocks < sms * 8 ? gblocks : sms * 8;
     int tok = lr::prof_begin(lr::PROF_GEN, st);
     if (p.sample_size == 3) {
-        k_gen<3><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
+        k_gen<3><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
                                                   ws.growth, ws.ctl, ws.slot_id, ws.samp);
-        k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
+        k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
     } else {
-        k_gen<4><<<gblocks, kGenThreads, 0, st>>>(src, tgt, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
+        k_gen<4><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
                                                   ws.growth, ws.ctl, ws.slot_id, ws.samp);
-        k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(src, tgt, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
+        k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
     }
     lr::prof_end(tok, st);
     if (p.scoring == LR_SCORE_MSAC) return gc_launch_score(src, tgt, n, p, ws, lo, len, scores_out, counts_out, st);
