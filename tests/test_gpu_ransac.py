@@ -197,3 +197,26 @@ def test_find_rigid_transform_mask_in_pinned_host_memory():
     res = engine.ransac_rigid(d["src"], d["tgt"], params, want_mask=True)
     assert mask.dtype == bool and np.array_equal(mask, res["mask"].cpu().numpy())
     assert int(mask.sum()) == res["best_count"] and close_T(pose.T, res["T_refit"])
+
+
+def test_sweep_early_out_is_exact():
+    """lr_ransac_set_mode: the warp-uniform early-out on the first residual component changes no count --
+    fed samples (every count) and full runs, incl. coordinates that force the fp64 recount."""
+    d = synthetic.make_correspondences(9000, inlier_ratio=0.4, seed=17)
+    rng = np.random.default_rng(5)
+    samples = rng.integers(0, 9000, (30000, 3)).astype(np.int32)
+    big = {k: (v + np.float32(3000.0) if k in ("src", "tgt") else v) for k, v in d.items()}
+    out = {}
+    try:
+        for mode in (1, 0):
+            engine.ransac_set_mode(mode)
+            c, b, _ = engine.ransac_score_samples(d["src"], d["tgt"], samples, 0.6, False, 0.9)
+            cb, bb, _ = engine.ransac_score_samples(big["src"], big["tgt"], samples[:5000], 0.6, True, 0.9)
+            r = engine.ransac_rigid(d["src"], d["tgt"], engine.make_params(max_iters=50000, seed=2))
+            out[mode] = (c.cpu().numpy(), b, cb.cpu().numpy(), bb, r["best_id"], r["best_count"], r["n_scored"])
+    finally:
+        engine.ransac_set_mode(0)
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y)
+    oc, ob = O.score_samples(d["src"], d["tgt"], samples[:3000], 0.6, False, 0.9)
+    assert np.array_equal(out[0][0][:3000], oc)

@@ -38,4 +38,20 @@ s = rng.integers(0, 3000, (5000, 3)).astype(np.int32)
 c, b, _ = engine.ransac_score_samples(d["src"], d["tgt"], s)
 oc, ob = O.score_samples(d["src"], d["tgt"], s, 0.6)
 assert np.array_equal(c.cpu().numpy(), oc) and b == ob
+# GC semantics: MSAC selection, local optimisation, iterated least squares (single call, batch entry, fed hook)
+pg = engine.make_params(max_iters=20000, round_size=4096, confidence=0.999, scoring=engine.SCORE_MSAC, lo_rounds=3,
+                        lo_trials=8, lsq_iters=2)
+rg = engine.ransac_rigid(d["src"], d["tgt"], pg, want_mask=True)
+og = O.ransac_gc(d["src"], d["tgt"], conf=0.999, max_iters=20000, round_size=4096, lo_rounds=3, lo_trials=8, lsq_iters=2)
+assert (rg["best_id"], rg["best_score"], rg["lo_score"]) == (og["best_id"], og["best_score"], og["lo_score"])
+rgb = engine.ransac_rigid_batch(pairs, pg)
+assert all(x["best_id"] == rg["best_id"] and x["lo_score"] == rg["lo_score"] for x in rgb)
+sc, si, sb = engine.ransac_score_samples_msac(d["src"], d["tgt"], s)
+osc, osi, osb = O.score_samples_msac(d["src"], d["tgt"], s, 0.6)
+assert np.array_equal(sc.cpu().numpy(), osc) and np.array_equal(si.cpu().numpy(), osi) and sb == osb
+# the inlier sweep without the early-out gives the same result
+engine.ransac_set_mode(1)
+r1 = engine.ransac_rigid(*pairs[0], pb)
+engine.ransac_set_mode(0)
+assert r1["best_id"] == rs["best_id"] and r1["best_count"] == rs["best_count"]
 print("sanitize workload ok")
