@@ -136,7 +136,9 @@ int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, v
 /* Replaces pygcransac.findRigidTransform (GC_RANSAC.py:46-49,
  * gcransac_python.cpp:404-624) and Open3D's
  * registration_ransac_based_on_correspondence (FR.py:128-137): src[n,3],
- * tgt[n,3] fp32 correspondences.  T_out[16] [host] = selected model (identity
+ * tgt[n,3] fp32 correspondences -- device memory, or pinned host memory under
+ * unified addressing: both arrays are read once by the pack kernel (plus the
+ * three rows of the selected sample), every sweep works on packed device copies.  T_out[16] [host] = selected model (identity
  * if none); T_refit[16] [host, nullable] = Kabsch over its inliers
  * (FR.py:99-111); mask[n] (device, nullable) = inlier mask of the selected
  * model; stats [host, nullable].  Synchronises `stream` before returning.

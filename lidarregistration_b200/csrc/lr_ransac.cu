@@ -894,6 +894,10 @@ __device__ __forceinline__ double block_sum(double v, double *sh)
 __device__ __forceinline__ void fetch_pair(const float *a, const float *b, const int64_t *ia, const int64_t *ib,
                                            int64_t i, double (&p)[3], double (&q)[3])
 {
+    if (a == nullptr) {  // packed records of the run (Ws::P8) passed through `b`: same floats, one sector per pair
+        load_pq(reinterpret_cast<const float4 *>(b), i, p, q);
+        return;
+    }
     const int64_t ka = ia ? ia[i] : i, kb = ib ? ib[i] : i;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -1203,8 +1207,11 @@ void identity16(double *T)
 
 // model from key + mask + refit (launches only)
 int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
-                  uint64_t key, bool want_refit, uint8_t *mask, bool want_stats, cudaStream_t st)
+                  uint64_t key, bool want_refit, uint8_t *mask, bool want_stats, cudaStream_t st, bool packed = true)
 {
+    // after launch_pack the run's kernels read the packed device copy; src / tgt themselves (device or pinned
+    // host memory) are then only touched by k_pack and by the three-point k_model_from_key
+    const float *fa = packed ? nullptr : src, *fb = packed ? reinterpret_cast<const float *>(ws.P8) : tgt;
     const double thr2 = p.threshold * p.threshold;
     if (p.scoring == LR_SCORE_MSAC)
         k_gc_commit<<<1, 32, 0, st>>>(ws.ctl);  // the model was kept in ctl->gc, there is no key to decode
@@ -1216,9 +1223,9 @@ int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacP
         int blocks = (int)((n + 255) / 256);
         if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
         if (blocks < 1) blocks = 1;
-        k_mask_sums<<<blocks, 256, 0, st>>>(src, tgt, nullptr, nullptr, n, thr2, ws.ctl, mask);
+        k_mask_sums<<<blocks, 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl, mask);
         if (want_refit) {
-            k_refit_H<<<blocks, 256, 0, st>>>(src, tgt, nullptr, nullptr, n, thr2, ws.ctl);
+            k_refit_H<<<blocks, 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl);
             k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
         }
     }
@@ -1263,10 +1270,11 @@ void finish_read(const Ctl &h, bool want_refit, double *T_out, double *T_refit, 
 
 // model from key + mask + refit + D2H
 int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
-           uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st)
+           uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st,
+           bool packed = true)
 {
     const bool want_refit = (T_refit != nullptr) && p.refit;
-    int rc = finish_launch(src, tgt, n, p, ws, use_ctl_key, key, want_refit, mask, stats != nullptr, st);
+    int rc = finish_launch(src, tgt, n, p, ws, use_ctl_key, key, want_refit, mask, stats != nullptr, st, packed);
     if (rc) return rc;
     Ctl h;
     LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
@@ -1605,7 +1613,7 @@ LR_EXPORT int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, 
     rc = upload_growth(ws, n, params->sample_size, st);
     if (rc) return rc;
     k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
-    return finish(src, tgt, n, *params, ws, 0, key, T_out, T_refit, mask, stats, st);
+    return finish(src, tgt, n, *params, ws, 0, key, T_out, T_refit, mask, stats, st, /*packed=*/false);
 }
 
 LR_EXPORT int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t id_lo, int64_t H, int32_t *samples,

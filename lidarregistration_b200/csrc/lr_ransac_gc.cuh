@@ -37,7 +37,7 @@ __device__ __forceinline__ long long msac_term(double r2, double tau2)
 // 256-correspondence chunks (chosen from the survivor count so that every CTA gets work); points are converted
 // to fp64 once per stage and read as shared-memory broadcasts.
 __global__ void __launch_bounds__(kMsacThreads)
-k_score_msac(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, Ctl *ctl,
+k_score_msac(const float4 *__restrict__ P8, int64_t n, Ctl *ctl,
              const double *__restrict__ m64, unsigned long long *__restrict__ q64, int *__restrict__ cnt, double tau2)
 {
     if (ctl->done) return;
@@ -65,16 +65,36 @@ k_score_msac(const float *__restrict__ src, const float *__restrict__ tgt, int64
             __syncthreads();
             const int64_t base = (int64_t)ch * kMsacChunk;
             const int len = (int)(n - base < kMsacChunk ? n - base : kMsacChunk);
-            for (int e = threadIdx.x; e < 3 * len; e += kMsacThreads) {
-                sP[e / 3][e % 3] = (double)src[3 * base + e];
-                sP[e / 3][3 + e % 3] = (double)tgt[3 * base + e];
+            for (int e = threadIdx.x; e < len; e += kMsacThreads) {
+                double pp[3], qq[3];
+                load_pq(P8, base + e, pp, qq);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    sP[e][k] = pp[k];
+                    sP[e][3 + k] = qq[k];
+                }
             }
             __syncthreads();
-            if (valid) {
-#pragma unroll 4
-                for (int j = 0; j < len; ++j) {
-                    const double r2 = res2_f64(T, sP[j][0], sP[j][1], sP[j][2], sP[j][3], sP[j][4], sP[j][5]);
-                    if (r2 < tau2) {
+            // first residual component of four points at a time; d0^2 >= tau^2 for the whole warp => the point
+            // scores nothing for any of its 32 hypotheses (r^2 >= d0^2, rounding is monotone) and the other two
+            // components are skipped (warp-uniform branch, as in k_score)
+            for (int j0 = 0; j0 < len; j0 += 4) {
+                double d0[4];
+                bool live[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u < len ? j0 + u : len - 1;
+                    d0[u] = (((T[0] * sP[j][0] + T[1] * sP[j][1]) + T[2] * sP[j][2]) + T[3]) - sP[j][3];
+                    live[u] = __any_sync(0xffffffffu, valid && j0 + u < len && d0[u] * d0[u] < tau2);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!live[u]) continue;
+                    const int j = j0 + u;
+                    const double d1 = (((T[4] * sP[j][0] + T[5] * sP[j][1]) + T[6] * sP[j][2]) + T[7]) - sP[j][4];
+                    const double d2 = (((T[8] * sP[j][0] + T[9] * sP[j][1]) + T[10] * sP[j][2]) + T[11]) - sP[j][5];
+                    const double r2 = (d0[u] * d0[u] + d1 * d1) + d2 * d2;  // == res2_f64
+                    if (valid && r2 < tau2) {
                         q += msac_term(r2, tau2);
                         ++c;
                     }
@@ -184,8 +204,7 @@ __global__ void k_lo_begin(Ctl *ctl, int lo_rounds)
 
 // L = { i : |cur p_i - q_i|^2 < thr^2 } in ascending order (graph-cut labelling with weight 0); one block
 __global__ void __launch_bounds__(1024)
-k_lo_label(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, double thr2, int m, Ctl *ctl,
-           int32_t *__restrict__ L)
+k_lo_label(const float4 *__restrict__ P8, int64_t n, double thr2, int m, Ctl *ctl, int32_t *__restrict__ L)
 {
     if (!ctl->gc.lo_active) return;
     __shared__ int s_wsum[32];
@@ -199,9 +218,11 @@ k_lo_label(const float *__restrict__ src, const float *__restrict__ tgt, int64_t
     for (int64_t tile = 0; tile < n; tile += blockDim.x) {
         const int64_t i = tile + threadIdx.x;
         bool in = false;
-        if (i < n)
-            in = res2_f64(T, (double)src[3 * i], (double)src[3 * i + 1], (double)src[3 * i + 2], (double)tgt[3 * i],
-                          (double)tgt[3 * i + 1], (double)tgt[3 * i + 2]) < thr2;
+        if (i < n) {
+            double pp[3], qq[3];
+            load_pq(P8, i, pp, qq);
+            in = res2_f64(T, pp[0], pp[1], pp[2], qq[0], qq[1], qq[2]) < thr2;
+        }
         const unsigned b = __ballot_sync(0xffffffffu, in);
         if (lane == 0) s_wsum[w] = __popc(b);
         __syncthreads();
@@ -278,7 +299,7 @@ __device__ void kabsch_rt(const double (*P)[3], const double (*Q)[3], int k, dou
 
 // one thread per inner draw of the round: sample of L -> non-minimal Kabsch
 __global__ void __launch_bounds__(kGcMaxTrials)
-k_lo_gen(const float *__restrict__ src, const float *__restrict__ tgt, uint64_t lo_seed, int round, int trials,
+k_lo_gen(const float4 *__restrict__ P8, uint64_t lo_seed, int round, int trials,
          Ctl *ctl, const int32_t *__restrict__ L, double *__restrict__ tr_T, unsigned long long *__restrict__ tr_q,
          int *__restrict__ tr_inl)
 {
@@ -289,14 +310,7 @@ k_lo_gen(const float *__restrict__ src, const float *__restrict__ tgt, uint64_t 
     int32_t pos[kLoMaxSample];
     double P[kLoMaxSample][3], Q[kLoMaxSample][3], T[12];
     unique_ids_rt(lo_seed, (uint64_t)round * (uint64_t)trials + (uint64_t)t, s, I, pos);
-    for (int d = 0; d < s; ++d) {
-        const int64_t i = L[pos[d]];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            P[d][c] = (double)src[3 * i + c];
-            Q[d][c] = (double)tgt[3 * i + c];
-        }
-    }
+    for (int d = 0; d < s; ++d) load_pq(P8, (int64_t)L[pos[d]], P[d], Q[d]);
     kabsch_rt(P, Q, s, T);
 #pragma unroll
     for (int k = 0; k < 12; ++k) tr_T[t * 12 + k] = T[k];
@@ -307,7 +321,7 @@ k_lo_gen(const float *__restrict__ src, const float *__restrict__ tgt, uint64_t 
 // q and #(r^2 < tau^2) of `trials` candidate models over all correspondences: thread = correspondence, the
 // models sit in shared memory, integer warp / block reductions
 __global__ void __launch_bounds__(256)
-k_trial_score(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, double tau2, int trials,
+k_trial_score(const float4 *__restrict__ P8, int64_t n, double tau2, int trials,
               const int *__restrict__ active, const double *__restrict__ tr_T, unsigned long long *__restrict__ tr_q,
               int *__restrict__ tr_inl)
 {
@@ -325,8 +339,10 @@ k_trial_score(const float *__restrict__ src, const float *__restrict__ tgt, int6
     const bool have = i < n;
     double px = 0, py = 0, pz = 0, qx = 0, qy = 0, qz = 0;
     if (have) {
-        px = (double)src[3 * i], py = (double)src[3 * i + 1], pz = (double)src[3 * i + 2];
-        qx = (double)tgt[3 * i], qy = (double)tgt[3 * i + 1], qz = (double)tgt[3 * i + 2];
+        double pp[3], qq[3];
+        load_pq(P8, i, pp, qq);
+        px = pp[0], py = pp[1], pz = pp[2];
+        qx = qq[0], qy = qq[1], qz = qq[2];
     }
     const int lane = threadIdx.x & 31;
     for (int t = 0; t < trials; ++t) {
@@ -451,7 +467,7 @@ int gc_launch_score(const float *src, const float *tgt, int64_t n, const LrRansa
     // split items add into q64 (k_kabsch already cleared cnt)
     LR_CUDA_TRY(cudaMemsetAsync(ws.q64, 0, sizeof(unsigned long long) * (size_t)(len < slots ? len : slots), st));
     int tok = lr::prof_begin(lr::PROF_SCORE, st);
-    k_score_msac<<<sms * 4, kMsacThreads, 0, st>>>(src, tgt, n, ws.ctl, ws.m64, ws.q64, ws.cnt, gc_tau2(p.threshold));
+    k_score_msac<<<sms * 4, kMsacThreads, 0, st>>>(ws.P8, n, ws.ctl, ws.m64, ws.q64, ws.cnt, gc_tau2(p.threshold));
     lr::prof_end(tok, st);
     int rblocks = (int)((len + 255) / 256);
     if (rblocks > sms * 4) rblocks = sms * 4;
@@ -469,27 +485,26 @@ int gc_enqueue_polish(const float *src, const float *tgt, int64_t n, const LrRan
     const int trials = p.lo_trials < 1 ? 1 : (p.lo_trials > kGcMaxTrials ? kGcMaxTrials : p.lo_trials);
     const int lo_rounds = p.lo_rounds < 0 ? 0 : p.lo_rounds, lsq_iters = p.lsq_iters < 0 ? 0 : p.lsq_iters;
     const uint64_t lo_seed = mix64(p.seed ^ kLoSeedSalt);
+    const float *P8f = reinterpret_cast<const float *>(ws.P8);  // fetch_pair's packed-record convention
     const int sblocks = (int)((n + 255) / 256) > 0 ? (int)((n + 255) / 256) : 1;
     int rblocks = sblocks;
     if (rblocks > lr::sm_count() * 8) rblocks = lr::sm_count() * 8;
     k_lo_begin<<<1, 32, 0, st>>>(ws.ctl, lo_rounds);
     for (int rd = 0; rd < lo_rounds; ++rd) {
-        k_lo_label<<<1, 1024, 0, st>>>(src, tgt, n, thr2, p.sample_size, ws.ctl, ws.lo_L);
-        k_lo_gen<<<1, kGcMaxTrials, 0, st>>>(src, tgt, lo_seed, rd, trials, ws.ctl, ws.lo_L, ws.tr_T, ws.tr_q,
-                                            ws.tr_inl);
-        k_trial_score<<<sblocks, 256, 0, st>>>(src, tgt, n, tau2, trials, &ws.ctl->gc.lo_active, ws.tr_T, ws.tr_q,
+        k_lo_label<<<1, 1024, 0, st>>>(ws.P8, n, thr2, p.sample_size, ws.ctl, ws.lo_L);
+        k_lo_gen<<<1, kGcMaxTrials, 0, st>>>(ws.P8, lo_seed, rd, trials, ws.ctl, ws.lo_L, ws.tr_T, ws.tr_q, ws.tr_inl);
+        k_trial_score<<<sblocks, 256, 0, st>>>(ws.P8, n, tau2, trials, &ws.ctl->gc.lo_active, ws.tr_T, ws.tr_q,
                                                ws.tr_inl);
         k_lo_select<<<1, 32, 0, st>>>(ws.ctl, trials, ws.tr_T, ws.tr_q);
     }
     for (int it = 0; it <= lsq_iters; ++it) {
         k_lsq_step<<<1, 32, 0, st>>>(ws.ctl, it == 0, lsq_iters, ws.tr_T, ws.tr_q);
         if (it == lsq_iters) break;
-        k_mask_sums<<<rblocks, 256, 0, st>>>(src, tgt, nullptr, nullptr, n, thr2, ws.ctl, nullptr);
-        k_refit_H<<<rblocks, 256, 0, st>>>(src, tgt, nullptr, nullptr, n, thr2, ws.ctl);
+        k_mask_sums<<<rblocks, 256, 0, st>>>(nullptr, P8f, nullptr, nullptr, n, thr2, ws.ctl, nullptr);
+        k_refit_H<<<rblocks, 256, 0, st>>>(nullptr, P8f, nullptr, nullptr, n, thr2, ws.ctl);
         k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
         k_lsq_stage<<<1, 32, 0, st>>>(ws.ctl, p.sample_size, ws.tr_T, ws.tr_q, ws.tr_inl);
-        k_trial_score<<<sblocks, 256, 0, st>>>(src, tgt, n, tau2, 1, &ws.ctl->gc.lsq_active, ws.tr_T, ws.tr_q,
-                                               ws.tr_inl);
+        k_trial_score<<<sblocks, 256, 0, st>>>(ws.P8, n, tau2, 1, &ws.ctl->gc.lsq_active, ws.tr_T, ws.tr_q, ws.tr_inl);
     }
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;

@@ -122,22 +122,34 @@ def _pinned_mask(n):
     return _PINNED_MASK[:n]
 
 
+def _dev_or_pinned_f32(x):
+    """A pinned, contiguous fp32 HOST tensor is passed to the library as it is: under unified addressing the
+    pack kernel reads it straight over PCIe / C2C (the host->device transfer of the call, no staging copy, no
+    extra launches); everything else goes through to_dev_f32."""
+    if isinstance(x, torch.Tensor) and not x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() \
+            and x.is_pinned() and x.numel() > 0:
+        _lib.require_cuda()
+        return x.detach()
+    return to_dev_f32(x)
+
+
 def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
     """lr_ransac_rigid -> dict(T, T_refit, mask | None, + LrRansacStats fields).
 
     mask: CUDA bool tensor, or with mask_on_host a numpy bool array: the kernel then writes the inlier bytes
     straight into pinned, device-mapped host memory (unified addressing) and the call's own synchronisation
     covers them -- no conversion kernel, no second copy, no second synchronisation."""
-    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    src, tgt = _dev_or_pinned_f32(src), _dev_or_pinned_f32(tgt)
     n = src.shape[0]
     T = (ctypes.c_double * 16)()
     Tr = (ctypes.c_double * 16)()
     st = LrRansacStats()
     mask = None
     if want_mask:
-        mask = _pinned_mask(n) if mask_on_host else torch.empty(n, dtype=torch.uint8, device=src.device)
+        mask = _pinned_mask(n) if mask_on_host else torch.empty(n, dtype=torch.uint8, device=_dev())
     mask_ptr = None if mask is None else ctypes.c_void_p(mask.data_ptr())
-    rc = _lib.lib().lr_ransac_rigid(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), ctypes.byref(params), T, Tr,
+    rc = _lib.lib().lr_ransac_rigid(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(tgt.data_ptr()),
+                                    ctypes.c_int64(n), ctypes.byref(params), T, Tr,
                                     mask_ptr, ctypes.byref(st), _lib.stream_ptr())
     _lib.check(rc, "lr_ransac_rigid")
     if mask is not None:

@@ -220,3 +220,22 @@ def test_sweep_early_out_is_exact():
         assert np.array_equal(x, y)
     oc, ob = O.score_samples(d["src"], d["tgt"], samples[:3000], 0.6, False, 0.9)
     assert np.array_equal(out[0][0][:3000], oc)
+
+
+def test_pinned_host_inputs_are_read_in_place():
+    """engine.ransac_rigid hands pinned fp32 host tensors to the library as they are (k_pack reads them over the
+    bus, everything after works on packed device copies): same results as device-resident inputs, both scorings."""
+    d = synthetic.make_correspondences(7000, inlier_ratio=0.3, seed=23)
+    hs, ht = torch.from_numpy(d["src"]).pin_memory(), torch.from_numpy(d["tgt"]).pin_memory()
+    ds, dt = hs.cuda(), ht.cuda()
+    for kw in (dict(), dict(scoring=engine.SCORE_MSAC, lo_rounds=3, lo_trials=8, lsq_iters=2)):
+        p = engine.make_params(max_iters=40000, seed=4, **kw)
+        a = engine.ransac_rigid(hs, ht, p, want_mask=True, mask_on_host=True)
+        b = engine.ransac_rigid(ds, dt, p, want_mask=True)
+        for k in ("best_id", "best_count", "n_scored", "refit_count", "best_score", "lo_score", "lo_improved"):
+            assert a[k] == b[k], k
+        # (the least-squares passes of the MSAC run reduce with fp64 atomics: equal to ~1e-15, not bit for bit)
+        assert np.abs(a["T"] - b["T"]).max() < 1e-9 and np.array_equal(a["mask"], b["mask"].cpu().numpy())
+        if not kw:
+            assert np.array_equal(a["T"], b["T"])
+        assert close_T(a["T_refit"], b["T_refit"])
