@@ -161,6 +161,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     use_elc = not args.no_elc
@@ -310,12 +311,12 @@ def run_ours(args):
             line["mnn_match"] = bench_matching(engine, torch, dev)
             other = bench_other_regime(engine, torch, resident, not use_elc)
             line["other_regime"] = other
-            line["gc_semantics"] = bench_gc_semantics(engine, torch, resident, pairs[0], use_elc)
-            try:
+            try:  # torchrun exports OMP_NUM_THREADS=1: the CPU legs use every core this rank may run on
                 from oracle import lr_oracle as _O
                 _O.set_threads(len(os.sched_getaffinity(0)))
             except Exception:
                 pass
+            line["gc_semantics"] = bench_gc_semantics(engine, torch, resident, pairs[0], use_elc)
             cpu_pairs = make_pairs(1, CFG_SEED) * 8
             cpu_ransac_rate(cpu_pairs[:1], use_elc)  # warm the thread pool
             v, cores, secs = cpu_ransac_rate(cpu_pairs, use_elc)
