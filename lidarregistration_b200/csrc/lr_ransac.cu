@@ -29,9 +29,10 @@
 
 namespace {
 
-constexpr int kScoreThreads = 128;  // threads per score CTA; each thread owns TWO hypotheses (packed f32x2)
+constexpr int kScoreThreads = 32;   // threads per score CTA (ONE warp: warps with different early-out rates never wait for
+                                    // each other at a barrier); each thread owns TWO hypotheses (packed f32x2)
 constexpr int kHypPerItem = 2 * kScoreThreads;
-constexpr int kChunk = 512;         // correspondences per shared-memory stage (48 B each, double buffered)
+constexpr int kChunk = 128;         // correspondences per shared-memory stage (48 B each, double buffered)
 constexpr int kGroup = 4;           // points whose first residual component is evaluated together (early-out votes)
 constexpr int kBlock = 32;          // points between two checks of the "some residual is in the band" flag
 constexpr int kGenThreads = 128;
@@ -415,9 +416,9 @@ __global__ void k_ctl_reset(Ctl *ctl)
 }
 
 // fp32 models are stored so that the sweep can load ready-made f32x2 operands:
-// slots s and s + 128 of the same 256-slot block share 16 float2
-// {r00 r01 r02 t0 | r10 r11 r12 t1 | r20 r21 r22 t2 | lo hi - -}, value v of slot s
-// sits at float index ((s / 256 * 128 + s % 128) * 16 + v) * 2 + (s % 256) / 128.
+// slots s and s + W of the same 2W-slot block (W = kScoreThreads) share 16 float2
+// {r00 r01 r02 t0 | r10 r11 r12 t1 | r20 r21 r22 t2 | lo hi c -}, value v of slot s
+// sits at float index ((s / 2W * W + s % W) * 16 + v) * 2 + (s % 2W) / W.
 __device__ __forceinline__ size_t m32_index(int slot, int v)
 {
     const int blk = slot / kHypPerItem, r = slot % kHypPerItem;
@@ -634,7 +635,7 @@ __device__ __noinline__ int recheck_group(const float4 *grp, int npts, const flo
 // residual instead of 15).  Correspondences are staged with cp.async in
 // double-buffered chunks.  Counting is exact: residuals below `lo` are inliers,
 // above `hi` outliers, and the rare ones in between are decided in fp64 by
-// recheck_group().  Work item = (256 survivors) x (range of point chunks); the
+// recheck_group().  Work item = (64 survivors) x (range of point chunks); the
 // split over points is chosen on the device from the survivor count so that a
 // round with few survivors (ELC rejects ~97 % at 70 % outliers) fills the chip.
 // SKIP (default): the first residual component d0 of four points is evaluated first (4 of
@@ -644,7 +645,7 @@ __device__ __noinline__ int recheck_group(const float4 *grp, int npts, const flo
 // 58 % of the (warp, point) pairs take the early-out at cfg 3 (ncu: 0.86 M of 2.05 M
 // executions of the live path); counts are unchanged by construction.
 template <bool SKIP>
-__global__ void __launch_bounds__(kScoreThreads, 4)
+__global__ void __launch_bounds__(kScoreThreads, 16)
 k_score(const float4 *__restrict__ P12, int64_t n_pad, Ctl *ctl, const float4 *__restrict__ m32,
         const double *__restrict__ m64, int *__restrict__ cnt, double thr2)
 {
@@ -1179,11 +1180,12 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     lr::prof_end(tok, st);
     if (p.scoring == LR_SCORE_MSAC) return gc_launch_score(src, tgt, n, p, ws, lo, len, scores_out, counts_out, st);
     tok = lr::prof_begin(lr::PROF_SCORE, st);
-    // 4 resident CTAs of 128 threads per SM (48 KB of staging each)
+    // 16 resident one-warp CTAs per SM (128 registers per thread fill the register file; 12 KB of staging each):
+    // no CTA-level barrier couples warps whose early-out rates differ
     if (g_score_mode == 0)
-        k_score<true><<<sms * 4, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
+        k_score<true><<<sms * 16, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
     else
-        k_score<false><<<sms * 4, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
+        k_score<false><<<sms * 16, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
     lr::prof_end(tok, st);
     int rblocks = (int)((len + 255) / 256);
     if (rblocks > sms * 4) rblocks = sms * 4;
