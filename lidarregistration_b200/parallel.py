@@ -69,10 +69,14 @@ def ransac_rigid_sharded(src, tgt, params, backend=None, group=None, device=None
     params: engine.LrRansacParams.  Returns the same dict as engine.ransac_rigid on every rank.
     Semantics are those of the single-GPU call: with a confidence < 1 the exit is evaluated at
     round ends (round_size hypotheses, all ranks together); with a fixed budget the whole budget is
-    one round per rank and a single all-reduce.
+    one round per rank and a single all-reduce.  Count scoring only: the exchanged key packs (inlier count,
+    hypothesis id) into 64 bits, a quantised MSAC score needs up to 47 bits on its own (shard MSAC runs by pair).
     """
     if backend is None:
         from . import engine as backend
+    if int(getattr(params, "scoring", 0)) != 0:
+        raise ValueError("ransac_rigid_sharded: hypothesis sharding supports count scoring only "
+                         "(LR_SCORE_COUNT); use ransac_rigid_pairs for LR_SCORE_MSAC runs")
     rank, ws = world(group)
     n = int(src.shape[0])
     m = int(params.sample_size)

@@ -62,3 +62,28 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "lr_oracle" not in txt.replace("oracle/lr_oracle.c", "") and "import oracle" not in txt \
                     and "from oracle" not in txt, f
+
+
+def test_hypothesis_sharding_refuses_msac_scoring():
+    """host-side guard (no GPU needed): the packed (count, id) key cannot carry an MSAC score"""
+    import numpy as np
+    import pytest
+    from lidarregistration_b200 import engine, parallel
+    p = engine.make_params(scoring=engine.SCORE_MSAC, lo_rounds=2)
+    with pytest.raises(ValueError, match="count scoring only"):
+        parallel.ransac_rigid_sharded(np.zeros((10, 3), np.float32), np.zeros((10, 3), np.float32), p)
+
+
+def test_gc_options_mapping():
+    """--GC_scoring / --GC_LO -> native parameters (GC_RANSAC.py:12-37, gcransac_python.cpp:418-423, 511-521)"""
+    import sys
+    import pytest
+    import lidarregistration_b200.algorithms  # noqa: F401
+    G = sys.modules["lidarregistration_b200.algorithms.GC_RANSAC"]
+    assert G.gc_options(None, True) == dict(scoring=0) == G.gc_options("count", False)
+    assert G.gc_options("MSAC", True) == dict(scoring=1, lo_rounds=10, lo_trials=20, lsq_iters=10)
+    assert G.gc_options("msac", False) == dict(scoring=1, lo_rounds=0, lo_trials=20, lsq_iters=0)
+    with pytest.raises(ValueError):
+        G.gc_options("LMEDS", True)
+    with pytest.raises(NotImplementedError):
+        G.gc_options("MSAC", True, spatial_coherence_weight=0.1)
