@@ -458,7 +458,7 @@ __device__ __forceinline__ void load_pq(const float4 *__restrict__ P8, int64_t k
 }
 
 // one thread per hypothesis id: counter-based sample -> ELC; survivors are
-// compacted (warp-aggregated) as (id, sample indices)
+// compacted (block-aggregated) as (id, sample indices)
 template <int M>
 __global__ void __launch_bounds__(kGenThreads)
 k_gen(const float4 *__restrict__ P8, int64_t n, uint64_t seed, int sampler,
@@ -483,12 +483,25 @@ k_gen(const float4 *__restrict__ P8, int64_t n, uint64_t seed, int sampler,
             ok = elc_pass_fast<M>(P, Q, elc_ratio);
         }
     }
-    unsigned ballot = __ballot_sync(0xffffffffu, ok);
-    int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0 && ballot) base = atomicAdd(&ctl->n_surv, __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
+    // block-aggregated compaction: ONE atomic on the survivor counter per CTA (a warp-level atomic per warp with
+    // survivors means ~30k same-address atomics per million hypotheses, which serialise in L2)
+    __shared__ int s_wcnt[kGenThreads / 32];
+    __shared__ int s_base;
+    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_wcnt[w] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < kGenThreads / 32; ++k) tot += s_wcnt[k];
+        s_base = tot ? atomicAdd(&ctl->n_surv, tot) : 0;
+    }
+    __syncthreads();
     if (!ok) return;
+    int base = s_base;
+#pragma unroll
+    for (int k = 0; k < kGenThreads / 32; ++k) base += (k < w) ? s_wcnt[k] : 0;
     int slot = base + __popc(ballot & ((1u << lane) - 1u));
     slot_id[slot] = (uint32_t)id;
 #pragma unroll
