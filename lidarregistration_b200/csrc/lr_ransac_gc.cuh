@@ -483,7 +483,8 @@ int gc_enqueue_polish(const float *src, const float *tgt, int64_t n, const LrRan
 {
     const double thr2 = p.threshold * p.threshold, tau2 = gc_tau2(p.threshold);
     const int trials = p.lo_trials < 1 ? 1 : (p.lo_trials > kGcMaxTrials ? kGcMaxTrials : p.lo_trials);
-    const int lo_rounds = p.lo_rounds < 0 ? 0 : p.lo_rounds, lsq_iters = p.lsq_iters < 0 ? 0 : p.lsq_iters;
+    // no inner draws = no local optimisation (the oracle's trial loop is then empty and the stage ends at once)
+    const int lo_rounds = (p.lo_rounds < 0 || p.lo_trials < 1) ? 0 : p.lo_rounds, lsq_iters = p.lsq_iters < 0 ? 0 : p.lsq_iters;
     const uint64_t lo_seed = mix64(p.seed ^ kLoSeedSalt);
     const float *P8f = reinterpret_cast<const float *>(ws.P8);  // fetch_pair's packed-record convention
     const int sblocks = (int)((n + 255) / 256) > 0 ? (int)((n + 255) / 256) : 1;
