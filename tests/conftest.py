@@ -32,3 +32,16 @@ def matching_golden(golden_dir):
 def kabsch_golden(golden_dir):
     import numpy as np
     return np.load(os.path.join(golden_dir, "kabsch_ref.npz"))
+
+
+@pytest.fixture(scope="session")
+def refit_golden(golden_dir):
+    """24 cases of the reference's weighted_procrustes (DGR/util/procrustes.py:34-56) with 0/1 weights = the inlier
+    mask of a coarse model at 0.6 m: the refit step of FR.py:99-111 (tests/golden/make_golden.py::refit_cases)"""
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "refit_ref.npz"))
+    cases = {}
+    for key in z.files:
+        case, field = key.split("/")
+        cases.setdefault(case, {})[field] = z[key]
+    return [cases[k] for k in sorted(cases)]

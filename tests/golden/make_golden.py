@@ -6,6 +6,8 @@ on the GPU box):   python tests/golden/make_golden.py
 Imports, unmodified:
   /root/reference/Experiments/algorithms/matching.py   (find_nn, nn_to_mutual, ratio)
   /root/reference/Experiments/models/common.py         (rigid_transform_3d: Kabsch witness)
+  /root/reference/DGR/util/procrustes.py                (weighted_procrustes: witness of the refit over an
+                                                         inlier mask, FR.py:99-111 / SURVEY 8 a13-a14)
 on CPU torch and stores inputs + the reference's outputs as .npz.
 """
 import os
@@ -112,8 +114,46 @@ def gpf_case():
     print("gpf_ref.npz:", len(k0), "of", N, "pairs kept")
 
 
+def refit_cases():
+    """Refit over the inliers of a coarse model (FR.py:99-111): the reference's weighted_procrustes with 0/1
+    weights = the inlier mask at 0.6 m.  Stored per case: correspondences, the coarse model, the mask, R, t."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dgr_procrustes", "/root/reference/DGR/util/procrustes.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from lidarregistration_b200 import synthetic
+    rng = np.random.default_rng(54)
+    out = {}
+    for c in range(24):
+        n = int(rng.integers(300, 6000))
+        d = synthetic.make_correspondences(n, inlier_ratio=float(rng.uniform(0.1, 0.8)), seed=540 + c,
+                                           noise=float(rng.uniform(0.03, 0.15)))
+        # a coarse model: the true motion disturbed like a 3-point RANSAC estimate
+        ang = rng.normal(0, 0.004)
+        dR = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+        T = d["T_gt"].copy()
+        T[:3, :3] = dR @ T[:3, :3]
+        T[:3, 3] += rng.normal(0, 0.1, 3)
+        if c == 0:
+            T = np.eye(4)  # hardly any inlier: tiny sets
+        p, q = d["src"].astype(np.float64), d["tgt"].astype(np.float64)
+        r2 = ((p @ T[:3, :3].T + T[:3, 3] - q) ** 2).sum(1)
+        mask = r2 < 0.36
+        assert np.abs(r2 - 0.36).min() > 1e-7  # no borderline decision in the fixture
+        R, t = mod.weighted_procrustes(torch.from_numpy(d["src"]), torch.from_numpy(d["tgt"]),
+                                       torch.from_numpy(mask.astype(np.float32))[:, None])
+        out["c%02d/src" % c], out["c%02d/tgt" % c] = d["src"], d["tgt"]
+        out["c%02d/T_in" % c], out["c%02d/mask" % c] = T, mask
+        out["c%02d/R" % c], out["c%02d/t" % c] = R.numpy(), t.numpy()
+    np.savez_compressed(os.path.join(OUT, "refit_ref.npz"), **out)
+    print("refit_ref.npz: 24 cases")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    matching_cases()
-    kabsch_cases()
-    gpf_case()
+    if "--only-refit" not in sys.argv:  # the older fixtures are kept byte-identical unless regenerated on purpose
+        matching_cases()
+        kabsch_cases()
+        gpf_case()
+    refit_cases()

@@ -182,3 +182,20 @@ def test_oracle_recovers_motion(outlier):
     from lidarregistration_b200 import metrics
     assert metrics.registration_success(r["T_refit"], d["T_gt"])
     assert 0 < r["n_passed"] < 4096
+
+
+def test_refit_against_reference_weighted_procrustes(refit_golden):
+    """a13: inliers of a coarse model at 0.6 m -> Kabsch, against the reference's own weighted_procrustes
+    (DGR/util/procrustes.py:34-56, fp32 output) run on the same inputs with the mask as 0/1 weights."""
+    for g in refit_golden:
+        n = len(g["src"])
+        idx = np.arange(n)
+        cnt, mask = O.count_inliers(g["src"], g["tgt"], g["T_in"], 0.6, return_mask=True)
+        assert np.array_equal(mask, g["mask"]) and cnt == int(g["mask"].sum())
+        T, k = O.refit_indexed(g["src"], g["tgt"], idx, idx, g["T_in"], 0.6)
+        assert k == cnt
+        if k < 3:
+            continue  # rank-deficient sets: both sides return *a* rotation, not a comparable one
+        scale = 1.0 + np.abs(g["src"][g["mask"]]).max()
+        assert np.abs(T[:3, :3] - g["R"]).max() < 5e-6, np.abs(T[:3, :3] - g["R"]).max()
+        assert np.abs(T[:3, 3] - g["t"]).max() < 1e-5 * scale, np.abs(T[:3, 3] - g["t"]).max()
