@@ -8,6 +8,8 @@ Imports, unmodified:
   /root/reference/Experiments/models/common.py         (rigid_transform_3d: Kabsch witness)
   /root/reference/DGR/util/procrustes.py                (weighted_procrustes: witness of the refit over an
                                                          inlier mask, FR.py:99-111 / SURVEY 8 a13-a14)
+  /root/reference/Experiments/libs/loss.py              (TransformationLoss: the RE / TE / recall definitions
+                                                         behind stats columns 0-2, Experiments/test.py:325-331)
 on CPU torch and stores inputs + the reference's outputs as .npz.
 """
 import os
@@ -150,10 +152,43 @@ def refit_cases():
     print("refit_ref.npz: 24 cases")
 
 
+def metrics_cases():
+    """RE (deg), TE (cm), success at 5 deg / 60 cm from the reference's TransformationLoss.forward."""
+    from libs.loss import TransformationLoss
+    crit = TransformationLoss(re_thre=5, te_thre=60)  # Experiments/test.py:325-331 for the RANSAC path
+    rng = np.random.default_rng(55)
+
+    def rand_T(ang_scale, t_scale):
+        ax = rng.standard_normal(3); ax /= np.linalg.norm(ax)
+        ang = rng.normal(0, ang_scale)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        T = np.eye(4)
+        T[:3, :3] = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        T[:3, 3] = rng.normal(0, t_scale, 3)
+        return T
+
+    Ts, Tgs, REs, TEs, OKs = [], [], [], [], []
+    for c in range(60):
+        Tg = rand_T(1.0, 20.0)
+        T = rand_T([0.002, 0.05, 0.2, 3.0][c % 4], [0.01, 0.3, 1.0][c % 3]) @ Tg
+        pts = torch.zeros(1, 1, 3)
+        _, rec, re, te, _ = crit(torch.from_numpy(T).float()[None], torch.from_numpy(Tg).float()[None], pts, pts,
+                                 torch.zeros(1, 1))
+        Ts.append(T), Tgs.append(Tg), REs.append(float(re)), TEs.append(float(te)), OKs.append(rec > 50.0)
+    np.savez_compressed(os.path.join(OUT, "metrics_ref.npz"), T=np.array(Ts), T_gt=np.array(Tgs), RE=np.array(REs),
+                        TE=np.array(TEs), ok=np.array(OKs))
+    print("metrics_ref.npz: 60 cases,", int(np.sum(OKs)), "successes")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--only-metrics" in sys.argv:
+        metrics_cases()
+        sys.exit(0)
     if "--only-refit" not in sys.argv:  # the older fixtures are kept byte-identical unless regenerated on purpose
         matching_cases()
         kabsch_cases()
         gpf_case()
     refit_cases()
+    if "--only-refit" not in sys.argv:
+        metrics_cases()

@@ -87,3 +87,17 @@ def test_gc_options_mapping():
         G.gc_options("LMEDS", True)
     with pytest.raises(NotImplementedError):
         G.gc_options("MSAC", True, spatial_coherence_weight=0.1)
+
+
+def test_metrics_match_reference_transformation_loss(golden_dir):
+    """RE / TE / success (stats columns 0-2) against the reference's TransformationLoss.forward
+    (Experiments/libs/loss.py:44-51, run by tests/golden/make_golden.py::metrics_cases; fp32 on its side)."""
+    import os
+    import numpy as np
+    from lidarregistration_b200 import metrics
+    g = np.load(os.path.join(golden_dir, "metrics_ref.npz"))
+    for T, Tg, re, te, ok in zip(g["T"], g["T_gt"], g["RE"], g["TE"], g["ok"]):
+        assert abs(metrics.rotation_error_deg(T, Tg) - re) < 2e-2 + 1e-4 * re   # acos near 1 in fp32 on the reference side
+        assert abs(metrics.translation_error_cm(T, Tg) - te) < 1e-2 + 1e-5 * te
+        near = abs(re - 5.0) < 0.05 or abs(te - 60.0) < 0.05
+        assert near or metrics.registration_success(T, Tg) == bool(ok)
