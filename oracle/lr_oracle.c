@@ -12,6 +12,7 @@
  *              Experiments/algorithms/matching.py:222-239 (nn_to_mutual)
  *              Experiments/algorithms/matching.py:89-98   (ratio quality)
  *   ELC      : GC-RANSAC/src/pygcransac/include/preemption/preemption_edge_length.h:71-128
+ *              (checked against that header itself, compiled in place into oracle/_ref by `make ref`)
  *   RANSAC   : Experiments/algorithms/FR.py:99-111,122-139 (Open3D branch: parameters + refit)
  *              Experiments/algorithms/GC_RANSAC.py:8-55, gcransac_python.cpp:404-624 (GC branch wiring)
  *              The loop arithmetic itself lives in un-vendored third-party code

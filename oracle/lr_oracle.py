@@ -42,6 +42,38 @@ def build(force=False):
     return _SO
 
 
+_REF_SO = os.path.join(_HERE, "_ref", "libelc_ref.so")
+_ref = None
+
+
+def build_ref():
+    """oracle/_ref: compile the reference's own ELC header in place (needs /root/reference; a prebuilt file is kept
+    otherwise).  Returns the path, or None if neither the reference nor a prebuilt file exists."""
+    if os.path.exists("/root/reference/GC-RANSAC/src/pygcransac/include/preemption/preemption_edge_length.h"):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return _REF_SO if os.path.exists(_REF_SO) else None
+
+
+def ref_elc(src, tgt, sample):
+    """The REFERENCE's EdgeLenPreemptiveVerification::verifyModel (preemption_edge_length.h:71-128, compiled from
+    the reference tree into oracle/_ref) on the N x 6 fp64 matrix pygcransac builds (gcransac_python.cpp:426-435)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_SO):
+            raise FileNotFoundError(_REF_SO)
+        _ref = ctypes.CDLL(_REF_SO)
+        _ref.ref_elc_verify.restype = ctypes.c_int
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(src, np.float32).astype(np.float64),
+                                               np.asarray(tgt, np.float32).astype(np.float64)], axis=1))
+    smp = np.ascontiguousarray(sample, dtype=np.uint64)
+    return bool(_ref.ref_elc_verify(_p(pts, c_f64p), ctypes.c_long(len(pts)),
+                                    smp.ctypes.data_as(ctypes.POINTER(ctypes.c_size_t)), ctypes.c_size_t(len(smp))))
+
+
+def has_ref():
+    return os.path.exists(_REF_SO)
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -179,3 +179,33 @@ def test_reference_interface_with_msac_scoring():
     T = FR(*t, args, p["T_gt"])[0]
     assert metrics.registration_success(T, p["T_gt"])
     assert metrics.translation_error_cm(T, p["T_gt"]) < 10.0
+
+
+@pytest.mark.skipif(not O.has_ref(), reason="oracle/_ref/libelc_ref.so not built (needs /root/reference)")
+def test_zz_cuda_elc_against_compiled_reference_header():
+    """k_gen's edge-length decision (elc_pass_fast: squared lengths, sqrt form only near equality) against the
+    REFERENCE's own verifyModel (preemption_edge_length.h:71-128 compiled into oracle/_ref), through the fed-sample
+    hook: count == -1 <=> the reference rejects.  Random triplets plus edges placed on / within two fp32 ulps of
+    the 0.9 boundary.  (Last test of the suite on purpose.)"""
+    d = synthetic.make_correspondences(4000, inlier_ratio=0.5, seed=77)
+    rng = np.random.default_rng(9)
+    inl = np.flatnonzero(d["is_inlier"])
+    P_extra, Q_extra = [], []
+    for k in range(300):
+        L = np.float32(rng.uniform(1, 60))
+        for nudge in (-2, -1, 0, 1, 2):
+            P = np.zeros((3, 3), np.float32); P[1, 0] = L; P[2, 1] = L
+            Q = np.zeros((3, 3), np.float32); Q[1, 0] = np.float32(L / np.float32(0.9)); Q[2, 1] = L
+            for _ in range(abs(nudge)):
+                Q[1, 0] = np.nextafter(Q[1, 0], np.float32(np.inf if nudge > 0 else -np.inf))
+            P_extra.append(P), Q_extra.append(Q)
+    src = np.concatenate([d["src"]] + P_extra).astype(np.float32)
+    tgt = np.concatenate([d["tgt"]] + Q_extra).astype(np.float32)
+    rand = np.stack([rng.choice(inl, 3, replace=False) if t % 2 else rng.integers(0, 4000, 3) for t in range(6000)])
+    edge = 4000 + 3 * np.arange(len(P_extra))[:, None] + np.arange(3)[None, :]
+    samples = np.concatenate([rand, edge]).astype(np.int32)
+    counts, _, _ = engine.ransac_score_samples(src, tgt, samples, THR, True, 0.9)
+    rejected = counts.cpu().numpy() < 0
+    ref = np.array([O.ref_elc(src, tgt, s) for s in samples])
+    assert np.array_equal(rejected, ~ref)
+    assert 0.2 < ref[:6000].mean() < 0.8 and 0 < ref[6000:].sum() < len(edge)  # both outcomes, also at the boundary

@@ -199,3 +199,40 @@ def test_refit_against_reference_weighted_procrustes(refit_golden):
         scale = 1.0 + np.abs(g["src"][g["mask"]]).max()
         assert np.abs(T[:3, :3] - g["R"]).max() < 5e-6, np.abs(T[:3, :3] - g["R"]).max()
         assert np.abs(T[:3, 3] - g["t"]).max() < 1e-5 * scale, np.abs(T[:3, 3] - g["t"]).max()
+
+
+needs_ref = pytest.mark.skipif(not O.has_ref(), reason="oracle/_ref/libelc_ref.so not built (needs /root/reference)")
+
+
+@needs_ref
+def test_elc_against_compiled_reference_header():
+    """The oracle's lro_elc vs the REFERENCE's own EdgeLenPreemptiveVerification::verifyModel
+    (preemption_edge_length.h:71-128, compiled unmodified from the reference tree into oracle/_ref): random
+    triplets / quadruplets on LiDAR-shaped correspondences (about half pass), duplicate indices, and edges
+    constructed to sit exactly on / one ulp around the 0.9 boundary."""
+    d = synthetic.make_correspondences(4000, inlier_ratio=0.5, seed=77)
+    src, tgt = d["src"], d["tgt"]
+    rng = np.random.default_rng(8)
+    inl = np.flatnonzero(d["is_inlier"])
+    n_pass = 0
+    for m in (3, 4):
+        for trial in range(6000):
+            s = rng.choice(inl, m, replace=False) if trial % 2 else rng.integers(0, 4000, m)
+            if trial % 50 == 0:
+                s[1] = s[0]  # duplicates: 0 < 0 is false -> that edge passes (SURVEY App. B)
+            ref = O.ref_elc(src, tgt, s)
+            mine = O.elc(src[s].astype(np.float64), tgt[s].astype(np.float64), 0.9)
+            assert ref == mine, (m, trial, s)
+            n_pass += ref
+    assert 2000 < n_pass < 10000  # both outcomes are exercised
+    # boundary: target edge = source edge / 0.9 along one axis, nudged by single ulps of fp32 coordinates
+    base = np.zeros((3, 3), np.float32)
+    for k in range(400):
+        L = np.float32(rng.uniform(1, 60))
+        P = base.copy(); P[1, 0] = L; P[2, 1] = L
+        Q = base.copy(); Q[1, 0] = np.float32(L / np.float32(0.9)); Q[2, 1] = L
+        for nudge in (-2, -1, 0, 1, 2):
+            Qn = Q.copy()
+            for _ in range(abs(nudge)):
+                Qn[1, 0] = np.nextafter(Qn[1, 0], np.float32(np.inf if nudge > 0 else -np.inf))
+            assert O.ref_elc(P, Qn, [0, 1, 2]) == O.elc(P.astype(np.float64), Qn.astype(np.float64), 0.9)
