@@ -240,15 +240,3 @@ def test_pinned_host_inputs_are_read_in_place():
             assert np.array_equal(a["T"], b["T"])
         assert close_T(a["T_refit"], b["T_refit"])
 
-
-def test_refit_against_reference_weighted_procrustes(refit_golden):
-    """a13 on the GPU (lr_refit_indexed) against the reference's own weighted_procrustes run on the same inputs
-    (tests/golden/refit_ref.npz; the oracle agrees with it to 1e-7 / 3e-6 m, tests/test_oracle_ransac.py)."""
-    for g in refit_golden:
-        n = len(g["src"])
-        idx = np.arange(n)
-        T, k = engine.refit_indexed(g["src"], g["tgt"], idx, idx, g["T_in"], 0.6)
-        assert k == int(g["mask"].sum())
-        if k < 3:
-            continue
-        assert np.abs(T[:3, :3] - g["R"]).max() < ROT_TOL and np.abs(T[:3, 3] - g["t"]).max() < TRANS_TOL

@@ -181,6 +181,18 @@ def test_reference_interface_with_msac_scoring():
     assert metrics.translation_error_cm(T, p["T_gt"]) < 10.0
 
 
+def test_zy_refit_against_reference_weighted_procrustes(refit_golden):
+    """a13 on the GPU (lr_refit_indexed) against the reference's own weighted_procrustes run on the same inputs
+    (tests/golden/refit_ref.npz; the oracle agrees with it to 1e-7 / 3e-6 m, tests/test_oracle_ransac.py)."""
+    for g in refit_golden:
+        n = len(g["src"])
+        idx = np.arange(n)
+        T, k = engine.refit_indexed(g["src"], g["tgt"], idx, idx, g["T_in"], 0.6)
+        assert k == int(g["mask"].sum())
+        if k < 3:
+            continue
+        assert np.abs(T[:3, :3] - g["R"]).max() < ROT_TOL and np.abs(T[:3, 3] - g["t"]).max() < TRANS_TOL  # north star
+
 @pytest.mark.skipif(not O.has_ref(), reason="oracle/_ref/libelc_ref.so not built (needs /root/reference)")
 def test_zz_cuda_elc_against_compiled_reference_header():
     """k_gen's edge-length decision (elc_pass_fast: squared lengths, sqrt form only near equality) against the
