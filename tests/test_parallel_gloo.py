@@ -38,6 +38,13 @@ class OracleBackend:
     def ransac_rigid_batch(pairs, p):
         out = []
         for src, tgt in pairs:
+            if p.scoring == engine.SCORE_MSAC:  # GC semantics shard by pair like any other run
+                r = O.ransac_gc(src, tgt, m=p.sample_size, sampler=p.sampler, use_elc=bool(p.use_elc), thr=p.threshold,
+                                conf=p.confidence, max_iters=p.max_iters, round_size=p.round_size, seed=p.seed,
+                                lo_rounds=p.lo_rounds, lo_trials=p.lo_trials, lsq_iters=p.lsq_iters)
+                out.append(dict(T=r["T"], best_id=r["best_id"], best_count=r["best_inliers"],
+                                final_score=r["final_score"]))
+                continue
             r = O.ransac(src, tgt, m=p.sample_size, sampler=p.sampler, use_elc=bool(p.use_elc), thr=p.threshold,
                          conf=p.confidence, max_iters=p.max_iters, round_size=p.round_size, seed=p.seed)
             out.append(dict(T=r["T"], best_id=r["best_id"], best_count=r["best_count"]))
@@ -61,6 +68,15 @@ def _worker(rank, world, port, q):
     p = engine.make_params(confidence=1.0, max_iters=500, seed=3, use_elc=True)
     mine = parallel.ransac_rigid_pairs([(d["src"], d["tgt"]) for d in sets], p, backend=OracleBackend)
     out["set"] = [(i, r["best_id"], r["best_count"]) for i, r in mine]
+    pg = engine.make_params(confidence=1.0, max_iters=500, seed=3, use_elc=True, scoring=engine.SCORE_MSAC,
+                            lo_rounds=3, lo_trials=6, lsq_iters=2)
+    mine = parallel.ransac_rigid_pairs([(d["src"], d["tgt"]) for d in sets], pg, backend=OracleBackend)
+    out["set_gc"] = [(i, r["best_id"], r["final_score"]) for i, r in mine]
+    try:
+        parallel.ransac_rigid_sharded(sets[0]["src"], sets[0]["tgt"], pg, backend=OracleBackend)
+        out["gc_sharded_refused"] = False
+    except ValueError:
+        out["gc_sharded_refused"] = True
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -106,3 +122,10 @@ def test_world2_matches_single_process():
         d = synthetic.make_correspondences(400 + 50 * k, inlier_ratio=0.4, seed=900 + k)
         ref = O.ransac(d["src"], d["tgt"], conf=1.0, max_iters=500, seed=3)
         assert (bid, bcnt) == (ref["best_id"], ref["best_count"]), k
+    # GC semantics (MSAC + LO + least squares) shard by pair the same way; hypothesis sharding refuses them
+    got = sorted(res[0]["set_gc"] + res[1]["set_gc"])
+    assert [g[0] for g in got] == list(range(5)) and res[0]["gc_sharded_refused"] and res[1]["gc_sharded_refused"]
+    for k, bid, fq in got:
+        d = synthetic.make_correspondences(400 + 50 * k, inlier_ratio=0.4, seed=900 + k)
+        ref = O.ransac_gc(d["src"], d["tgt"], conf=1.0, max_iters=500, seed=3, lo_rounds=3, lo_trials=6, lsq_iters=2)
+        assert (bid, fq) == (ref["best_id"], ref["final_score"]), k
