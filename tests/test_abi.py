@@ -101,3 +101,14 @@ def test_metrics_match_reference_transformation_loss(golden_dir):
         assert abs(metrics.translation_error_cm(T, Tg) - te) < 1e-2 + 1e-5 * te
         near = abs(re - 5.0) < 0.05 or abs(te - 60.0) < 0.05
         assert near or metrics.registration_success(T, Tg) == bool(ok)
+
+
+def test_mode_switches_validate_their_argument():
+    """host-only entries of the ABI: bad arguments come back as LR_ERR_ARG with a message, nothing throws"""
+    from lidarregistration_b200 import _lib
+    L = _lib.lib()
+    assert L.lr_ransac_set_mode(0) == 0 and L.lr_ransac_set_mode(1) == 0 and L.lr_ransac_set_mode(0) == 0
+    assert L.lr_ransac_set_mode(7) == 1 and b"mode" in L.lr_last_error()
+    assert L.lr_match_set_mode(0) == 0
+    assert L.lr_match_set_mode(99) != 0 and len(L.lr_last_error()) > 0
+    assert L.lr_match_set_mode(0) == 0
