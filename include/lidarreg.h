@@ -86,7 +86,7 @@ typedef struct LrRansacStats {
 
 /* ---- library ---------------------------------------------------------- */
 const char *lr_last_error(void);
-int lr_version(void);
+int lr_version(void); /* 110 since LrRansacParams / LrRansacStats carry the LR_SCORE_MSAC fields (100 before) */
 /* [host] outputs; number of SMs and compute capability of the current device */
 int lr_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* release every device workspace held by the library */

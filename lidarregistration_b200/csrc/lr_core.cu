@@ -80,7 +80,7 @@ int sm_count()
 
 LR_EXPORT const char *lr_last_error(void) { return lr::g_err; }
 
-LR_EXPORT int lr_version(void) { return 100; }
+LR_EXPORT int lr_version(void) { return 110; }  // 110: LrRansacParams / LrRansacStats grew the LR_SCORE_MSAC fields
 
 LR_EXPORT int lr_device_info(int *sms, int *major, int *minor)
 {
