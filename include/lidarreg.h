@@ -86,7 +86,7 @@ typedef struct LrRansacStats {
 
 /* ---- library ---------------------------------------------------------- */
 const char *lr_last_error(void);
-int lr_version(void); /* 110 since LrRansacParams / LrRansacStats carry the LR_SCORE_MSAC fields (100 before) */
+int lr_version(void); /* 120: lr_comm_*, lr_ransac_rigid_sharded, lr_ransac_tc_probe, three sweep modes (110: LR_SCORE_MSAC) */
 /* [host] outputs; number of SMs and compute capability of the current device */
 int lr_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* release every device workspace held by the library */
@@ -149,8 +149,11 @@ int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, v
 int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
                     double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
 
-/* Implementation switch of the inlier sweep (identical results): 0 = with the warp-uniform early-out on the first
- * residual component [default], 1 = every residual evaluated in full (A/B measurements). */
+/* Implementation switch of the LR_SCORE_COUNT inlier sweep (identical results):
+ * 0 = tensor-core sweep [default]: the three residual components as tcgen05 MMAs over fp16 operand pieces,
+ *     residuals inside the proven error band decided in fp64 (csrc/lr_score_tc.cuh);
+ * 1 = fp32 CUDA-core sweep, every residual in full; 2 = the same with the warp-uniform early-out on the first
+ *     residual component (round 1's default).  A/B measurements and parity tests. */
 int lr_ransac_set_mode(int mode);
 
 /* The same for `count` independent pairs (the reference's per-pair loop over a registration set,
@@ -180,7 +183,8 @@ int lr_ransac_score_samples_msac(const float *src, const float *tgt, int64_t n, 
                                  int m, double threshold, int use_elc, double elc_ratio, int64_t *scores,
                                  int32_t *inliers, int64_t *best, void *stream);
 
-/* Multi-GPU hypothesis sharding: score hypotheses [id_lo, id_hi)
+/* Multi-GPU hypothesis sharding, caller-owned collective (the transport-agnostic form: the caller
+ * all-reduces the key with NCCL / gloo / MPI; lr_ransac_rigid_sharded is the fused form): score hypotheses [id_lo, id_hi)
  * of the run described by `params` and max-merge the packed result
  *   key = (count + 1) << 32 | (0xFFFFFFFF - id)
  * into *key [device, uint64].  Asynchronous on `stream`.  The caller
@@ -193,6 +197,37 @@ int lr_ransac_shard(const float *src, const float *tgt, int64_t n, const LrRansa
  * `key` [host].  Synchronises `stream`. */
 int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, const LrRansacParams *params, uint64_t key,
                        double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
+
+/* ---- hypothesis sharding with a library-owned communicator (SURVEY 8(b) lr_comm_init, 8(e)) ----------------
+ * One process per GPU of one node.  Every rank owns a small mailbox in device memory that its peers write into
+ * directly over NVLink / NVSwitch (cudaIpc-mapped peer memory): the 8-byte packed (count, id) key of a round is
+ * exchanged inside the kernel that ends the round, so a sharded run has no host round trip and no separate
+ * collective launch.  Set-up: every rank calls lr_comm_init (allocates the mailbox, returns its 64-byte IPC
+ * handle in handle_out [host]), the caller all-gathers the handles (torch.distributed, MPI, a file, ...) and
+ * every rank calls lr_comm_connect with all `world` handles in rank order (all_handles [host], world x 64 B;
+ * may be null when world == 1).  At most 16 ranks.  lr_comm_info: *world = 0 when no communicator is connected. */
+int lr_comm_init(int rank, int world, void *handle_out);
+int lr_comm_connect(const void *all_handles);
+int lr_comm_info(int *rank, int *world);
+int lr_comm_destroy(void);
+
+/* lr_ransac_rigid with the hypotheses of every round split across the ranks of the communicator (a COLLECTIVE:
+ * every rank calls it with the same correspondences and parameters).  Rank g generates and scores the g-th
+ * contiguous slice of each round; the winner is the arg-max over all ranks of the packed key (ties -> lowest id),
+ * so the outputs are those of the single-GPU call for any number of ranks; every rank regenerates the selected
+ * model from its id, computes mask / refit itself and returns the same values.  stats->n_scored counts all
+ * ranks.  LR_SCORE_COUNT only.  An unanswered exchange (a rank missing) times out after ~3 s with LR_ERR_CUDA. */
+int lr_ransac_rigid_sharded(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
+                            double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream);
+
+/* Error-bound probe of the tensor-core sweep (parity tests / micro-benchmark): models[H,12] (device, fp64 rows
+ * [R|t]) are installed as the surviving hypotheses of one round over the correspondences src/tgt[n,3].
+ * d_out [H, pad128(n), 3] fp32 (device, nullable) = the three residual components as the tensor cores deliver
+ * them; E_out[H] (device, nullable) = the bound |d_tc - d_fp64| <= E the sweep's band is derived from;
+ * counts_out[H] int32 (device, nullable) = exact inlier counts of the models through the production sweep.
+ * pad128(n) = n rounded up to a multiple of 128.  H <= 2^20.  Synchronises `stream`. */
+int lr_ransac_tc_probe(const float *src, const float *tgt, int64_t n, const double *models, int64_t H,
+                       double threshold, float *d_out, double *E_out, int32_t *counts_out, void *stream);
 
 /* Confidence stopping rule shared by every rank: hypotheses needed once the
  * best inlier count is c (Open3D: log(1-conf)/log(1-(c/n)^m)). */

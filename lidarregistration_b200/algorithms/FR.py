@@ -15,8 +15,8 @@ import torch
 
 from .. import engine
 from .GC_RANSAC import GC_RANSAC, gc_options
-from .matching import (Grid_Prioritized_Filter, calc_distance_ratio_in_feature_space, find_2nn,
-                       measure_inlier_ratio, nn_to_mutual)
+from .matching import (Grid_Prioritized_Filter, calc_distance_ratio_in_feature_space, find_2nn,  # noqa: F401
+                       find_2nn_dev, measure_inlier_ratio, measure_inlier_ratio_dev, nn_to_mutual, nn_to_mutual_dev)
 
 __doc__ = (__doc__ or "") + "\nFast RANSAC algorithms\n"
 
@@ -61,14 +61,18 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
 
     fcgf_feats0 = engine.to_dev_f32(A_feat)  # FR.py:32-34 [H->D]
     fcgf_feats1 = engine.to_dev_f32(B_feat)
+    xyz0_d, xyz1_d = engine.to_dev_f32(xyz0), engine.to_dev_f32(xyz1)
     mode = "MNN" if args.mode == "MMN" else args.mode
 
+    # The index tensors stay in HBM from the sweep to the RANSAC call (the reference moves them to the CPU after
+    # every step, matching.py:62-65); only counts come back to the host.  --mode GPF still runs its host-side
+    # bookkeeping (matching.Grid_Prioritized_Filter) and converts at its boundary.
     with torch.no_grad():
         # 1. Coarse correspondences
-        corres_idx0, corres_idx1, idx1_2nd, additional_time_for_finding_2nd_closest = find_2nn(fcgf_feats0,
-                                                                                              fcgf_feats1)
+        corres_idx1, idx1_2nd, additional_time_for_finding_2nd_closest = find_2nn_dev(fcgf_feats0, fcgf_feats1)
+        corres_idx0 = torch.arange(corres_idx1.shape[0], device=corres_idx1.device)
         num_pairs_init = len(corres_idx0)
-        inlier_ratio_init = measure_inlier_ratio(corres_idx0, corres_idx1, pcd0, pcd1, T_gt, voxel_size)
+        inlier_ratio_init = measure_inlier_ratio_dev(corres_idx0, corres_idx1, xyz0_d, xyz1_d, T_gt, voxel_size)
 
         torch.cuda.synchronize()
         start_time = time()
@@ -76,11 +80,11 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
         norm_feat_dist = None
         if mode == "MNN":
             corres_idx0_orig, corres_idx1_orig = corres_idx0, corres_idx1
-            corres_idx0, corres_idx1, idx1_2nd = nn_to_mutual(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
-                                                              idx1_2nd, force_return_2nd=True)
+            corres_idx0, corres_idx1, idx1_2nd = nn_to_mutual_dev(fcgf_feats0, fcgf_feats1, corres_idx1, idx1_2nd)
         elif mode == "GPF":
             corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, _, norm_feat_dist = \
-                Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args)
+                Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0.cpu(), corres_idx1.cpu(), idx1_2nd.cpu(),
+                                        xyz0, args)
         elif mode == "no_filter":
             corres_idx0_orig, corres_idx1_orig = corres_idx0, corres_idx1
         else:
@@ -89,7 +93,8 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
         filter_time = time() - start_time
 
         num_pairs_filtered = len(corres_idx0)
-        inlier_ratio_filtered = measure_inlier_ratio(corres_idx0, corres_idx1, pcd0, pcd1, T_gt, voxel_size)
+        inlier_ratio_filtered = measure_inlier_ratio_dev(engine.to_dev_i64(corres_idx0), engine.to_dev_i64(corres_idx1),
+                                                         xyz0_d, xyz1_d, T_gt, voxel_size)
 
     start_time = time()
     ransac_iters = 500 * 10 ** 3  # FR.py:65
@@ -102,22 +107,23 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
         # correspondences, PROSAC quality = -ratio, sort best first, native call, None -> identity.
         # Everything stays in HBM: the gathers, the ratio and the (stable) sort run on the device and
         # lr_ransac_rigid is called directly instead of round-tripping through numpy.
-        src = engine.gather_xyz(xyz0.detach(), corres_idx0)
-        tgt = engine.gather_xyz(xyz1.detach(), corres_idx1)
-        if args.prosac:
+        src = engine.gather_xyz(xyz0_d, corres_idx0)
+        tgt = engine.gather_xyz(xyz1_d, corres_idx1)
+        if args.prosac and num_pairs_filtered > 0:
             if mode == 'GPF':
                 feat_dist = engine.to_dev_f32(norm_feat_dist)
             else:
                 feat_dist = engine.match_ratio(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd)
             order = torch.argsort(feat_dist, stable=True)  # == argsort(-match_quality), match_quality = -ratio
             src, tgt = src[order].contiguous(), tgt[order].contiguous()
-        if args.fast_rejection == "SPRT":
-            raise NotImplementedError("SPRT pre-verification is not part of the B200 hot path (use ELC or NONE)")
-        gc = gc_options(getattr(args, "GC_scoring", "count"), args.GC_LO, args.spatial_coherence_weight)
+        # --fast_rejection: ELC = edge-length test, NONE = the glue's no-preemption branch, SPRT = every hypothesis
+        # scored in full (GC_RANSAC.py docstring: the sequential test is a speed-up device of the reference engine)
+        gc = gc_options(getattr(args, "GC_scoring", "count"), args.GC_LO, args.spatial_coherence_weight,
+                        preemption=args.fast_rejection != "NONE")
         params = engine.make_params(threshold=2 * voxel_size, confidence=args.GC_conf, max_iters=ransac_iters,
                                     seed=getattr(args, "seed", 51), sample_size=3,
                                     sampler=engine.SAMPLER_PROSAC if args.prosac else engine.SAMPLER_UNIFORM,
-                                    use_elc=args.fast_rejection != "NONE", elc_ratio=0.9, refit=True, **gc)
+                                    use_elc=args.fast_rejection == "ELC", elc_ratio=0.9, refit=True, **gc)
         res = engine.ransac_rigid(src, tgt, params)
         # count scoring ends with the least-squares refit over the winner's inliers; the MSAC run's own
         # local optimisation + iterated least squares already produced the final model (GC_RANSAC.py docstring)
@@ -127,8 +133,7 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
         T = RANSAC_registration(pcd0, pcd1, corres_idx0, corres_idx1, 2 * voxel_size, num_iterations=ransac_iters,
                                 args=args)
         # estimate motion using all inlier pairs of the ORIGINAL (unfiltered) NN set (FR.py:99-111)
-        T, _ = engine.refit_indexed(xyz0.detach().float(), xyz1.detach().float(), corres_idx0_orig,
-                                    corres_idx1_orig, T, 2 * voxel_size)
+        T, _ = engine.refit_indexed(xyz0_d, xyz1_d, corres_idx0_orig, corres_idx1_orig, T, 2 * voxel_size)
     else:
         assert False, "unknown codebase"
 
@@ -145,6 +150,8 @@ def RANSAC_registration(pcd0, pcd1, idx0, idx1, distance_threshold, num_iteratio
     xyz1 = torch.from_numpy(np.asarray(pcd1.points)).float()
     src = engine.gather_xyz(xyz0, idx0)
     tgt = engine.gather_xyz(xyz1, idx1)
+    if src.shape[0] < 4:  # Open3D: |corres| < ransac_n -> identity
+        return np.eye(4)
     params = engine.make_params(threshold=distance_threshold, confidence=0.9995, max_iters=num_iterations,
                                 seed=getattr(args, "seed", 51), sample_size=4, sampler=engine.SAMPLER_REPLACE,
                                 use_elc=True, elc_ratio=0.9, refit=False)

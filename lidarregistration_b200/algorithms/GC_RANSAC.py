@@ -10,7 +10,12 @@ Python 3 (tab-indented lines 29-30); this one does.
 What the flags select here (DESIGN.md "GC codebase mapping"):
   --fast_rejection ELC  -> edge-length pre-rejection (preemption_edge_length.h:71-128)
   --fast_rejection NONE -> no pre-rejection
-  --fast_rejection SPRT -> not implemented (raises)
+  --fast_rejection SPRT -> every hypothesis is scored in full, no pre-rejection: the sequential probability ratio
+                           test (gcransac_python.cpp:534-568) only abandons the evaluation of models that are
+                           unlikely to beat the best so far -- a model it lets through gets exactly the score it
+                           has without the test, so it is a speed-up device with a bounded false-rejection rate,
+                           not part of the result's definition; the chip-wide sweep needs no such shortcut.
+                           LO settings are those of the ELC branch (:548-555).  A one-time warning says so.
   --prosac True         -> correspondences pre-sorted best-first (GC_RANSAC.py:39-43) and the
                            PROSAC progressive sampler (sampler id 1, gcransac_python.cpp:464-465)
   --GC_conf c           -> confidence of the stopping rule
@@ -20,7 +25,11 @@ What the flags select here (DESIGN.md "GC codebase mapping"):
   --GC_scoring MSAC     -> pygcransac's own criterion: MSAC score at 1.5 x threshold,
                            then, with --GC_LO True, local optimisation (10 rounds x 20 inner draws of
                            min(21, #inliers) inliers; the graph cut with spatial_coherence_weight = 0 is
-                           thresholding) and 10 passes of iterated least squares; the final model is returned
+                           thresholding) and, whatever --GC_LO says, up to 10 passes of iterated least squares
+                           (--GC_LO False only sets max_graph_cut_number = 0, :518-521; the finishing fit still
+                           runs, App. A "Finish"); the final model is returned.  With --fast_rejection NONE the
+                           reference takes its no-preemption branch (:570-592): 50 inner draws, local optimisation
+                           on regardless of --GC_LO.
   (`GC_scoring` is an attribute this drop-in adds; the reference has no such flag because pygcransac
    knows only MSAC.  args without it get "count".)
 """
@@ -38,10 +47,28 @@ GC_LO_TRIALS = 20   # settings.max_local_optimization_number
 GC_LSQ_ITERS = 10   # iterated least squares, upstream's cap
 
 
-def gc_options(scoring, local_optimisation, spatial_coherence_weight=0.0):
-    """--GC_scoring / --GC_LO -> the scoring / lo_rounds / lo_trials / lsq_iters of engine.make_params"""
+GC_LO_TRIALS_NOPREEMPT = 50  # the no-preemption branch's max_local_optimization_number (gcransac_python.cpp:577)
+
+_warned = set()
+
+
+def _warn_once(key, msg):
+    if key not in _warned:
+        _warned.add(key)
+        import warnings
+        warnings.warn(msg, stacklevel=3)
+
+
+def gc_options(scoring, local_optimisation, spatial_coherence_weight=0.0, preemption=True):
+    """--GC_scoring / --GC_LO / --fast_rejection -> the scoring / lo_rounds / lo_trials / lsq_iters of
+    engine.make_params.  `preemption` False = --fast_rejection NONE = the glue's no-preemption branch."""
     scoring = "count" if scoring is None else str(scoring)
     if scoring.lower() == "count":
+        # count scoring has no local-optimisation stage: say so instead of silently ignoring the flags
+        if not local_optimisation:
+            _warn_once("lo", "--GC_LO False has no effect under --GC_scoring count (no local optimisation stage)")
+        if spatial_coherence_weight != 0.0:
+            _warn_once("scw", "--spatial_coherence_weight has no effect under --GC_scoring count")
         return dict(scoring=engine.SCORE_COUNT)
     if scoring.upper() != "MSAC":
         raise ValueError("GC_scoring must be 'count' or 'MSAC'")
@@ -49,9 +76,12 @@ def gc_options(scoring, local_optimisation, spatial_coherence_weight=0.0):
         # the pairwise term needs the neighbourhood graph (FLANN, gcransac_python.cpp:444-446); the reference's
         # default and README examples all use 0.0 (test.py:306), for which the graph cut is thresholding
         raise NotImplementedError("spatial_coherence_weight != 0 (graph-cut pairwise term) is not built")
+    if not preemption:  # :570-592 ignores do_local_optimization and raises the inner-draw budget to 50
+        return dict(scoring=engine.SCORE_MSAC, lo_rounds=GC_LO_ROUNDS, lo_trials=GC_LO_TRIALS_NOPREEMPT,
+                    lsq_iters=GC_LSQ_ITERS)
     on = bool(local_optimisation)
     return dict(scoring=engine.SCORE_MSAC, lo_rounds=GC_LO_ROUNDS if on else 0, lo_trials=GC_LO_TRIALS,
-                lsq_iters=GC_LSQ_ITERS if on else 0)
+                lsq_iters=GC_LSQ_ITERS)
 
 
 def findRigidTransform(x1y1z1, x2y2z2, threshold, conf, spatial_coherence_weight, max_iters, use_sprt,
@@ -61,12 +91,15 @@ def findRigidTransform(x1y1z1, x2y2z2, threshold, conf, spatial_coherence_weight
 
     -> (pose[4,4] float64 in pygcransac's ROW-vector convention | None, mask[n] bool)
     """
-    if use_sprt and not (min_inlier_ratio_for_sprt < 0):
-        raise NotImplementedError("SPRT pre-verification is not part of the B200 hot path (use ELC or NONE)")
-    opts = gc_options(scoring, int(neighborhood) == 0, spatial_coherence_weight)  # neighborhood != 0: no LO (:418-423)
+    sprt = bool(use_sprt) and not (min_inlier_ratio_for_sprt < 0)
+    if sprt:
+        _warn_once("sprt", "--fast_rejection SPRT: every hypothesis is scored in full (the sequential test is a "
+                           "speed-up device of the reference engine, not part of the result's definition)")
+    # neighborhood != 0: no LO (:418-423)
+    opts = gc_options(scoring, int(neighborhood) == 0, spatial_coherence_weight, preemption=bool(use_sprt))
     params = engine.make_params(threshold=threshold, confidence=conf, max_iters=max_iters, seed=seed, sample_size=3,
                                 sampler=engine.SAMPLER_PROSAC if int(sampler) == 1 else engine.SAMPLER_UNIFORM,
-                                use_elc=bool(use_sprt), elc_ratio=0.9,
+                                use_elc=bool(use_sprt) and not sprt, elc_ratio=0.9,
                                 round_size=round_size, refit=True, **opts)
     res = engine.ransac_rigid(x1y1z1, x2y2z2, params, want_mask=True, mask_on_host=True)
     mask = res["mask"]

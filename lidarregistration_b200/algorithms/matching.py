@@ -30,25 +30,55 @@ def find_nn(F0, F1, return_2nd=False):
     return corres_idx0, corres_idx1, None
 
 
-def find_2nn(fcgf_feats0, fcgf_feats1):
-    """matching.py:6-19: NN + 2nd NN and the *extra* seconds the 2nd NN costs.
+_EXTRA_2ND = {}  # (N, M, D) -> seconds the 2nd neighbour adds to one sweep, measured once per shape
 
-    The reference times find_nn twice and reports the difference; the same
-    bookkeeping is kept (both sweeps are timed on the device) so that
-    `model_time` keeps its meaning (FR.py:117).
-    """
+
+def find_2nn_dev(fcgf_feats0, fcgf_feats1):
+    """find_2nn with everything left in HBM: (idx1, idx1_2nd) int64 CUDA tensors + the extra seconds.
+
+    The reference runs find_nn twice and charges `model_time` the difference (matching.py:6-19, FR.py:117).
+    Here ONE sweep delivers both neighbours; what the second one adds to it (the WANT2 variant of the sweep and
+    of the re-rank against the 1-NN variant) is measured on the device the first time a shape is seen -- two
+    extra sweeps, once -- and reused, so the steady state costs a single sweep and no host round trip."""
     f0, f1 = engine.to_dev_f32(fcgf_feats0), engine.to_dev_f32(fcgf_feats1)
-    _sync()
-    t0 = time()
-    engine.match_nn(f0, f1, want_2nd=False)
-    _sync()
-    simple = time() - t0
-    t0 = time()
+    key = (int(f0.shape[0]), int(f1.shape[0]), int(f0.shape[1]))
+    if key not in _EXTRA_2ND:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        engine.match_nn(f0, f1, want_2nd=True)  # warm-up (scratch allocation)
+        ev[0].record()
+        engine.match_nn(f0, f1, want_2nd=False)
+        ev[1].record()
+        engine.match_nn(f0, f1, want_2nd=True)
+        ev[2].record()
+        ev[2].synchronize()
+        _EXTRA_2ND[key] = max(0.0, (ev[1].elapsed_time(ev[2]) - ev[0].elapsed_time(ev[1])) * 1e-3)
     idx1, idx2 = engine.match_nn(f0, f1, want_2nd=True)
-    _sync()
-    extra = (time() - t0) - simple
+    return idx1, idx2, _EXTRA_2ND[key]
+
+
+def find_2nn(fcgf_feats0, fcgf_feats1):
+    """matching.py:6-19: NN + 2nd NN (int64 CPU tensors) and the *extra* seconds the 2nd NN costs
+    (see find_2nn_dev for how that figure is obtained without running the sweep twice per call)."""
+    idx1, idx2, extra = find_2nn_dev(fcgf_feats0, fcgf_feats1)
     N = idx1.shape[0]
     return torch.arange(N).long().squeeze(), idx1.cpu(), idx2.cpu(), extra
+
+
+def nn_to_mutual_dev(feats0, feats1, idx1, idx1_2nd=None):
+    """nn_to_mutual on device tensors: (idx0'[K], idx1'[K], idx1_2nd'[K] | None), sorted by idx0; one 8-byte
+    read-back (K) is the only host round trip."""
+    out_i, out_j = engine.match_mutual(feats0, feats1, idx1)
+    return out_i, out_j, (idx1_2nd[out_i] if idx1_2nd is not None else None)
+
+
+def measure_inlier_ratio_dev(idx0, idx1, xyz0_d, xyz1_d, T_gt, voxel_size):
+    """measure_inlier_ratio (matching.py:241-249) on device tensors, fp64 like the reference's numpy."""
+    if idx0.shape[0] == 0:
+        return float("nan")  # 0 / 0 in the reference
+    T = torch.as_tensor(np.asarray(T_gt, dtype=np.float64), device=xyz0_d.device)
+    p = xyz0_d[idx0].double() @ T[:3, :3].T + T[:3, 3]
+    d2 = ((p - xyz1_d[idx1].double()) ** 2).sum(dim=1)
+    return float((d2 < (2 * voxel_size) ** 2).double().mean().item())
 
 
 def torch_intersect(Na, Nb, i_ab, j_ab, i_ba, j_ba):

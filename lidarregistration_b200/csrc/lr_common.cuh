@@ -40,11 +40,13 @@ enum Slot { SLOT_RANSAC = 0, SLOT_MATCH = 1, SLOT_MISC = 2, SLOT_RANSAC_B = 3, S
 struct Arena {
     void *ptr = nullptr;
     size_t cap = 0;
+    uint64_t gen = 0;  // bumped whenever the block is (re)allocated or released: cached contents are gone
 };
 
 // returns nullptr (and sets the error) on failure
 void *arena_get(int slot, size_t bytes);
 void arena_release_all();
+uint64_t arena_gen(int slot);
 int sm_count();
 
 struct Lock {

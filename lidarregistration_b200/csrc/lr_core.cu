@@ -46,8 +46,16 @@ void *arena_get(int slot, size_t bytes)
             return nullptr;
         }
         a.cap = want;
+        ++a.gen;
     }
     return a.ptr;
+}
+
+uint64_t arena_gen(int slot)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 0;
+    return g_arena[dev][slot].gen;
 }
 
 void arena_release_all()
@@ -59,7 +67,9 @@ void arena_release_all()
             if (g_arena[d][s].ptr) {
                 cudaSetDevice(d);
                 cudaFree(g_arena[d][s].ptr);
+                const uint64_t gen = g_arena[d][s].gen + 1;
                 g_arena[d][s] = Arena();
+                g_arena[d][s].gen = gen;
             }
     cudaSetDevice(cur);
 }
@@ -80,7 +90,7 @@ int sm_count()
 
 LR_EXPORT const char *lr_last_error(void) { return lr::g_err; }
 
-LR_EXPORT int lr_version(void) { return 110; }  // 110: LrRansacParams / LrRansacStats grew the LR_SCORE_MSAC fields
+LR_EXPORT int lr_version(void) { return 120; }  // 120: lr_comm_*, lr_ransac_rigid_sharded, lr_ransac_tc_probe
 
 LR_EXPORT int lr_device_info(int *sms, int *major, int *minor)
 {

@@ -21,6 +21,7 @@
 //   k_resolve / k_round_end  packed (count, id) arg-max, confidence exit flag
 // fp64 arithmetic follows oracle/lr_oracle.c operation for operation (this
 // file is compiled with -fmad=false; FMAs are written explicitly where wanted).
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <vector>
@@ -37,7 +38,8 @@ constexpr int kGroup = 4;           // points whose first residual component is 
 constexpr int kBlock = 32;          // points between two checks of the "some residual is in the band" flag
 constexpr int kGenThreads = 128;
 constexpr int kGcMaxTrials = 64;    // inner LO draws scored by one launch
-int g_score_mode = 0;               // lr_ransac_set_mode: 0 = sweep with the first-component early-out, 1 = without (A/B)
+int g_score_mode = 0;               // lr_ransac_set_mode: 0 = tensor-core sweep, 1 = fp32 sweep in full, 2 = fp32 sweep with
+                                    // the first-component early-out (A/B)
 
 struct Ctl {
     unsigned long long best_key;   // over finished rounds
@@ -48,11 +50,14 @@ struct Ctl {
     int pad0;
     long long iters_run, n_scored, n_rechecked;
     unsigned int p1max_bits, qmax_bits;  // max |p|_1, max |q|_inf as float bits
+    unsigned int pt2max_bits, qtmax_bits;  // max |p - c|_2, max |q - c'|_inf (lr_score_tc.cuh: operand frame)
     long long refit_count;
     double T[12], Tref[12];
     double csum[6];
     double H[9];
     double err2;  // sum of squared residuals over the inliers (ICP rmse)
+    unsigned int ticket_end, ticket_fin;  // "last block finishes" counters of k_resolve_end / k_finish
+    int comm_error, pad1;                 // hypothesis sharding: a peer did not answer in time
     // LR_SCORE_MSAC runs only (lr_ransac_gc.cuh); q = quantised MSAC score (include/lidarreg.h)
     struct Gc {
         unsigned long long round_q;     // highest q of the current round
@@ -81,6 +86,11 @@ struct Ws {
     uint32_t *growth; // PROSAC growth function T'_n (null unless the sampler is PROSAC)
     double *scratchT; // 16 doubles of staging
     int64_t n_pad;
+    // tensor-core sweep (lr_score_tc.cuh)
+    uint4 *Aimg;      // fp16 operand image of the surviving hypotheses, 12 KB per 128 slots
+    uint4 *Bimg;      // fp16 operand image of the correspondences, 64 B each
+    float *band;      // per slot: half-width of the r^2 band that is decided in fp64
+    double *partial;  // k_finish: kFinBlocksMax x kFinVals per-block sums
     // LR_SCORE_MSAC runs only (null otherwise)
     unsigned long long *q64;  // per slot: quantised MSAC score
     int32_t *lo_L;            // inlier index list of the current LO round, ascending
@@ -355,6 +365,47 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+// one sampled correspondence = one 32-byte sector of the packed copy (the [n,3] arrays cost 2-4 sectors)
+__device__ __forceinline__ void load_pq(const float4 *__restrict__ P8, int64_t k, double (&P)[3], double (&Q)[3])
+{
+    const float4 a = __ldg(P8 + 2 * k), b = __ldg(P8 + 2 * k + 1);
+    P[0] = (double)a.x, P[1] = (double)a.y, P[2] = (double)a.z;
+    Q[0] = (double)a.w, Q[1] = (double)b.x, Q[2] = (double)b.y;
+}
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ void upk2(u64 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// same instruction, but `volatile`: ptxas keeps these in source order, which is written so that
+// three consecutive FMAs share their B operand (register-reuse cache; tools/micro_ffma2.cu:
+// 100 instead of 87 FMA/clk/SM)
+__device__ __forceinline__ u64 fma2v(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+#include "lr_score_tc.cuh"
+
 // ------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------
@@ -365,10 +416,12 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // far-away points that can never be inliers.  Also the coordinate bound that
 // enters the fp32 error band.
 __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, int64_t n_pad,
-                       float4 *__restrict__ P12, float4 *__restrict__ P8, Ctl *ctl)
+                       float4 *__restrict__ P12, float4 *__restrict__ P8, uint4 *__restrict__ Bimg, Ctl *ctl)
 {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    float p1 = 0.f;
+    float p1 = 0.f, pt2 = 0.f, qt = 0.f;
+    double c[3] = {0, 0, 0}, cq[3] = {0, 0, 0};
+    if (n > 0) tcs::tc_centre6(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(tgt), __ldg(tgt + 1), __ldg(tgt + 2), c, cq);
     if (i < n) {
         float px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
         float qx = tgt[3 * i], qy = tgt[3 * i + 1], qz = tgt[3 * i + 2];
@@ -378,15 +431,32 @@ __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ 
         P8[2 * i + 0] = make_float4(px, py, pz, qx);
         P8[2 * i + 1] = make_float4(qy, qz, 0.f, 0.f);
         p1 = fabsf(px) + fabsf(py) + fabsf(pz);
+        // the tensor-core sweep's operand image, in the frame (c, c'): differences of fp32 values are exact in fp64
+        const double pt[3] = {(double)px - c[0], (double)py - c[1], (double)pz - c[2]};
+        const double qq[3] = {(double)qx - cq[0], (double)qy - cq[1], (double)qz - cq[2]};
+        tcs::tc_write_corr(Bimg, i, pt, qq);
+        pt2 = __double2float_ru(sqrt((pt[0] * pt[0] + pt[1] * pt[1]) + pt[2] * pt[2])) * 1.000001f;
+        qt = __double2float_ru(fmax(fabs(qq[0]), fmax(fabs(qq[1]), fabs(qq[2]))));
     } else if (i < n_pad) {
         P12[3 * i + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
         P12[3 * i + 1] = make_float4(0.f, 0.f, -1e18f, -1e18f);
         P12[3 * i + 2] = make_float4(-1e18f, -1e18f, -1e18f, -1e18f);
+        // padding: 60 km away from wherever a model can send the origin (|t~| <= 2 x tcs::kRangeLimit)
+        const double pt[3] = {0.0, 0.0, 0.0}, qq[3] = {60000.0, 60000.0, 60000.0};
+        tcs::tc_write_corr(Bimg, i, pt, qq);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) p1 = fmaxf(p1, __shfl_xor_sync(0xffffffffu, p1, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        p1 = fmaxf(p1, __shfl_xor_sync(0xffffffffu, p1, o));
+        pt2 = fmaxf(pt2, __shfl_xor_sync(0xffffffffu, pt2, o));
+        qt = fmaxf(qt, __shfl_xor_sync(0xffffffffu, qt, o));
+    }
     // round up a little: the fp32 sum above is itself rounded
-    if ((threadIdx.x & 31) == 0) atomicMax(&ctl->p1max_bits, __float_as_uint(p1 * 1.000001f));
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&ctl->p1max_bits, __float_as_uint(p1 * 1.000001f));
+        atomicMax(&ctl->pt2max_bits, __float_as_uint(pt2));
+        atomicMax(&ctl->qtmax_bits, __float_as_uint(qt));
+    }
 }
 
 __global__ void k_ctl_reset(Ctl *ctl)
@@ -402,6 +472,10 @@ __global__ void k_ctl_reset(Ctl *ctl)
         ctl->n_rechecked = 0;
         ctl->p1max_bits = 0u;
         ctl->qmax_bits = 0u;
+        ctl->pt2max_bits = 0u;
+        ctl->qtmax_bits = 0u;
+        ctl->ticket_end = ctl->ticket_fin = 0u;
+        ctl->comm_error = 0;
         ctl->refit_count = 0;
         ctl->gc.round_q = ctl->gc.best_q = ctl->gc.cur_q = ctl->gc.lo_q = 0ULL;
         ctl->gc.round_pick = ~0ULL;
@@ -447,14 +521,6 @@ __device__ __forceinline__ bool elc_pass_fast(const double (&P)[M][3], const dou
         }
     if (ok && unsure) ok = elc_pass<M>(P, Q, ratio);
     return ok;
-}
-
-// one sampled correspondence = one 32-byte sector of the packed copy (the [n,3] arrays cost 2-4 sectors)
-__device__ __forceinline__ void load_pq(const float4 *__restrict__ P8, int64_t k, double (&P)[3], double (&Q)[3])
-{
-    const float4 a = __ldg(P8 + 2 * k), b = __ldg(P8 + 2 * k + 1);
-    P[0] = (double)a.x, P[1] = (double)a.y, P[2] = (double)a.z;
-    Q[0] = (double)a.w, Q[1] = (double)b.x, Q[2] = (double)b.y;
 }
 
 // one thread per hypothesis id: counter-based sample -> ELC; survivors are
@@ -514,10 +580,13 @@ template <int M>
 __global__ void __launch_bounds__(kGenThreads)
 k_kabsch(const float4 *__restrict__ P8, double thr2, Ctl *ctl,
          const int32_t *__restrict__ samp, float4 *__restrict__ m32, double *__restrict__ m64,
-         int *__restrict__ cnt)
+         int *__restrict__ cnt, uint4 *__restrict__ Aimg, float *__restrict__ band)
 {
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
+    double cen[3], cenq[3];
+    tcs::tc_centre(P8, cen, cenq);
+    const double P2 = (double)__uint_as_float(ctl->pt2max_bits), Qt = (double)__uint_as_float(ctl->qtmax_bits);
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
         double P[M][3], Q[M][3], T[12];
 #pragma unroll
@@ -536,6 +605,16 @@ k_kabsch(const float4 *__restrict__ P8, double thr2, Ctl *ctl,
         double delta = 4.0 * E * thr + 4.0 * E * E + 8.0 * u * thr2 + 1e-9;
         float lo = __double2float_rd(thr2 - delta);
         float hi = __double2float_ru(thr2 + delta);
+        if (Aimg) {
+            // tensor-core sweep: the model in the operand frame, t~ = t + R c - c', and the band its error bound gives
+            double tt[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                tt[a] = (T[4 * a + 3] + ((T[4 * a] * cen[0] + T[4 * a + 1] * cen[1]) + T[4 * a + 2] * cen[2])) - cenq[a];
+            tcs::tc_write_model(Aimg, slot, T, tt);
+            const double Et = tcs::tc_err_bound(P2, Qt, fmax(fabs(tt[0]), fmax(fabs(tt[1]), fabs(tt[2]))));
+            band[slot] = __double2float_ru(4.0 * Et * thr + 4.0 * Et * Et + 8.0 * u * thr2 + 1e-9);
+        }
         float *mf = reinterpret_cast<float *>(m32);
 #pragma unroll
         for (int k = 0; k < 12; ++k) mf[m32_index(slot, k)] = (float)T[k];
@@ -565,37 +644,6 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
-}
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ void upk2(u64 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
-{
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-// same instruction, but `volatile`: ptxas keeps these in source order, which is written so that
-// three consecutive FMAs share their B operand (register-reuse cache; tools/micro_ffma2.cu:
-// 100 instead of 87 FMA/clk/SM)
-__device__ __forceinline__ u64 fma2v(u64 a, u64 b, u64 c)
-{
-    u64 d;
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b)
-{
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b)
-{
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
 }
 
 // cl += (r < lo); ch += (r < hi)  as two FSETP + two predicated IADD
@@ -852,6 +900,161 @@ __global__ void k_round_end(Ctl *ctl, int64_t round_len, const int *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------
+// hypothesis sharding over NVLink peer memory: every rank owns a mailbox that its peers write
+// into directly (cudaIpc-mapped device memory, lr_comm_init / lr_comm_connect); the exchange of a round's
+// packed (count, id) key is part of the kernel that ends the round -- no host round trip, no separate collective
+// ------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+struct Mail {
+    unsigned long long key;  // packed (count + 1) << 32 | ~id of the sender's slice of the round
+    unsigned long long aux;  // survivors the sender scored in the round
+    unsigned long long seq;  // exchange number the entry belongs to (written last, release)
+    unsigned long long pad;
+};
+struct Comm {
+    int rank, world;
+    unsigned long long epoch;  // exchanges completed (identical on every rank: the calls are collective)
+    int error, pad;
+    Mail *peer[kMaxRanks];     // peer[g] = rank g's mailbox [2][kMaxRanks] (parity of the exchange, sender)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// one warp: all-gather of (key, aux) through the peers' mailboxes, MAX / SUM reduced; every rank gets the same
+__device__ __forceinline__ void comm_exchange(Comm *cm, unsigned long long &key, unsigned long long &aux, int &err)
+{
+    const int lane = threadIdx.x & 31;
+    const int G = cm->world, me = cm->rank;
+    const unsigned long long ep = cm->epoch + 1;
+    unsigned long long k = 0ULL, a = 0ULL;
+    int bad = 0;
+    if (lane < G) {
+        Mail *dst = cm->peer[lane] + (size_t)(ep & 1ULL) * kMaxRanks + me;
+        st_relaxed_sys(&dst->key, key);
+        st_relaxed_sys(&dst->aux, aux);
+        __threadfence_system();
+        st_release_sys(&dst->seq, ep);
+        const Mail *src = cm->peer[me] + (size_t)(ep & 1ULL) * kMaxRanks + lane;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&src->seq) != ep) {
+            if (clock64() - t0 > 6000000000LL) {  // ~3 s: a rank is missing; give up instead of hanging the GPU
+                bad = 1;
+                break;
+            }
+        }
+        k = ld_acquire_sys(&src->key);
+        a = ld_acquire_sys(&src->aux);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    k = warp_max_u64(k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    __syncwarp();
+    if (lane == 0) {
+        cm->epoch = ep;
+        if (bad) cm->error = 1;
+    }
+    key = k;
+    aux = a;
+    err = bad;
+}
+
+struct EndArgs {
+    int64_t round_len;     // hypotheses of the whole round (all ranks together)
+    const int *need;       // confidence exit table (nullable)
+    int round_idx;
+    int is_last;           // last enqueued round: the selected model is materialised in ctl->T
+    Comm *comm;            // hypothesis sharding: exchange the round's key with the peers (nullable)
+    uint64_t seed;
+    int sampler;
+    int64_t n;
+    const uint32_t *growth;
+    const float4 *P8;
+};
+
+// key -> fp64 model of the selected hypothesis (identity when none / zero inliers), sample read from the packed records
+template <int M>
+__device__ void model_from_key(unsigned long long key, const EndArgs &a, double (&T)[12])
+{
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    const long long cnt = (long long)(key >> 32) - 1;
+    if (key != 0ULL && cnt > 0) {
+        const uint64_t id = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFULL));
+        int32_t s[M];
+        sample_ids<M>(a.seed, id, a.sampler, a.n, a.growth, s);
+        double P[M][3], Q[M][3];
+#pragma unroll
+        for (int d = 0; d < M; ++d) load_pq(a.P8, (int64_t)s[d], P[d], Q[d]);
+        kabsch_small<M>(P, Q, T);
+    }
+}
+
+// k_resolve + k_round_end (+ the peer exchange + the winner's model) in one launch: the last block to finish
+// (ticket) ends the round.  Used by the count-scoring runs; the fed-sample hook keeps the two-kernel form.
+template <int M>
+__global__ void __launch_bounds__(256)
+k_resolve_end(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restrict__ cnt, EndArgs a)
+{
+    if (ctl->done) return;
+    const int nsurv = ctl->n_surv;
+    unsigned long long key = 0ULL;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
+        const unsigned long long k = make_key(cnt[slot], slot_id[slot]);
+        key = k > key ? k : key;
+    }
+    key = warp_max_u64(key);
+    if ((threadIdx.x & 31) == 0 && key) atomicMax(&ctl->round_key, key);
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket_end, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    unsigned long long rkey = __ldcg(&ctl->round_key);
+    unsigned long long scored = (unsigned long long)nsurv;
+    int err = 0;
+    if (a.comm) comm_exchange(a.comm, rkey, scored, err);
+    if (threadIdx.x != 0) return;
+    ctl->ticket_end = 0u;
+    if (err) ctl->comm_error = 1;
+    unsigned long long best = ctl->best_key;
+    if (rkey > best) best = rkey;
+    ctl->best_key = best;
+    ctl->iters_run += a.round_len;
+    ctl->n_scored += (long long)scored;
+    ctl->round_key = 0ULL;
+    ctl->n_surv = 0;
+    ctl->n_flag = 0;
+    int done = err;
+    if (a.need) {
+        const long long c = (long long)(best >> 32) - 1;
+        if (best != 0ULL && c >= (long long)a.need[a.round_idx]) done = 1;
+    }
+    if (done) ctl->done = 1;
+    if (done || a.is_last) {
+        double T[12];
+        model_from_key<M>(best, a, T);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ctl->T[k] = T[k];
+    }
+}
+
 // key -> model of the selected hypothesis (identity when none / zero inliers)
 template <int M>
 __global__ void k_model_from_key(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n,
@@ -1016,10 +1219,125 @@ __global__ void k_refit_solve(Ctl *ctl)
     for (int j = 0; j < 12; ++j) ctl->Tref[j] = T[j];
 }
 
+// Inlier mask of ctl->T, count, squared-error sum and the least-squares refit over the inliers in ONE launch
+// (FR.py:99-111): per-block partial sums of {1, r^2, p', q', q' p'^T} (coordinates relative to the first pair
+// rounded to 1024 m, so map-frame offsets do not cancel in the covariance), written to fixed slots; the last
+// block to finish (ticket) adds them in block order -- a fixed-order two-stage reduction, so T_refit is
+// bit-reproducible run to run -- and solves the Kabsch problem:  H = sum q' p'^T - (sum q')(sum p')^T / k.
+// `host_out` (nullable, pinned + mapped): the control block is written there by the same block, so the caller
+// needs no copy after the kernel, only the stream synchronisation.
+constexpr int kFinVals = 17;
+constexpr int kFinBlocksMax = 512;
+__global__ void __launch_bounds__(256)
+k_finish(const float *__restrict__ a, const float *__restrict__ b, const int64_t *__restrict__ ia,
+         const int64_t *__restrict__ ib, int64_t n, double thr2, Ctl *ctl, uint8_t *__restrict__ mask,
+         double *__restrict__ partial, int want_refit, Ctl *host_out)
+{
+    __shared__ double sh[8];
+    __shared__ int s_last;
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = ctl->T[k];
+    double o[3] = {0, 0, 0}, oq[3] = {0, 0, 0};
+    if (n > 0) {
+        double p0[3], q0[3];
+        fetch_pair(a, b, ia, ib, 0, p0, q0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            o[c] = 1024.0 * rint(p0[c] * (1.0 / 1024.0));
+            oq[c] = 1024.0 * rint(q0[c] * (1.0 / 1024.0));
+        }
+    }
+    double v[kFinVals];
+#pragma unroll
+    for (int k = 0; k < kFinVals; ++k) v[k] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double p[3], q[3];
+        fetch_pair(a, b, ia, ib, i, p, q);
+        const double r2 = res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]);
+        const bool in = r2 < thr2;
+        if (mask) mask[i] = in ? 1 : 0;
+        if (in) {
+            v[0] += 1.0;
+            v[1] += r2;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                p[c] -= o[c];
+                q[c] -= oq[c];
+                v[2 + c] += p[c];
+                v[5 + c] += q[c];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] += q[r] * p[c];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kFinVals; ++k) {
+        const double r = block_sum(v[k], sh);
+        if (threadIdx.x == 0) partial[(size_t)blockIdx.x * kFinVals + k] = r;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket_fin, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // second stage: thread t adds blocks t, t + 256, ... in order, then the fixed tree of block_sum
+    double tot[kFinVals];
+#pragma unroll
+    for (int k = 0; k < kFinVals; ++k) {
+        double x = 0.0;
+        for (int blk = threadIdx.x; blk < (int)gridDim.x; blk += blockDim.x) x += __ldcg(&partial[(size_t)blk * kFinVals + k]);
+        tot[k] = block_sum(x, sh);
+    }
+    if (threadIdx.x == 0) {
+        const long long k = (long long)(tot[0] + 0.5);
+        double Tr[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (k > 0 && want_refit) {
+            double H[3][3], R[3][3], cp[3], cq[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) H[r][c] = tot[8 + 3 * r + c] - tot[5 + r] * tot[2 + c] / (double)k;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                cp[c] = o[c] + tot[2 + c] / (double)k;
+                cq[c] = oq[c] + tot[5 + c] / (double)k;
+            }
+            rot_from_H(H, R);
+            finish_T(R, cp, cq, Tr);
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) ctl->Tref[j] = Tr[j];
+        ctl->refit_count = k;
+        ctl->err2 = tot[1];
+        ctl->ticket_fin = 0u;
+        __threadfence();
+    }
+    __syncthreads();
+    if (host_out) {
+        const unsigned long long *srcw = reinterpret_cast<const unsigned long long *>(ctl);
+        unsigned long long *dstw = reinterpret_cast<unsigned long long *>(host_out);
+        for (int w = threadIdx.x; w < (int)(sizeof(Ctl) / 8); w += blockDim.x) dstw[w] = __ldcg(srcw + w);
+        __threadfence_system();
+    }
+}
+
+__global__ void k_set_identity(Ctl *ctl)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int k = 0; k < 12; ++k) ctl->T[k] = (k % 5 == 0) ? 1.0 : 0.0;
+}
+
 __global__ void k_set_T(Ctl *ctl, const double *T12)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     for (int k = 0; k < 12; ++k) ctl->T[k] = T12[k];
+    ctl->ticket_fin = 0u;  // (these entries run on a bare control block: no k_ctl_reset before them)
+    ctl->comm_error = 0;
+    ctl->gc.mode = 0;
     ctl->refit_count = 0;
     ctl->err2 = 0.0;
     for (int k = 0; k < 6; ++k) ctl->csum[k] = 0.0;
@@ -1068,6 +1386,21 @@ __global__ void k_scatter_models(const Ctl *ctl, const uint32_t *slot_id, const 
 // host side
 // ------------------------------------------------------------------------
 
+// PROSAC growth function T'_n (same expressions as the oracle's lro_prosac_growth).  The table is a
+// function of (N, m) only: the host copy is cached, and the upload is skipped while the device copy of the same
+// table still sits at the same address of the same arena block (a run of same-sized PROSAC pairs uploads once).
+struct GrowthCache {
+    std::vector<uint32_t> host;
+    int64_t N = -1;
+    int m = 0;
+    const void *dev[lr::SLOT_COUNT] = {nullptr, nullptr, nullptr, nullptr};   // where the cached table was uploaded last
+    int64_t devN[lr::SLOT_COUNT] = {-1, -1, -1, -1};
+    int devm[lr::SLOT_COUNT] = {0, 0, 0, 0};
+    // signature of the layout ws_setup carved last in each arena slot: any other layout may overwrite the table
+    int64_t sig[lr::SLOT_COUNT][7] = {};
+};
+GrowthCache g_growth[64];
+
 int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false, int slot = lr::SLOT_RANSAC,
              bool gc = false)
 {
@@ -1080,13 +1413,27 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
                    lr::padded(sizeof(int32_t) * 4 * slots) + lr::padded(sizeof(uint32_t) * slots) +
                    lr::padded(sizeof(float4) * 4 * slots) + lr::padded(sizeof(double) * 12 * slots) +
                    lr::padded(sizeof(int) * slots) + lr::padded(sizeof(int) * (nrounds + 1)) +
-                   lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1));
+                   lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1)) +
+                   lr::padded((size_t)((slots + tcs::TM - 1) / tcs::TM) * tcs::A_BLOCK_BYTES) +
+                   lr::padded((size_t)ws.n_pad * 64) + lr::padded(sizeof(float) * slots) +
+                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals);
     if (gc)
         bytes += lr::padded(sizeof(unsigned long long) * slots) + lr::padded(sizeof(int32_t) * (n > 0 ? n : 1)) +
                  lr::padded(sizeof(double) * 12 * kGcMaxTrials) + lr::padded(sizeof(unsigned long long) * kGcMaxTrials) +
                  lr::padded(sizeof(int) * kGcMaxTrials);
     void *base = lr::arena_get(slot, bytes);
     if (!base) return LR_ERR_ALLOC;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+            const int64_t sig[7] = {n, round, nrounds, (int64_t)prosac, (int64_t)gc, (int64_t)(uintptr_t)base,
+                                    (int64_t)lr::arena_gen(slot)};
+            if (memcmp(sig, g_growth[dev].sig[slot], sizeof(sig)) != 0) {
+                memcpy(g_growth[dev].sig[slot], sig, sizeof(sig));
+                g_growth[dev].dev[slot] = nullptr;
+            }
+        }
+    }
     lr::Carver cv(base);
     ws.ctl = cv.take<Ctl>(1);
     ws.P12 = cv.take<float4>(3 * ws.n_pad);
@@ -1100,6 +1447,10 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     ws.scratchT = cv.take<double>(16);
     ws.growth = prosac ? cv.take<uint32_t>(n) : cv.take<uint32_t>(1);
     if (!prosac) ws.growth = nullptr;
+    ws.Aimg = reinterpret_cast<uint4 *>(cv.take<char>((size_t)((slots + tcs::TM - 1) / tcs::TM) * tcs::A_BLOCK_BYTES));
+    ws.Bimg = reinterpret_cast<uint4 *>(cv.take<char>((size_t)ws.n_pad * 64));
+    ws.band = cv.take<float>(slots);
+    ws.partial = cv.take<double>((size_t)kFinBlocksMax * kFinVals);
     ws.q64 = gc ? cv.take<unsigned long long>(slots) : nullptr;
     ws.lo_L = gc ? cv.take<int32_t>(n > 0 ? n : 1) : nullptr;
     ws.tr_T = gc ? cv.take<double>(12 * kGcMaxTrials) : nullptr;
@@ -1132,37 +1483,66 @@ int64_t batch_len(int64_t total)
     return total < 1 ? 1 : (total < cap ? total : cap);
 }
 
-// PROSAC growth function T'_n (same expressions as the oracle's lro_prosac_growth)
-int upload_growth(const Ws &ws, int64_t N, int m, cudaStream_t st)
+int upload_growth(const Ws &ws, int64_t N, int m, cudaStream_t st, int slot = lr::SLOT_RANSAC)
 {
     if (!ws.growth) return LR_OK;
-    std::vector<uint32_t> g((size_t)N);
-    double T_n = (double)kProsacTN;
-    for (int i = 0; i < m; ++i) T_n *= (double)(m - i) / (double)(N - i);
-    uint32_t T_prime = 1;
-    for (int64_t i = 0; i < N; ++i) {
-        if (i + 1 <= m) {
-            g[i] = T_prime;
-            continue;
+    int dev = 0;
+    LR_CUDA_TRY(cudaGetDevice(&dev));
+    LR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    GrowthCache &gc = g_growth[dev];
+    if (gc.N != N || gc.m != m) {
+        gc.host.resize((size_t)N);
+        std::vector<uint32_t> &g = gc.host;
+        double T_n = (double)kProsacTN;
+        for (int i = 0; i < m; ++i) T_n *= (double)(m - i) / (double)(N - i);
+        uint32_t T_prime = 1;
+        for (int64_t i = 0; i < N; ++i) {
+            if (i + 1 <= m) {
+                g[i] = T_prime;
+                continue;
+            }
+            double T_next = (double)(i + 1) * T_n / (double)(i + 1 - m);
+            double inc = ceil(T_next - T_n);
+            if (!(inc < 4.0e9)) inc = 4.0e9;
+            uint64_t v = (uint64_t)T_prime + (uint64_t)inc;
+            g[i] = v > 0xFFFFFFF0ULL ? 0xFFFFFFF0U : (uint32_t)v;
+            T_n = T_next;
+            T_prime = g[i];
         }
-        double T_next = (double)(i + 1) * T_n / (double)(i + 1 - m);
-        double inc = ceil(T_next - T_n);
-        if (!(inc < 4.0e9)) inc = 4.0e9;
-        uint64_t v = (uint64_t)T_prime + (uint64_t)inc;
-        g[i] = v > 0xFFFFFFF0ULL ? 0xFFFFFFF0U : (uint32_t)v;
-        T_n = T_next;
-        T_prime = g[i];
+        gc.N = N;
+        gc.m = m;
+        for (int k = 0; k < lr::SLOT_COUNT; ++k) gc.dev[k] = nullptr;
     }
-    LR_CUDA_TRY(cudaMemcpyAsync(ws.growth, g.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
-    LR_CUDA_TRY(cudaStreamSynchronize(st));  // g is a local
+    if (gc.dev[slot] == (const void *)ws.growth && gc.devN[slot] == N && gc.devm[slot] == m) return LR_OK;
+    // pageable source: the runtime stages it before returning; no stream synchronisation needed
+    LR_CUDA_TRY(cudaMemcpyAsync(ws.growth, gc.host.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+    gc.dev[slot] = ws.growth;
+    gc.devN[slot] = N;
+    gc.devm[slot] = m;
     return LR_OK;
+}
+
+// opt the tensor sweep's kernels into their dynamic shared memory once per device
+cudaError_t tc_smem_attr()
+{
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(tcs::k_score_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcs::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tcs::k_score_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcs::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    done[dev] = true;
+    return cudaSuccess;
 }
 
 int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cudaStream_t st)
 {
     k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
     int blocks = (int)((ws.n_pad + 255) / 256);
-    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.ctl);
+    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.Bimg, ws.ctl);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1170,39 +1550,58 @@ int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cud
 #include "lr_ransac_gc.cuh"
 
 // one round: ids [lo, hi) (or H fed samples), leaves the result in ctl->round_key (LR_SCORE_MSAC:
-// ctl->gc.round_q / round_pick; counts_out then receives #(r^2 < tau^2) and scores_out the q values)
+// ctl->gc.round_q / round_pick; counts_out then receives #(r^2 < tau^2) and scores_out the q values).
+// With `end` (count scoring) the round is also closed by the same launch sequence: k_resolve_end.
 int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int64_t lo,
-                 int64_t hi, const int32_t *fed, int32_t *counts_out, cudaStream_t st, int64_t *scores_out = nullptr)
+                 int64_t hi, const int32_t *fed, int32_t *counts_out, cudaStream_t st, int64_t *scores_out = nullptr,
+                 const EndArgs *end = nullptr)
 {
     const int64_t len = hi - lo;
-    if (len <= 0) return LR_OK;
+    if (len <= 0 && !end) return LR_OK;
     const double thr2 = p.threshold * p.threshold;
     const int sms = lr::sm_count();
-    int gblocks = (int)((len + kGenThreads - 1) / kGenThreads);
-    int kblocks = gblocks < sms * 8 ? gblocks : sms * 8;
-    int tok = lr::prof_begin(lr::PROF_GEN, st);
-    if (p.sample_size == 3) {
-        k_gen<3><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
-                                                  ws.growth, ws.ctl, ws.slot_id, ws.samp);
-        k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
-    } else {
-        k_gen<4><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
-                                                  ws.growth, ws.ctl, ws.slot_id, ws.samp);
-        k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt);
+    if (len > 0) {
+        int gblocks = (int)((len + kGenThreads - 1) / kGenThreads);
+        int kblocks = gblocks < sms * 8 ? gblocks : sms * 8;
+        // the tensor-core sweep serves count scoring; its operand image is only built when it will run
+        const bool use_tc = p.scoring == LR_SCORE_COUNT && g_score_mode == 0;
+        uint4 *aimg = use_tc ? ws.Aimg : nullptr;
+        int tok = lr::prof_begin(lr::PROF_GEN, st);
+        if (p.sample_size == 3) {
+            k_gen<3><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
+                                                      ws.growth, ws.ctl, ws.slot_id, ws.samp);
+            k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt, aimg, ws.band);
+        } else {
+            k_gen<4><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
+                                                      ws.growth, ws.ctl, ws.slot_id, ws.samp);
+            k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt, aimg, ws.band);
+        }
+        lr::prof_end(tok, st);
+        if (p.scoring == LR_SCORE_MSAC) return gc_launch_score(src, tgt, n, p, ws, lo, len, scores_out, counts_out, st);
+        tok = lr::prof_begin(lr::PROF_SCORE, st);
+        if (use_tc) {
+            // persistent CTAs, one per SM (TMEM: 4 x 96 accumulator columns; 57 KB of operand staging)
+            LR_CUDA_TRY(tc_smem_attr());
+            tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl,
+                                                                                 ws.m64, ws.band, ws.cnt, thr2, nullptr);
+        } else if (g_score_mode == 2) {
+            // fp32 sweep: 16 resident one-warp CTAs per SM (128 registers per thread fill the register file; 12 KB of
+            // staging each): no CTA-level barrier couples warps whose early-out rates differ
+            k_score<true><<<sms * 16, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
+        } else {
+            k_score<false><<<sms * 16, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
+        }
+        lr::prof_end(tok, st);
     }
-    lr::prof_end(tok, st);
-    if (p.scoring == LR_SCORE_MSAC) return gc_launch_score(src, tgt, n, p, ws, lo, len, scores_out, counts_out, st);
-    tok = lr::prof_begin(lr::PROF_SCORE, st);
-    // 16 resident one-warp CTAs per SM (128 registers per thread fill the register file; 12 KB of staging each):
-    // no CTA-level barrier couples warps whose early-out rates differ
-    if (g_score_mode == 0)
-        k_score<true><<<sms * 16, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
-    else
-        k_score<false><<<sms * 16, kScoreThreads, 0, st>>>(ws.P12, ws.n_pad, ws.ctl, ws.m32, ws.m64, ws.cnt, thr2);
-    lr::prof_end(tok, st);
     int rblocks = (int)((len + 255) / 256);
-    if (rblocks > sms * 4) rblocks = sms * 4;
-    k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, counts_out, lo);
+    if (rblocks > sms * 2) rblocks = sms * 2;
+    if (rblocks < 1) rblocks = 1;
+    if (end) {
+        if (p.sample_size == 3) k_resolve_end<3><<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, *end);
+        else k_resolve_end<4><<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, *end);
+    } else {
+        k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, counts_out, lo);
+    }
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1220,30 +1619,39 @@ void identity16(double *T)
     for (int k = 0; k < 16; ++k) T[k] = (k % 5 == 0) ? 1.0 : 0.0;
 }
 
-// model from key + mask + refit (launches only)
-int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
-                  uint64_t key, bool want_refit, uint8_t *mask, bool want_stats, cudaStream_t st, bool packed = true)
+int finish_blocks(int64_t n)
+{
+    int64_t blocks = (n + 255) / 256;
+    const int cap = lr::sm_count() * 3 < kFinBlocksMax ? lr::sm_count() * 3 : kFinBlocksMax;
+    if (blocks > cap) blocks = cap;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+// where the selected model comes from when a run is finished
+enum FinHow {
+    FIN_MODEL_READY = 0,  // count scoring through enqueue_run: k_resolve_end left it in ctl->T
+    FIN_GC = 1,           // LR_SCORE_MSAC: kept in ctl->gc
+    FIN_FROM_KEY = 2      // lr_ransac_finalize: decode the caller's key
+};
+
+// (model) + mask + refit + control block to `host_out` (pinned, nullable): launches only
+int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, FinHow how,
+                  uint64_t key, bool want_refit, uint8_t *mask, cudaStream_t st, bool packed, Ctl *host_out)
 {
     // after launch_pack the run's kernels read the packed device copy; src / tgt themselves (device or pinned
-    // host memory) are then only touched by k_pack and by the three-point k_model_from_key
+    // host memory) are then only touched by k_pack
     const float *fa = packed ? nullptr : src, *fb = packed ? reinterpret_cast<const float *>(ws.P8) : tgt;
     const double thr2 = p.threshold * p.threshold;
-    if (p.scoring == LR_SCORE_MSAC)
+    if (how == FIN_GC)
         k_gc_commit<<<1, 32, 0, st>>>(ws.ctl);  // the model was kept in ctl->gc, there is no key to decode
-    else if (p.sample_size == 3)
-        k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
-    else
-        k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, use_ctl_key, ws.ctl);
-    if (want_refit || mask || want_stats) {
-        int blocks = (int)((n + 255) / 256);
-        if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
-        if (blocks < 1) blocks = 1;
-        k_mask_sums<<<blocks, 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl, mask);
-        if (want_refit) {
-            k_refit_H<<<blocks, 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl);
-            k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
-        }
+    else if (how == FIN_FROM_KEY) {
+        if (p.sample_size == 3)
+            k_model_from_key<3><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, 0, ws.ctl);
+        else
+            k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, 0, ws.ctl);
     }
+    k_finish<<<finish_blocks(n), 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl, mask, ws.partial, want_refit ? 1 : 0,
+                                               host_out);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1283,23 +1691,83 @@ void finish_read(const Ctl &h, bool want_refit, double *T_out, double *T_refit, 
     }
 }
 
-// model from key + mask + refit + D2H
-int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, int use_ctl_key,
+// per device: two internal streams + pinned result staging (lr_ransac_rigid_batch), one pinned control block
+// for the single-run entries, and the hypothesis-sharding communicator
+struct CommHost {
+    bool ready = false;
+    int rank = 0, world = 1;
+    Comm *dev = nullptr;    // device copy handed to the kernels
+    Mail *box = nullptr;    // this rank's mailbox [2][kMaxRanks]
+    void *peer[kMaxRanks] = {};
+};
+struct BatchCtx {
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+    Ctl *host = nullptr;
+    int host_cap = 0;
+    Ctl *host1 = nullptr;
+    CommHost comm;
+};
+BatchCtx g_batch[64];
+
+int dev_ctx(BatchCtx **out)
+{
+    int dev = 0;
+    LR_CUDA_TRY(cudaGetDevice(&dev));
+    LR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    BatchCtx &c = g_batch[dev];
+    if (!c.host1) LR_CUDA_TRY(cudaMallocHost(&c.host1, sizeof(Ctl)));
+    *out = &c;
+    return LR_OK;
+}
+
+int batch_ctx(int count, BatchCtx **out)
+{
+    int rc = dev_ctx(out);
+    if (rc) return rc;
+    BatchCtx &c = **out;
+    if (!c.lane[0]) {
+        for (int l = 0; l < 2; ++l) {
+            LR_CUDA_TRY(cudaStreamCreateWithFlags(&c.lane[l], cudaStreamNonBlocking));
+            LR_CUDA_TRY(cudaEventCreateWithFlags(&c.done[l], cudaEventDisableTiming));
+        }
+        LR_CUDA_TRY(cudaEventCreateWithFlags(&c.start, cudaEventDisableTiming));
+    }
+    if (c.host_cap < count) {
+        if (c.host) cudaFreeHost(c.host);
+        c.host = nullptr;
+        c.host_cap = 0;
+        LR_CUDA_TRY(cudaMallocHost(&c.host, sizeof(Ctl) * (size_t)(count + 16)));
+        c.host_cap = count + 16;
+    }
+    return LR_OK;
+}
+
+// (model) + mask + refit, control block written into pinned host memory by the last kernel, one synchronisation
+int finish(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, const Ws &ws, FinHow how,
            uint64_t key, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st,
            bool packed = true)
 {
     const bool want_refit = (T_refit != nullptr) && p.refit;
-    int rc = finish_launch(src, tgt, n, p, ws, use_ctl_key, key, want_refit, mask, stats != nullptr, st, packed);
+    BatchCtx *ctx = nullptr;
+    int rc = dev_ctx(&ctx);
     if (rc) return rc;
-    Ctl h;
-    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    rc = finish_launch(src, tgt, n, p, ws, how, key, want_refit, mask, st, packed, ctx->host1);
+    if (rc) return rc;
     LR_CUDA_TRY(cudaStreamSynchronize(st));
-    finish_read(h, want_refit, T_out, T_refit, stats);
+    if (ctx->host1->comm_error) {
+        lr::set_error("hypothesis sharding: a peer rank did not answer the key exchange (timeout)");
+        return LR_ERR_CUDA;
+    }
+    finish_read(*ctx->host1, want_refit, T_out, T_refit, stats);
     return LR_OK;
 }
 
-// everything of one lr_ransac_rigid run up to (not including) the model read-back, enqueued on `st`
-int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, int slot, Ws &ws, cudaStream_t st)
+// everything of one run up to (not including) the mask / refit / read-back, enqueued on `st`.  With a
+// communicator (`world` > 1) this rank generates and scores only its contiguous slice of every round and the
+// round's packed key is exchanged with the peers inside k_resolve_end; every rank then holds the same selection.
+int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacParams &p, int slot, Ws &ws, cudaStream_t st,
+                Comm *comm = nullptr, int rank = 0, int world = 1)
 {
     // With the confidence exit the round length is part of the result's
     // definition (the exit is evaluated at round ends); with a fixed budget the
@@ -1311,7 +1779,7 @@ int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacPar
     const bool gc = p.scoring == LR_SCORE_MSAC;
     int rc = ws_setup(n, R, nrounds, ws, p.sampler == LR_SAMPLER_PROSAC, slot, gc);
     if (rc) return rc;
-    rc = upload_growth(ws, n, p.sample_size, st);
+    rc = upload_growth(ws, n, p.sample_size, st, slot);
     if (rc) return rc;
     rc = launch_pack(src, tgt, n, ws, st);
     if (rc) return rc;
@@ -1333,58 +1801,80 @@ int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacPar
         // pageable source: the runtime stages it before returning, `need` may go out of scope
         LR_CUDA_TRY(cudaMemcpyAsync(ws.need, need.data(), sizeof(int) * nrounds, cudaMemcpyHostToDevice, st));
     }
+    if (nrounds == 0 && !gc) {  // max_iters == 0: nothing is selected, the identity is the model
+        k_set_identity<<<1, 32, 0, st>>>(ws.ctl);
+    }
     for (int64_t r = 0; r < nrounds; ++r) {
         int64_t lo = r * R, hi = (r + 1) * R < p.max_iters ? (r + 1) * R : p.max_iters;
-        rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
-        if (rc) return rc;
-        if (gc)
+        if (gc) {
+            rc = launch_round(src, tgt, n, p, ws, lo, hi, nullptr, nullptr, st);
+            if (rc) return rc;
             k_round_end_msac<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, ws.m64, ws.cnt);
-        else
-            k_round_end<<<1, 32, 0, st>>>(ws.ctl, hi - lo, use_conf ? ws.need : nullptr, (int)r, nullptr);
+            continue;
+        }
+        EndArgs ea;
+        ea.round_len = hi - lo;
+        ea.need = use_conf ? ws.need : nullptr;
+        ea.round_idx = (int)r;
+        ea.is_last = r == nrounds - 1 ? 1 : 0;
+        ea.comm = world > 1 ? comm : nullptr;
+        ea.seed = p.seed;
+        ea.sampler = p.sampler;
+        ea.n = n;
+        ea.growth = ws.growth;
+        ea.P8 = ws.P8;
+        // this rank's contiguous slice of the round's ids
+        const int64_t a = lo + ((hi - lo) * rank) / world, b = lo + ((hi - lo) * (rank + 1)) / world;
+        rc = launch_round(src, tgt, n, p, ws, a, b, nullptr, nullptr, st, nullptr, &ea);
+        if (rc) return rc;
     }
     LR_CUDA_TRY(cudaGetLastError());
     if (gc) return gc_enqueue_polish(src, tgt, n, p, ws, st);
     return LR_OK;
 }
 
-// two internal streams + pinned staging for lr_ransac_rigid_batch, per device
-struct BatchCtx {
-    cudaStream_t lane[2] = {nullptr, nullptr};
-    cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
-    Ctl *host = nullptr;
-    int host_cap = 0;
-};
-BatchCtx g_batch[64];
-
-int batch_ctx(int count, BatchCtx **out)
+int identity_result(int64_t n, double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, cudaStream_t st)
 {
-    int dev = 0;
-    LR_CUDA_TRY(cudaGetDevice(&dev));
-    LR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
-    BatchCtx &c = g_batch[dev];
-    if (!c.lane[0]) {
-        for (int l = 0; l < 2; ++l) {
-            LR_CUDA_TRY(cudaStreamCreateWithFlags(&c.lane[l], cudaStreamNonBlocking));
-            LR_CUDA_TRY(cudaEventCreateWithFlags(&c.done[l], cudaEventDisableTiming));
-        }
-        LR_CUDA_TRY(cudaEventCreateWithFlags(&c.start, cudaEventDisableTiming));
-    }
-    if (c.host_cap < count) {
-        if (c.host) cudaFreeHost(c.host);
-        c.host = nullptr;
-        c.host_cap = 0;
-        LR_CUDA_TRY(cudaMallocHost(&c.host, sizeof(Ctl) * (size_t)(count + 16)));
-        c.host_cap = count + 16;
-    }
-    *out = &c;
+    identity16(T_out);
+    if (T_refit) identity16(T_refit);
+    if (mask && n > 0) LR_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)n, st));
+    if (stats) *stats = LrRansacStats{0, 0, 0, -1, -1, 0, 0, 0, 0, 0, 0};
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
     return LR_OK;
+}
+
+// one slot of the error-bound probe: the caller's fp64 model becomes survivor `h`
+__global__ void k_probe_install(const double *__restrict__ models, int H, const float4 *__restrict__ P8, double thr2,
+                                Ctl *ctl, double *__restrict__ m64, uint4 *__restrict__ Aimg, float *__restrict__ band,
+                                int *__restrict__ cnt, double *__restrict__ E_out)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h == 0) ctl->n_surv = H;
+    if (h >= H) return;
+    double cen[3], cenq[3], T[12], tt[3];
+    tcs::tc_centre(P8, cen, cenq);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        T[k] = models[(size_t)h * 12 + k];
+        m64[(size_t)h * 12 + k] = T[k];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        tt[a] = (T[4 * a + 3] + ((T[4 * a] * cen[0] + T[4 * a + 1] * cen[1]) + T[4 * a + 2] * cen[2])) - cenq[a];
+    tcs::tc_write_model(Aimg, h, T, tt);
+    const double Et = tcs::tc_err_bound((double)__uint_as_float(ctl->pt2max_bits), (double)__uint_as_float(ctl->qtmax_bits),
+                                        fmax(fabs(tt[0]), fmax(fabs(tt[1]), fabs(tt[2]))));
+    const double u = 5.9604644775390625e-08, thr = sqrt(thr2);
+    band[h] = __double2float_ru(4.0 * Et * thr + 4.0 * Et * Et + 8.0 * u * thr2 + 1e-9);
+    cnt[h] = 0;
+    if (E_out) E_out[h] = Et;
 }
 
 }  // namespace
 
 LR_EXPORT int lr_ransac_set_mode(int mode)
 {
-    LR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    LR_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
     g_score_mode = mode;
     return LR_OK;
 }
@@ -1412,18 +1902,145 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
     LR_REQUIRE(n == 0 || (src && tgt), "src/tgt is null");
     cudaStream_t st = (cudaStream_t)stream;
     const LrRansacParams &p = *params;
-    if (n < p.sample_size) {  // Open3D: |corres| < ransac_n -> identity (App. B)
-        identity16(T_out);
-        if (T_refit) identity16(T_refit);
-        if (mask && n > 0) LR_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)n, st));
-        if (stats) *stats = LrRansacStats{0, 0, 0, -1, -1, 0, 0, 0, 0, 0, 0};
-        LR_CUDA_TRY(cudaStreamSynchronize(st));
-        return LR_OK;
-    }
+    if (n < p.sample_size) return identity_result(n, T_out, T_refit, mask, stats, st);  // Open3D: |corres| < ransac_n (App. B)
     Ws ws;
     rc = enqueue_run(src, tgt, n, p, lr::SLOT_RANSAC, ws, st);
     if (rc) return rc;
-    return finish(src, tgt, n, p, ws, 1, 0, T_out, T_refit, mask, stats, st);
+    return finish(src, tgt, n, p, ws, p.scoring == LR_SCORE_MSAC ? FIN_GC : FIN_MODEL_READY, 0, T_out, T_refit, mask, stats, st);
+}
+
+// ---- hypothesis sharding with a library-owned communicator over NVLink peer memory --------------------------
+LR_EXPORT int lr_comm_init(int rank, int world, void *handle_out)
+{
+    lr::Lock lock;
+    LR_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "rank / world out of range (at most 16 ranks)");
+    LR_REQUIRE(handle_out != nullptr, "handle_out is null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI exchanges 64-byte handles");
+    BatchCtx *ctx = nullptr;
+    int rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    CommHost &c = ctx->comm;
+    LR_REQUIRE(!c.ready && !c.box, "communicator already initialised on this device (lr_comm_destroy first)");
+    LR_CUDA_TRY(cudaMalloc(&c.box, sizeof(Mail) * 2 * kMaxRanks));
+    LR_CUDA_TRY(cudaMemset(c.box, 0, sizeof(Mail) * 2 * kMaxRanks));
+    LR_CUDA_TRY(cudaMalloc(&c.dev, sizeof(Comm)));
+    c.rank = rank;
+    c.world = world;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (world > 1) LR_CUDA_TRY(cudaIpcGetMemHandle(&h, c.box));
+    memcpy(handle_out, &h, sizeof(h));
+    return LR_OK;
+}
+
+LR_EXPORT int lr_comm_connect(const void *all_handles)
+{
+    lr::Lock lock;
+    BatchCtx *ctx = nullptr;
+    int rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    CommHost &c = ctx->comm;
+    LR_REQUIRE(c.box && !c.ready, "lr_comm_init has not run on this device (or the communicator is already connected)");
+    LR_REQUIRE(all_handles != nullptr || c.world == 1, "all_handles is null");
+    Comm h;
+    memset(&h, 0, sizeof(h));
+    h.rank = c.rank;
+    h.world = c.world;
+    for (int g = 0; g < c.world; ++g) {
+        if (g == c.rank) {
+            c.peer[g] = c.box;
+        } else {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, reinterpret_cast<const char *>(all_handles) + 64 * (size_t)g, sizeof(hd));
+            LR_CUDA_TRY(cudaIpcOpenMemHandle(&c.peer[g], hd, cudaIpcMemLazyEnablePeerAccess));
+        }
+        h.peer[g] = reinterpret_cast<Mail *>(c.peer[g]);
+    }
+    LR_CUDA_TRY(cudaMemcpy(c.dev, &h, sizeof(h), cudaMemcpyHostToDevice));
+    LR_CUDA_TRY(cudaDeviceSynchronize());
+    c.ready = true;
+    return LR_OK;
+}
+
+LR_EXPORT int lr_comm_info(int *rank, int *world)
+{
+    lr::Lock lock;
+    BatchCtx *ctx = nullptr;
+    int rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    if (rank) *rank = ctx->comm.ready ? ctx->comm.rank : 0;
+    if (world) *world = ctx->comm.ready ? ctx->comm.world : 0;  // 0: no communicator on this device
+    return LR_OK;
+}
+
+LR_EXPORT int lr_comm_destroy(void)
+{
+    lr::Lock lock;
+    BatchCtx *ctx = nullptr;
+    int rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    CommHost &c = ctx->comm;
+    cudaDeviceSynchronize();
+    for (int g = 0; g < c.world; ++g)
+        if (g != c.rank && c.peer[g]) cudaIpcCloseMemHandle(c.peer[g]);
+    if (c.box) cudaFree(c.box);
+    if (c.dev) cudaFree(c.dev);
+    c = CommHost();
+    return LR_OK;
+}
+
+LR_EXPORT int lr_ransac_rigid_sharded(const float *src, const float *tgt, int64_t n, const LrRansacParams *params,
+                                      double *T_out, double *T_refit, uint8_t *mask, LrRansacStats *stats, void *stream)
+{
+    lr::Lock lock;
+    int rc = check_params(params, n);
+    if (rc) return rc;
+    LR_REQUIRE(T_out != nullptr, "T_out is null");
+    LR_REQUIRE(n == 0 || (src && tgt), "src/tgt is null");
+    LR_REQUIRE(params->scoring == LR_SCORE_COUNT, "hypothesis sharding packs (count, id): LR_SCORE_COUNT only");
+    BatchCtx *ctx = nullptr;
+    rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    LR_REQUIRE(ctx->comm.ready, "no communicator on this device: lr_comm_init + lr_comm_connect first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LrRansacParams &p = *params;
+    if (n < p.sample_size) return identity_result(n, T_out, T_refit, mask, stats, st);
+    Ws ws;
+    rc = enqueue_run(src, tgt, n, p, lr::SLOT_RANSAC, ws, st, ctx->comm.dev, ctx->comm.rank, ctx->comm.world);
+    if (rc) return rc;
+    return finish(src, tgt, n, p, ws, FIN_MODEL_READY, 0, T_out, T_refit, mask, stats, st);
+}
+
+// ---- error-bound probe of the tensor-core sweep -------------------------------------------------------------
+LR_EXPORT int lr_ransac_tc_probe(const float *src, const float *tgt, int64_t n, const double *models, int64_t H,
+                                 double threshold, float *d_out, double *E_out, int32_t *counts_out, void *stream)
+{
+    lr::Lock lock;
+    LR_REQUIRE(src && tgt && models, "null pointer");
+    LR_REQUIRE(n > 0 && n < (int64_t)1 << 31 && H > 0 && H <= ((int64_t)1 << 20), "n / H out of range");
+    LR_REQUIRE(threshold > 0.0, "threshold must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws ws;
+    int rc = ws_setup(n, H, 1, ws);
+    if (rc) return rc;
+    rc = launch_pack(src, tgt, n, ws, st);
+    if (rc) return rc;
+    const double thr2 = threshold * threshold;
+    const int sms = lr::sm_count();
+    LR_CUDA_TRY(tc_smem_attr());
+    k_probe_install<<<(int)((H + 127) / 128), 128, 0, st>>>(models, (int)H, ws.P8, thr2, ws.ctl, ws.m64, ws.Aimg, ws.band,
+                                                           ws.cnt, E_out);
+    if (d_out)
+        tcs::k_score_tc<true><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl, ws.m64,
+                                                                            ws.band, ws.cnt, thr2, d_out);
+    if (counts_out) {
+        tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl, ws.m64,
+                                                                             ws.band, ws.cnt, thr2, nullptr);
+        LR_CUDA_TRY(cudaMemcpyAsync(counts_out, ws.cnt, sizeof(int32_t) * H, cudaMemcpyDeviceToDevice, st));
+    }
+    LR_CUDA_TRY(cudaGetLastError());
+    LR_CUDA_TRY(cudaStreamSynchronize(st));
+    return LR_OK;
 }
 
 LR_EXPORT int lr_ransac_rigid_batch(const float *const *src, const float *const *tgt, const int64_t *n, int count,
@@ -1461,19 +2078,26 @@ LR_EXPORT int lr_ransac_rigid_batch(const float *const *src, const float *const 
     }
     LR_CUDA_TRY(cudaEventRecord(ctx->start, st));
     for (int l = 0; l < 2; ++l) LR_CUDA_TRY(cudaStreamWaitEvent(ctx->lane[l], ctx->start, 0));
+    // any failure below leaves work in flight on the lanes (it writes into ctx->host): join them before returning
+    auto bail = [&](int code) {
+        for (int l = 0; l < 2; ++l) cudaStreamSynchronize(ctx->lane[l]);
+        return code;
+    };
     for (int i = 0; i < count; ++i) {
         if (n[i] < p.sample_size) continue;  // identity, filled in below
         const int l = i & 1;
         Ws ws;
         rc = enqueue_run(src[i], tgt[i], n[i], p, l ? lr::SLOT_RANSAC_B : lr::SLOT_RANSAC, ws, ctx->lane[l]);
-        if (rc) return rc;
-        rc = finish_launch(src[i], tgt[i], n[i], p, ws, 1, 0, want_refit, nullptr, stats != nullptr, ctx->lane[l]);
-        if (rc) return rc;
-        LR_CUDA_TRY(cudaMemcpyAsync(&ctx->host[i], ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, ctx->lane[l]));
+        if (rc) return bail(rc);
+        rc = finish_launch(src[i], tgt[i], n[i], p, ws, p.scoring == LR_SCORE_MSAC ? FIN_GC : FIN_MODEL_READY, 0, want_refit,
+                           nullptr, ctx->lane[l], true, &ctx->host[i]);
+        if (rc) return bail(rc);
     }
     for (int l = 0; l < 2; ++l) {
-        LR_CUDA_TRY(cudaEventRecord(ctx->done[l], ctx->lane[l]));
-        LR_CUDA_TRY(cudaStreamWaitEvent(st, ctx->done[l], 0));
+        if (cudaEventRecord(ctx->done[l], ctx->lane[l]) != cudaSuccess || cudaStreamWaitEvent(st, ctx->done[l], 0) != cudaSuccess) {
+            lr::set_error("lr_ransac_rigid_batch: joining the internal streams failed");
+            return bail(LR_ERR_CUDA);
+        }
     }
     LR_CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < count; ++i) {
@@ -1628,7 +2252,7 @@ LR_EXPORT int lr_ransac_finalize(const float *src, const float *tgt, int64_t n, 
     rc = upload_growth(ws, n, params->sample_size, st);
     if (rc) return rc;
     k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
-    return finish(src, tgt, n, *params, ws, 0, key, T_out, T_refit, mask, stats, st, /*packed=*/false);
+    return finish(src, tgt, n, *params, ws, FIN_FROM_KEY, key, T_out, T_refit, mask, stats, st, /*packed=*/false);
 }
 
 LR_EXPORT int lr_ransac_sample(const LrRansacParams *params, int64_t n, int64_t id_lo, int64_t H, int32_t *samples,
@@ -1688,18 +2312,14 @@ LR_EXPORT int lr_icp_step(const float *xyz0, const float *xyz1, const int64_t *i
         for (int c = 0; c < 4; ++c) T12[4 * r + c] = T_in[4 * r + c];
     LR_CUDA_TRY(cudaMemcpyAsync(ws.scratchT, T12, sizeof(T12), cudaMemcpyHostToDevice, st));
     k_set_T<<<1, 32, 0, st>>>(ws.ctl, ws.scratchT);
-    if (K > 0) {
-        int blocks = (int)((K + 255) / 256);
-        if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
-        const double thr2 = threshold * threshold;
-        k_mask_sums<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl, nullptr);
-        k_refit_H<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl);
-    }
-    k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
+    BatchCtx *ctx = nullptr;
+    rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    k_finish<<<finish_blocks(K), 256, 0, st>>>(xyz0, xyz1, i0, i1, K, threshold * threshold, ws.ctl, nullptr, ws.partial, 1,
+                                               ctx->host1);
     LR_CUDA_TRY(cudaGetLastError());
-    Ctl h;
-    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     LR_CUDA_TRY(cudaStreamSynchronize(st));
+    const Ctl &h = *ctx->host1;
     T12_to_16(h.Tref, T_out);
     if (count) *count = h.refit_count;
     if (err2) *err2 = h.err2;
@@ -1722,18 +2342,14 @@ LR_EXPORT int lr_refit_indexed(const float *xyz0, const float *xyz1, const int64
         for (int c = 0; c < 4; ++c) T12[4 * r + c] = T_in[4 * r + c];
     LR_CUDA_TRY(cudaMemcpyAsync(dT, T12, sizeof(T12), cudaMemcpyHostToDevice, st));
     k_set_T<<<1, 32, 0, st>>>(ws.ctl, dT);
-    if (K > 0) {
-        int blocks = (int)((K + 255) / 256);
-        if (blocks > lr::sm_count() * 8) blocks = lr::sm_count() * 8;
-        const double thr2 = threshold * threshold;
-        k_mask_sums<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl, nullptr);
-        k_refit_H<<<blocks, 256, 0, st>>>(xyz0, xyz1, i0, i1, K, thr2, ws.ctl);
-    }
-    k_refit_solve<<<1, 32, 0, st>>>(ws.ctl);
+    BatchCtx *ctx = nullptr;
+    rc = dev_ctx(&ctx);
+    if (rc) return rc;
+    k_finish<<<finish_blocks(K), 256, 0, st>>>(xyz0, xyz1, i0, i1, K, threshold * threshold, ws.ctl, nullptr, ws.partial, 1,
+                                               ctx->host1);
     LR_CUDA_TRY(cudaGetLastError());
-    Ctl h;
-    LR_CUDA_TRY(cudaMemcpyAsync(&h, ws.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     LR_CUDA_TRY(cudaStreamSynchronize(st));
+    const Ctl &h = *ctx->host1;
     T12_to_16(h.Tref, T_out);
     if (count) *count = h.refit_count;
     return LR_OK;

@@ -1,0 +1,519 @@
+// lr_score_tc.cuh -- the inlier sweep on the 5th-gen tensor cores (tcgen05 + TMEM + bulk-TMA).
+// Included by lr_ransac.cu (needs its Ctl / helper definitions).
+//
+// Replaces the per-(hypothesis, correspondence) residual test of the reference engines
+// (Open3D EvaluateRANSACBasedOnCorrespondence behind Experiments/algorithms/FR.py:122-139; the score loop of
+// GCRANSAC::run behind GC-RANSAC/src/pygcransac/src/gcransac_python.cpp:507-533) for LR_SCORE_COUNT runs.
+//
+// The three components of a residual, d_a = sum_b R_ab p_b + t_a - q_a, are K <= 16 dot products between a
+// per-hypothesis row and a per-correspondence column, i.e. three [128 hypotheses] x [16] x [32 correspondences]
+// MMAs per tile.  Unlike the bilinear form of r^2 itself nothing cancels: every term is at most a coordinate
+// (~100 m), so fp16 operand pieces and the fp32 accumulator leave d_a within E ~ 1e-4 m of the canonical fp64
+// value, a band of ~4e-4 m^2 around thr^2 -- about one residual per hypothesis and 30k correspondences falls
+// inside it and is decided in fp64 on the spot, so every count is exact (same contract as the fp32 sweep).
+//
+//   operands   fp16 pieces, canonical no-swizzle K-major core matrices (8 rows x 16 B):
+//                hypothesis row a   core0 [R1_a0 R1_a0 R2_a0 R1_a1 R1_a1 R2_a1 t1_a t2_a]
+//                                   core1 [R1_a2 R1_a2 R2_a2 t3_a  -1    -1    -1   0   ]
+//                correspondence     core0 [p1_0  p2_0  p1_0  p1_1  p2_1  p1_1  1    1   ]   (shared by a = 0,1,2)
+//                                   core1_a [p1_2 p2_2 p1_2  1     q1_a  q2_a  q3_a 0   ]
+//              x1 = fp16(x), x2 = fp16(x - x1), x3 = fp16(x - x1 - x2).  q and t are exact in three pieces; of
+//              R p the products R1 p1 + R1 p2 + R2 p1 are kept, the dropped ones are <= 3 * 2^-22 |p|_2.
+//              The leading-byte-offset field of the smem descriptor selects core1_a, so the three B operands of
+//              a tile share core0: 64 B per correspondence instead of 96.
+//              Coordinates are taken relative to (c, c') = the first correspondence rounded to 1024 m
+//              (t~ = t + R c - c'), so map-frame offsets do not eat the fp16 range.
+//   staging    cp.async.bulk (UBLKCP): 12 KB hypothesis block per work item (double buffered), 8 KB stages of
+//              128 correspondences (4-deep ring), completion on mbarriers
+//   MMA        one elected lane: tcgen05.mma.cta_group::1.kind::f16, M 128, N 32, K 16, three per tile (a = 0,1,2)
+//              into a 96-column TMEM stage; four stages
+//   epilogue   16 warps = 4 classes x 4 TMEM lane quadrants; class k owns TMEM stage k = sub-tile k of every
+//              128-correspondence stage.  Thread = hypothesis: tcgen05.ld 32x32b.x16 of the three regions,
+//              u = d0^2 + d1^2 + d2^2 - thr^2 as three packed fma.rn.f32x2 per two residuals,
+//              count += sign bit (LEA.HI), running min |u| (FMNMX3): 3 issue slots per residual.
+//              min |u| < delta_h somewhere in the warp -> the 16 columns are checked one by one and the in-band
+//              ones decided with the canonical fp64 residual (rare: ~5e-5 of the residuals).
+// Work item = (128 survivors) x (range of 128-correspondence stages), round-robin over persistent CTAs; partial
+// counts merge through integer atomics.
+#pragma once
+// (cuda_fp16.h is included by lr_ransac.cu at file scope: this header sits inside its anonymous namespace)
+
+namespace tcs {
+
+constexpr int TM = 128;                 // hypotheses per row block (UMMA M)
+constexpr int TN = 32;                  // correspondences per MMA tile (UMMA N)
+constexpr int BROWS = 128;              // correspondences per shared-memory stage (== kChunk)
+constexpr int TILES_PER_STAGE = BROWS / TN;   // 4 == number of epilogue classes == TMEM stages
+constexpr int B_GROUP_BYTES = 512;      // 8 correspondences: core0 + 3 x core1_a
+constexpr int B_STAGE_BYTES = BROWS / 8 * B_GROUP_BYTES;  // 8 KB
+constexpr int B_STAGES = 4;
+constexpr int A_PART_BYTES = TM / 8 * 256;     // one residual component: 16 groups x (core0 + core1) = 4 KB
+constexpr int A_BLOCK_BYTES = 3 * A_PART_BYTES;  // 12 KB per 128 hypotheses
+constexpr int NCLASS = TILES_PER_STAGE;
+constexpr int TMEM_STAGE_COLS = 3 * TN;  // 96
+constexpr int WARP_PRODUCER = 4 * NCLASS, WARP_MMA = 4 * NCLASS + 1;
+constexpr int NTHREADS = 32 * (4 * NCLASS + 2);
+constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr float kRangeLimit = 15000.f;  // |p~|, |q~| above this: the fp16 pieces could overflow -> fp64 fallback
+constexpr double kAccKappa = 16.0;      // tensor-core accumulation error <= kappa * 2^-24 * sum |terms|
+                                        // (measured through lr_ransac_tc_probe: tests/test_gpu_score_tc.py)
+
+static_assert(BROWS == kChunk, "the correspondence padding of k_pack is the stage size of the tensor sweep");
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TCS_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra.uni TCS_WAIT_DONE;\n\t"
+        "bra.uni TCS_WAIT_LOOP;\n\t"
+        "TCS_WAIT_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar_addr)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar_addr)
+        : "memory");
+}
+// K-major, no swizzle: K-adjacent cores `lbo` bytes apart, 8-row groups `sbo` bytes apart
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// one tile: D_a = A_a . B_a for a = 0,1,2 (no accumulate), then the accumulator-ready commit
+__device__ __forceinline__ void tc_issue_tile(uint32_t d, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t b0, uint64_t b1,
+                                              uint64_t b2, uint32_t bar_full)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e, f;\n\t"
+        ".reg .b32 d1, d2;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 f, 0, 0;\n\t"
+        "add.u32 d1, %0, 32;\n\t"
+        "add.u32 d2, %0, 64;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %7, {%8, %8, %8, %8}, f;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [d1], %2, %5, %7, {%8, %8, %8, %8}, f;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [d2], %3, %6, %7, {%8, %8, %8, %8}, f;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "}" ::"r"(d),
+        "l"(a0), "l"(a1), "l"(a2), "l"(b0), "l"(b1), "l"(b2), "r"(IDESC), "r"(0u), "r"(bar_full)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// tcgen05.ld is asynchronous: the registers are valid only after tcgen05.wait::ld; listing them as in/out
+// operands keeps the compiler from scheduling a use above the wait
+__device__ __forceinline__ void tmem_ld_wait3(uint32_t (&a)[16], uint32_t (&b)[16], uint32_t (&c)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]),
+                   "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]),
+                   "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ u64 pk2(uint32_t lo, uint32_t hi)
+{
+    u64 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
+__device__ __forceinline__ float min3abs(float m, float a, float b)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));
+    return r;
+}
+
+// ---------------------------------------------------------------- operand images
+// x = h1 + h2 + h3 up to 2^-33 |x| (+ 2^-25 where a piece is subnormal); every difference below is exact in fp64
+__device__ __forceinline__ void split3(double x, __half &h1, __half &h2, __half &h3)
+{
+    h1 = __double2half(x);
+    double r = x - (double)__half2float(h1);
+    h2 = __double2half(r);
+    r = r - (double)__half2float(h2);
+    h3 = __double2half(r);
+}
+__device__ __forceinline__ void split2(double x, __half &h1, __half &h2)
+{
+    h1 = __double2half(x);
+    h2 = __double2half(x - (double)__half2float(h1));
+}
+
+// the frame the operands are expressed in: the first correspondence, rounded to 1024 m (exactly representable,
+// zero for sensor-centred scans)
+__device__ __forceinline__ void tc_centre6(float px, float py, float pz, float qx, float qy, float qz, double (&c)[3],
+                                           double (&cq)[3])
+{
+    c[0] = 1024.0 * rint((double)px * (1.0 / 1024.0));
+    c[1] = 1024.0 * rint((double)py * (1.0 / 1024.0));
+    c[2] = 1024.0 * rint((double)pz * (1.0 / 1024.0));
+    cq[0] = 1024.0 * rint((double)qx * (1.0 / 1024.0));
+    cq[1] = 1024.0 * rint((double)qy * (1.0 / 1024.0));
+    cq[2] = 1024.0 * rint((double)qz * (1.0 / 1024.0));
+}
+__device__ __forceinline__ void tc_centre(const float4 *__restrict__ P8, double (&c)[3], double (&cq)[3])
+{
+    const float4 a = __ldg(P8), b = __ldg(P8 + 1);
+    tc_centre6(a.x, a.y, a.z, a.w, b.x, b.y, c, cq);
+}
+
+union Core {
+    __half h[8];
+    uint4 u;
+};
+
+// correspondence i -> its four cores of the B image (group of 8 correspondences = 512 B)
+__device__ __forceinline__ void tc_write_corr(uint4 *__restrict__ Bimg, int64_t i, const double (&pt)[3],
+                                              const double (&qt)[3])
+{
+    __half p1[3], p2[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) split2(pt[b], p1[b], p2[b]);
+    const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+    uint4 *grp = Bimg + (i >> 3) * (B_GROUP_BYTES / 16) + (i & 7);
+    Core c0;
+    c0.h[0] = p1[0]; c0.h[1] = p2[0]; c0.h[2] = p1[0];
+    c0.h[3] = p1[1]; c0.h[4] = p2[1]; c0.h[5] = p1[1];
+    c0.h[6] = one; c0.h[7] = one;
+    grp[0] = c0.u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        Core c1;
+        c1.h[0] = p1[2]; c1.h[1] = p2[2]; c1.h[2] = p1[2];
+        c1.h[3] = one;
+        split3(qt[a], c1.h[4], c1.h[5], c1.h[6]);
+        c1.h[7] = zero;
+        grp[(1 + a) * 8] = c1.u;
+    }
+}
+
+// hypothesis slot -> its six cores of the A image (block of 128 slots = 12 KB: component a, group, core, row)
+__device__ __forceinline__ void tc_write_model(uint4 *__restrict__ Aimg, int slot, const double (&T)[12],
+                                               const double (&tt)[3])
+{
+    const int blk = slot / TM, g = (slot % TM) >> 3, r = slot & 7;
+    const __half m1 = __float2half_rn(-1.f), zero = __float2half_rn(0.f);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        __half r1[3], r2[3], t1, t2, t3;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) split2(T[4 * a + b], r1[b], r2[b]);
+        split3(tt[a], t1, t2, t3);
+        uint4 *base = Aimg + ((size_t)blk * A_BLOCK_BYTES + a * A_PART_BYTES + g * 256) / 16 + r;
+        Core c0, c1;
+        c0.h[0] = r1[0]; c0.h[1] = r1[0]; c0.h[2] = r2[0];
+        c0.h[3] = r1[1]; c0.h[4] = r1[1]; c0.h[5] = r2[1];
+        c0.h[6] = t1; c0.h[7] = t2;
+        c1.h[0] = r1[2]; c1.h[1] = r1[2]; c1.h[2] = r2[2];
+        c1.h[3] = t3; c1.h[4] = m1; c1.h[5] = m1; c1.h[6] = m1; c1.h[7] = zero;
+        base[0] = c0.u;
+        base[8] = c1.u;
+    }
+}
+
+// |d_tc - d_64| <= E for every component of every correspondence of the run (header comment; P2 = max |p~|_2,
+// Q = max |q~|_inf, tinf = |t~|_inf): dropped products, piece rounding, tensor-core accumulation
+__device__ __forceinline__ double tc_err_bound(double P2, double Q, double tinf)
+{
+    const double u22 = 2.384185791015625e-07, u24 = 5.9604644775390625e-08;
+    return 3.0 * u22 * P2 * 1.001 + kAccKappa * u24 * (1.7320508075688772 * P2 + tinf + Q + 1.0) + 1e-6;
+}
+
+// ---------------------------------------------------------------- the sweep
+struct __align__(8) Smem {
+    uint64_t a_full[2], a_empty[2], b_full[B_STAGES], b_empty[B_STAGES], t_full[NCLASS], t_empty[NCLASS];
+    uint32_t tmem_base;
+};
+
+struct Split {
+    int nhb, nps, cpp, nitems;
+};
+__device__ __forceinline__ Split make_split(int nsurv, int nchunks, int grid)
+{
+    Split s;
+    s.nhb = (nsurv + TM - 1) / TM;
+    int nps = s.nhb > 0 ? (6 * grid + s.nhb - 1) / s.nhb : 1;
+    nps = nps < 1 ? 1 : (nps > nchunks ? nchunks : nps);
+    s.cpp = (nchunks + nps - 1) / nps;  // 128-correspondence stages per item
+    s.nps = (nchunks + s.cpp - 1) / s.cpp;
+    s.nitems = s.nhb * s.nps;
+    return s;
+}
+
+__device__ __noinline__ int tc_exact_inlier(const float4 *__restrict__ P8, int64_t i, const double *__restrict__ m64s,
+                                            double thr2)
+{
+    double p[3], q[3], T[12];
+    load_pq(P8, i, p, q);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = m64s[k];
+    return res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]) < thr2 ? 1 : 0;
+}
+
+// DUMP: write the three tensor-core residual components of every (slot, correspondence) to `dump`
+// ([slot][n_pad][3] floats) instead of counting -- the error-bound probe of tests/test_gpu_score_tc.py
+template <bool DUMP>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const float4 *__restrict__ P8, int64_t n,
+           int64_t n_pad, Ctl *ctl, const double *__restrict__ m64, const float *__restrict__ band, int *__restrict__ cnt,
+           double thr2, float *__restrict__ dump)
+{
+    if (ctl->done) return;
+    const int nsurv = ctl->n_surv;
+    if (nsurv <= 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = (int)(n_pad / BROWS);
+
+    // operands out of the fp16 range (a cloud more than 15 km across): exact fp64 counts on the CUDA cores
+    if (!(__uint_as_float(ctl->pt2max_bits) < kRangeLimit && __uint_as_float(ctl->qtmax_bits) < kRangeLimit)) {
+        if (DUMP) return;
+        unsigned long long evals = 0;
+        for (int slot = blockIdx.x * NTHREADS + threadIdx.x; slot < nsurv; slot += gridDim.x * NTHREADS) {
+            double T[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) T[k] = m64[(size_t)slot * 12 + k];
+            int c = 0;
+            for (int64_t i = 0; i < n; ++i) {
+                double p[3], q[3];
+                load_pq(P8, i, p, q);
+                c += res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]) < thr2 ? 1 : 0;
+            }
+            cnt[slot] = c;
+            evals += (unsigned long long)n;
+        }
+        if (evals) atomicAdd(reinterpret_cast<unsigned long long *>(&ctl->n_rechecked), evals);
+        return;
+    }
+
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    uint8_t *sA = smem_raw;                             // 2 x 12 KB
+    uint8_t *sB = smem_raw + 2 * A_BLOCK_BYTES;         // B_STAGES x 8 KB
+    Smem *sm = reinterpret_cast<Smem *>(smem_raw + 2 * A_BLOCK_BYTES + B_STAGES * B_STAGE_BYTES);
+    const Split sp = make_split(nsurv, nchunks, (int)gridDim.x);
+
+    if (warp == WARP_MMA) {
+        if (lane == 0) {
+            for (int k = 0; k < 2; ++k) {
+                mbar_init(&sm->a_full[k], 1);
+                mbar_init(&sm->a_empty[k], 1);
+            }
+            for (int k = 0; k < B_STAGES; ++k) {
+                mbar_init(&sm->b_full[k], 1);
+                mbar_init(&sm->b_empty[k], 1);
+            }
+            for (int k = 0; k < NCLASS; ++k) {
+                mbar_init(&sm->t_full[k], 1);
+                mbar_init(&sm->t_empty[k], 4);  // the four warps (lane quadrants) of class k
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_base;
+
+    if (warp == WARP_PRODUCER) {
+        // ===== producer: bulk copies of the hypothesis block and the correspondence stages =====
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            for (int item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
+                const int hb = item / sp.nps, ps = item - hb * sp.nps;
+                const int c_lo = ps * sp.cpp, c_hi = min(nchunks, c_lo + sp.cpp);
+                const uint32_t ab = a_it & 1u;
+                mbar_wait(smem_u32(&sm->a_empty[ab]), ((a_it >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(smem_u32(&sm->a_full[ab]), A_BLOCK_BYTES);
+                bulk_g2s(smem_u32(sA + ab * A_BLOCK_BYTES), reinterpret_cast<const uint8_t *>(Aimg) + (size_t)hb * A_BLOCK_BYTES,
+                         A_BLOCK_BYTES, smem_u32(&sm->a_full[ab]));
+                ++a_it;
+                for (int c = c_lo; c < c_hi; ++c) {
+                    const uint32_t s = b_it % B_STAGES;
+                    mbar_wait(smem_u32(&sm->b_empty[s]), ((b_it / B_STAGES) & 1u) ^ 1u);
+                    mbar_expect_tx(smem_u32(&sm->b_full[s]), B_STAGE_BYTES);
+                    bulk_g2s(smem_u32(sB + s * B_STAGE_BYTES), reinterpret_cast<const uint8_t *>(Bimg) + (size_t)c * B_STAGE_BYTES,
+                             B_STAGE_BYTES, smem_u32(&sm->b_full[s]));
+                    ++b_it;
+                }
+            }
+        }
+    } else if (warp == WARP_MMA) {
+        // ===== MMA issuer: warp-uniform loop, elect.sync picks the lane =====
+        const uint32_t a_full = smem_u32(&sm->a_full[0]), a_empty = smem_u32(&sm->a_empty[0]);
+        const uint32_t b_full = smem_u32(&sm->b_full[0]), b_empty = smem_u32(&sm->b_empty[0]);
+        const uint32_t t_full = smem_u32(&sm->t_full[0]), t_empty = smem_u32(&sm->t_empty[0]);
+        uint32_t a_it = 0, b_it = 0;
+        for (int item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
+            const int ps = item % sp.nps;
+            const int c_lo = ps * sp.cpp, c_hi = min(nchunks, c_lo + sp.cpp);
+            const uint32_t ab = a_it & 1u;
+            mbar_wait(a_full + ab * 8u, (a_it >> 1) & 1u);
+            const uint32_t a_addr = smem_u32(sA + ab * A_BLOCK_BYTES);
+            const uint64_t ad0 = smem_desc(a_addr, 128, 256), ad1 = smem_desc(a_addr + A_PART_BYTES, 128, 256),
+                           ad2 = smem_desc(a_addr + 2 * A_PART_BYTES, 128, 256);
+            for (int c = c_lo; c < c_hi; ++c) {
+                const uint32_t s = b_it % B_STAGES;
+                mbar_wait(b_full + s * 8u, (b_it / B_STAGES) & 1u);
+                const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < TILES_PER_STAGE; ++j) {
+                    // TMEM stage j is free once class j has loaded the previous stage's sub-tile j into registers
+                    mbar_wait(t_empty + j * 8u, (b_it & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t bj = b_addr + j * (TN / 8) * B_GROUP_BYTES;
+                    tc_issue_tile(tmem_base + j * TMEM_STAGE_COLS, ad0, ad1, ad2, smem_desc(bj, 128, B_GROUP_BYTES),
+                                  smem_desc(bj, 256, B_GROUP_BYTES), smem_desc(bj, 384, B_GROUP_BYTES), t_full + j * 8u);
+                }
+                tc_commit_elect(b_empty + s * 8u);  // the stage's bytes are reusable once these MMAs have read them
+                ++b_it;
+            }
+            tc_commit_elect(a_empty + ab * 8u);
+            ++a_it;
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> counts =====
+        const int q = warp & 3;    // TMEM lane quadrant this warp may read
+        const int cls = warp >> 2;  // class = TMEM stage = sub-tile of every correspondence stage
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cls * TMEM_STAGE_COLS;
+        const uint32_t full_addr = smem_u32(&sm->t_full[cls]), empty_addr = smem_u32(&sm->t_empty[cls]);
+        const float nthr2 = -(float)thr2;
+        const u64 nthr2p = pk2(__float_as_uint(nthr2), __float_as_uint(nthr2));
+        unsigned long long *n_rechecked = reinterpret_cast<unsigned long long *>(&ctl->n_rechecked);
+        uint32_t t_it = 0;
+        for (int item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
+            const int hb = item / sp.nps, ps = item - hb * sp.nps;
+            const int c_lo = ps * sp.cpp, c_hi = min(nchunks, c_lo + sp.cpp);
+            const int slot = hb * TM + q * 32 + lane;
+            const bool valid = slot < nsurv;
+            const float delta = valid ? band[slot] : -1.f;  // rows past the survivor count hold stale models
+            int count = 0;
+            unsigned evals = 0;
+            for (int c = c_lo; c < c_hi; ++c) {
+                mbar_wait(full_addr, t_it & 1u);
+                tc_fence_after();
+                const int64_t col0 = (int64_t)c * BROWS + cls * TN;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t d0[16], d1[16], d2[16];
+                    tmem_ld16_issue(taddr + half * 16, d0);
+                    tmem_ld16_issue(taddr + TN + half * 16, d1);
+                    tmem_ld16_issue(taddr + 2 * TN + half * 16, d2);
+                    tmem_ld_wait3(d0, d1, d2);
+                    if (half == 1) {  // everything of this tile is in registers: hand the TMEM stage back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty_addr);
+                    }
+                    if (DUMP) {
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float *o = dump + ((size_t)slot * n_pad + (col0 + half * 16 + j)) * 3;
+                                o[0] = __uint_as_float(d0[j]);
+                                o[1] = __uint_as_float(d1[j]);
+                                o[2] = __uint_as_float(d2[j]);
+                            }
+                        }
+                        continue;
+                    }
+                    u64 u[8];
+                    float mn = INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const u64 e0 = pk2(d0[2 * j], d0[2 * j + 1]), e1 = pk2(d1[2 * j], d1[2 * j + 1]),
+                                  e2 = pk2(d2[2 * j], d2[2 * j + 1]);
+                        u[j] = fma2(e2, e2, fma2(e1, e1, fma2(e0, e0, nthr2p)));
+                        float ua, ub;
+                        upk2(u[j], ua, ub);
+                        count += (int)(__float_as_uint(ua) >> 31) + (int)(__float_as_uint(ub) >> 31);
+                        mn = min3abs(mn, ua, ub);
+                    }
+                    if (__any_sync(0xffffffffu, mn < delta)) {
+                        // rare: some residual of these 16 columns is within the error band of some hypothesis
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float ua, ub;
+                            upk2(u[j], ua, ub);
+                            if (fabsf(ua) < delta) {
+                                count -= (int)(__float_as_uint(ua) >> 31);
+                                count += tc_exact_inlier(P8, col0 + half * 16 + 2 * j, m64 + (size_t)slot * 12, thr2);
+                                ++evals;
+                            }
+                            if (fabsf(ub) < delta) {
+                                count -= (int)(__float_as_uint(ub) >> 31);
+                                count += tc_exact_inlier(P8, col0 + half * 16 + 2 * j + 1, m64 + (size_t)slot * 12, thr2);
+                                ++evals;
+                            }
+                        }
+                    }
+                }
+                ++t_it;
+            }
+            if (!DUMP && valid) {
+                if (sp.nps == 1) cnt[slot] = count;
+                else if (count) atomicAdd(&cnt[slot], count);
+                if (evals) atomicAdd(n_rechecked, (unsigned long long)evals);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+constexpr size_t kSmemBytes = 2 * A_BLOCK_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(Smem) + 1024 + 64;
+
+}  // namespace tcs

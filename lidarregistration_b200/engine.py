@@ -82,6 +82,8 @@ def match_ratio(f0, f1, i0, i1, i2):
     i0, i1, i2 = to_dev_i64(i0), to_dev_i64(i1), to_dev_i64(i2)
     K = i0.shape[0]
     out = torch.empty(K, dtype=torch.float32, device=f0.device)
+    if K == 0:
+        return out
     rc = _lib.lib().lr_match_ratio(_lib.ptr(f0), _lib.ptr(f1), int(f0.shape[1]), ctypes.c_int64(K), _lib.ptr(i0),
                                    _lib.ptr(i1), _lib.ptr(i2), _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "lr_match_ratio")
@@ -92,6 +94,8 @@ def gather_xyz(xyz, idx):
     xyz, idx = to_dev_f32(xyz), to_dev_i64(idx)
     K = idx.shape[0]
     out = torch.empty((K, 3), dtype=torch.float32, device=xyz.device)
+    if K == 0:
+        return out
     rc = _lib.lib().lr_gather_xyz(_lib.ptr(xyz), _lib.ptr(idx), ctypes.c_int64(K), _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "lr_gather_xyz")
     return out
@@ -139,6 +143,10 @@ def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
     mask: CUDA bool tensor, or with mask_on_host a numpy bool array: the kernel then writes the inlier bytes
     straight into pinned, device-mapped host memory (unified addressing) and the call's own synchronisation
     covers them -- no conversion kernel, no second copy, no second synchronisation."""
+    return _rigid_call("lr_ransac_rigid", src, tgt, params, want_mask, mask_on_host)
+
+
+def _rigid_call(fn_name, src, tgt, params, want_mask, mask_on_host):
     src, tgt = _dev_or_pinned_f32(src), _dev_or_pinned_f32(tgt)
     n = src.shape[0]
     T = (ctypes.c_double * 16)()
@@ -148,15 +156,63 @@ def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
     if want_mask:
         mask = _pinned_mask(n) if mask_on_host else torch.empty(n, dtype=torch.uint8, device=_dev())
     mask_ptr = None if mask is None else ctypes.c_void_p(mask.data_ptr())
-    rc = _lib.lib().lr_ransac_rigid(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(tgt.data_ptr()),
-                                    ctypes.c_int64(n), ctypes.byref(params), T, Tr,
-                                    mask_ptr, ctypes.byref(st), _lib.stream_ptr())
-    _lib.check(rc, "lr_ransac_rigid")
+    rc = getattr(_lib.lib(), fn_name)(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(tgt.data_ptr()),
+                                      ctypes.c_int64(n), ctypes.byref(params), T, Tr,
+                                      mask_ptr, ctypes.byref(st), _lib.stream_ptr())
+    _lib.check(rc, fn_name)
     if mask is not None:
         mask = mask.numpy().astype(bool) if mask_on_host else mask.bool()
     out = dict(T=_lib.T_from16(T), T_refit=_lib.T_from16(Tr), mask=mask)
     out.update(st.as_dict())
     return out
+
+
+# ------------------------------------------------ hypothesis sharding with the library-owned communicator
+def comm_world():
+    """(rank, world) of the communicator connected on the current device; world == 0: none"""
+    _lib.require_cuda()
+    r, w = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.lib().lr_comm_info(ctypes.byref(r), ctypes.byref(w)), "lr_comm_info")
+    return int(r.value), int(w.value)
+
+
+def comm_init(rank, world, all_gather_bytes):
+    """lr_comm_init + lr_comm_connect.  `all_gather_bytes(b: bytes) -> [bytes] * world` (rank order) is the
+    caller's transport for the 64-byte IPC handles (torch.distributed all_gather_object, MPI, ...)."""
+    _lib.require_cuda()
+    h = (ctypes.c_uint8 * 64)()
+    _lib.check(_lib.lib().lr_comm_init(int(rank), int(world), h), "lr_comm_init")
+    handles = all_gather_bytes(bytes(h))
+    assert len(handles) == world and all(len(x) == 64 for x in handles)
+    buf = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+    _lib.check(_lib.lib().lr_comm_connect(buf), "lr_comm_connect")
+
+
+def comm_destroy():
+    _lib.check(_lib.lib().lr_comm_destroy(), "lr_comm_destroy")
+
+
+def ransac_rigid_sharded(src, tgt, params, want_mask=False, mask_on_host=False):
+    """lr_ransac_rigid_sharded (a collective over the connected communicator) -> the dict ransac_rigid returns"""
+    return _rigid_call("lr_ransac_rigid_sharded", src, tgt, params, want_mask, mask_on_host)
+
+
+def tc_probe(src, tgt, models, threshold=0.6, want_d=True, want_counts=True):
+    """lr_ransac_tc_probe -> (d[H, pad128(n), 3] fp32 | None, E[H] fp64, counts[H] int32 | None), CUDA tensors"""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    if isinstance(models, np.ndarray):
+        models = torch.from_numpy(np.ascontiguousarray(models))
+    models = models.to(src.device).to(torch.float64).contiguous().reshape(-1, 12)
+    n, H = src.shape[0], models.shape[0]
+    n_pad = (n + 127) // 128 * 128
+    d = torch.empty((H, n_pad, 3), dtype=torch.float32, device=src.device) if want_d else None
+    E = torch.empty(H, dtype=torch.float64, device=src.device)
+    counts = torch.empty(H, dtype=torch.int32, device=src.device) if want_counts else None
+    rc = _lib.lib().lr_ransac_tc_probe(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), _lib.ptr(models), ctypes.c_int64(H),
+                                       ctypes.c_double(threshold), _lib.ptr(d), _lib.ptr(E), _lib.ptr(counts),
+                                       _lib.stream_ptr())
+    _lib.check(rc, "lr_ransac_tc_probe")
+    return d, E, counts
 
 
 def ransac_rigid_batch(pairs, params):
@@ -311,7 +367,8 @@ def match_set_mode(mode):
 
 
 def ransac_set_mode(mode):
-    """0 = inlier sweep with the first-component early-out (default); 1 = every residual in full (A/B)."""
+    """0 = tensor-core inlier sweep (default); 1 = fp32 sweep, every residual in full; 2 = fp32 sweep with the
+    first-component early-out (round 1's default).  Identical results."""
     _lib.check(_lib.lib().lr_ransac_set_mode(int(mode)), "lr_ransac_set_mode")
 
 

@@ -423,6 +423,39 @@ LRO_API int64_t lro_count_inliers(const float *src, const float *tgt, int64_t n,
     return cnt;
 }
 
+/* "Faithful" Open3D evaluation (FR.py:122-139 -> RegistrationRANSACBasedOnCorrespondence): for
+ * every hypothesis that passes the checkers Open3D copies the WHOLE source cloud, transforms the copy and then
+ * walks the correspondences (EvaluateRANSACBasedOnCorrespondence also accumulates the squared error for the rmse).
+ * Same arithmetic per residual as lro_res2, so the counts are those of lro_count_inliers; what changes is the
+ * memory traffic per hypothesis -- this variant exists for the CPU timing of bench.py ("faithful" vs "lean").
+ * cloud: xyz of the source cloud [cloud_n,3]; src_idx (nullable = identity): row of the cloud of correspondence i. */
+static int g_o3d_faithful = 0;
+LRO_API void lro_set_o3d_faithful(int on) { g_o3d_faithful = on; }
+LRO_API int lro_get_o3d_faithful(void) { return g_o3d_faithful; }
+
+static int64_t lro_count_inliers_faithful(const float *cloud, int64_t cloud_n, const float *tgt, int64_t n,
+                                          const double T[12], double thr, double *buf, double *err2_out)
+{
+    for (int64_t i = 0; i < cloud_n; ++i) { /* pcd = source; pcd.Transform(transformation) */
+        double px = cloud[3 * i], py = cloud[3 * i + 1], pz = cloud[3 * i + 2];
+        buf[3 * i + 0] = ((T[0] * px + T[1] * py) + T[2] * pz) + T[3];
+        buf[3 * i + 1] = ((T[4] * px + T[5] * py) + T[6] * pz) + T[7];
+        buf[3 * i + 2] = ((T[8] * px + T[9] * py) + T[10] * pz) + T[11];
+    }
+    const double thr2 = thr * thr;
+    int64_t cnt = 0;
+    double err2 = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        double d0 = buf[3 * i + 0] - (double)tgt[3 * i + 0];
+        double d1 = buf[3 * i + 1] - (double)tgt[3 * i + 1];
+        double d2 = buf[3 * i + 2] - (double)tgt[3 * i + 2];
+        double r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+        if (r2 < thr2) { ++cnt; err2 += r2; }
+    }
+    if (err2_out) *err2_out = err2;
+    return cnt;
+}
+
 /* MSAC score (App. A): sum over r^2 < tau^2 of (1 - r^2/tau^2), tau = 1.5*thr */
 LRO_API double lro_msac(const float *src, const float *tgt, int64_t n, const double T[12], double thr,
                         int64_t *inliers_out)
@@ -526,6 +559,7 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
 #pragma omp parallel
             {
                 int64_t t_id = -1, t_cnt = -1, t_pass = 0;
+                double *buf = g_o3d_faithful ? (double *)malloc(sizeof(double) * 3 * (size_t)n) : NULL;
 #pragma omp for schedule(dynamic, 256) nowait
                 for (int64_t id = lo; id < hi; ++id) {
                     int32_t s[4];
@@ -533,9 +567,11 @@ LRO_API void lro_ransac(const float *src, const float *tgt, int64_t n, int m, in
                     lro_sample(seed, (uint64_t)id, sampler, m, n, growth, s);
                     if (!lro_model_from_sample(src, tgt, s, m, use_elc, elc_ratio, Th)) continue;
                     ++t_pass;
-                    int64_t c = lro_count_inliers(src, tgt, n, Th, thr, NULL);
+                    int64_t c = buf ? lro_count_inliers_faithful(src, n, tgt, n, Th, thr, buf, NULL)
+                                    : lro_count_inliers(src, tgt, n, Th, thr, NULL);
                     if (c > t_cnt || (c == t_cnt && id < t_id)) { t_cnt = c; t_id = id; }
                 }
+                free(buf);
 #pragma omp critical
                 {
                     r_pass += t_pass;

@@ -108,6 +108,12 @@ def set_threads(t):
     lib().lro_set_threads(int(t))
 
 
+def set_o3d_faithful(on):
+    """CPU-timing variant of the loop: copy + transform the whole source cloud per surviving hypothesis as Open3D's
+    RegistrationRANSACBasedOnCorrespondence does; counts are unchanged"""
+    lib().lro_set_o3d_faithful(int(bool(on)))
+
+
 def sqnorms(F):
     F = _f32(F)
     out = np.empty(F.shape[0], np.float32)

@@ -80,9 +80,13 @@ def test_gc_options_mapping():
     import pytest
     import lidarregistration_b200.algorithms  # noqa: F401
     G = sys.modules["lidarregistration_b200.algorithms.GC_RANSAC"]
-    assert G.gc_options(None, True) == dict(scoring=0) == G.gc_options("count", False)
+    with pytest.warns(UserWarning, match="GC_LO False has no effect"):
+        assert G.gc_options(None, True) == dict(scoring=0) == G.gc_options("count", False)
     assert G.gc_options("MSAC", True) == dict(scoring=1, lo_rounds=10, lo_trials=20, lsq_iters=10)
-    assert G.gc_options("msac", False) == dict(scoring=1, lo_rounds=0, lo_trials=20, lsq_iters=0)
+    # --GC_LO False only switches the graph-cut rounds off; the finishing least squares still runs (:518-521, App. A)
+    assert G.gc_options("msac", False) == dict(scoring=1, lo_rounds=0, lo_trials=20, lsq_iters=10)
+    # --fast_rejection NONE: the no-preemption branch ignores --GC_LO and allows 50 inner draws (:570-592)
+    assert G.gc_options("MSAC", False, preemption=False) == dict(scoring=1, lo_rounds=10, lo_trials=50, lsq_iters=10)
     with pytest.raises(ValueError):
         G.gc_options("LMEDS", True)
     with pytest.raises(NotImplementedError):
