@@ -499,8 +499,9 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                 ++t_it;
             }
             if (!DUMP && valid) {
-                if (sp.nps == 1) cnt[slot] = count;
-                else if (count) atomicAdd(&cnt[slot], count);
+                // the four classes (sub-tiles) of a quadrant hold partial counts of the same slot: always merge
+                // (k_kabsch / k_probe_models zero cnt[] before the sweep)
+                if (count) atomicAdd(&cnt[slot], count);
                 if (evals) atomicAdd(n_rechecked, (unsigned long long)evals);
             }
         }

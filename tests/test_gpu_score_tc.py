@@ -99,8 +99,10 @@ def test_probe_adversarial_pieces():
     models = random_models(rng, H, t=120.0)
     err, E, counts, _ = probe_case(src, tgt, models)
     assert (err / E).max() < 1.0
-    src2 = (src * np.float32(100.0)).astype(np.float32)  # ~12.8 km: still inside the fp16 range guard
-    tgt2 = (tgt * np.float32(100.0)).astype(np.float32)
+    # coordinates up to 3.2 km: relative to the operand frame (first correspondence, rounded to 1024 m) that is
+    # |p~|_2 <= sqrt(3) (2 x 3.2 km + 512 m) = 12 km, still inside the fp16 range guard (15 km)
+    src2 = (src * np.float32(25.0)).astype(np.float32)
+    tgt2 = (tgt * np.float32(25.0)).astype(np.float32)
     err, E, counts, _ = probe_case(src2, tgt2, models)
     assert (err / E).max() < 1.0
     ref = np.array([O.count_inliers(src2, tgt2, np.vstack([m.reshape(3, 4), [0, 0, 0, 1]]), 0.6) for m in models])

@@ -159,8 +159,10 @@ def test_reference_interface_with_msac_scoring():
     o = O.ransac_gc(d["src"], d["tgt"], thr=THR, max_iters=30000, seed=7, return_mask=True)
     assert close_T(pose.T, o["T"], 1e-9, 1e-8) and np.array_equal(mask, o["mask"])
     pose_nolo, _ = G.findRigidTransform(d["src"], d["tgt"], neighborhood=1, scoring="MSAC", **common)
-    o2 = O.ransac_gc(d["src"], d["tgt"], thr=THR, max_iters=30000, seed=7, lo_rounds=0, lsq_iters=0)
-    assert np.array_equal(pose_nolo.T, o2["T"])
+    # --GC_LO False only switches the graph-cut rounds off (gcransac_python.cpp:518-521); the finishing iterated
+    # least squares still runs (SURVEY App. A "Finish")
+    o2 = O.ransac_gc(d["src"], d["tgt"], thr=THR, max_iters=30000, seed=7, lo_rounds=0)
+    assert close_T(pose_nolo.T, o2["T"], 1e-9, 1e-8)
     with pytest.raises(NotImplementedError):
         G.findRigidTransform(d["src"], d["tgt"], neighborhood=0, scoring="MSAC",
                              **dict(common, spatial_coherence_weight=0.1))

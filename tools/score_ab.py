@@ -20,12 +20,21 @@ def run(pairs, params, reps=5):
         out = [engine.ransac_rigid(a, b, params) for a, b in pairs]
     engine.prof_enable(False)
     ms, launches = engine.prof_read(engine.PROF_SCORE)
-    return ms / (reps * len(pairs)), out
+    gen_ms, _ = engine.prof_read(engine.PROF_GEN)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for a, b in pairs:
+            engine.ransac_rigid(a, b, params)
+    e1.record()
+    torch.cuda.synchronize()
+    return ms / (reps * len(pairs)), out, gen_ms / (reps * len(pairs)), e0.elapsed_time(e1) / (reps * len(pairs))
 
 
 def main():
     k = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-    modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 0]
+    modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 0]
     res = {}
     for name, ratio, elc in (("cfg3_elc", 0.3, True), ("cfg3_noelc_100k", 0.3, False),
                              ("inl10_elc", 0.1, True), ("inl60_elc", 0.6, True)):
@@ -39,8 +48,11 @@ def main():
         ref = None
         for mode in modes:
             engine.ransac_set_mode(mode)
-            ms, out = run(pairs, params)
-            sig = [(o["best_id"], o["best_count"], o["n_scored"], o["n_rechecked"]) for o in out]
+            ms, out, gen_ms, pair_ms = run(pairs, params)
+            sig = [(o["best_id"], o["best_count"], o["n_scored"]) for o in out]
+            row["mode%d_rechecked" % mode] = out[0]["n_rechecked"]
+            row["mode%d_gen_ms" % mode] = gen_ms
+            row["mode%d_pair_ms" % mode] = pair_ms
             if ref is None:
                 ref = sig
             row["mode%d_ms" % mode] = ms
