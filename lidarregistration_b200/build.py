@@ -45,7 +45,9 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
+    # LIDARREG_NVCC_FLAGS: extra -D switches for A/B builds of a kernel (tools/); empty in the product build
+    extra = os.environ.get("LIDARREG_NVCC_FLAGS", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
     env = dict(os.environ)
     # the image exports CC=/opt/gcc/bin/gcc; let nvcc pick its default host compiler
     r = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)

@@ -45,7 +45,7 @@ struct Ctl {
     unsigned long long best_key;   // over finished rounds
     unsigned long long round_key;  // current round
     int n_surv;                    // survivors of the current round (compacted slots)
-    int n_flag;                    // slots whose fp32 bracket is open
+    unsigned int n_events;         // tensor sweep: in-band residuals listed for k_tc_events in the current round
     int done;                      // confidence exit reached
     int pad0;
     long long iters_run, n_scored, n_rechecked;
@@ -91,6 +91,8 @@ struct Ws {
     uint4 *Bimg;      // fp16 operand image of the correspondences, 64 B each
     float *band;      // per slot: half-width of the r^2 band that is decided in fp64
     double *partial;  // k_finish: kFinBlocksMax x kFinVals per-block sums
+    int4 *events;     // records of the residuals inside the tensor sweep's error band, one list per epilogue warp and CTA
+    unsigned *ev_count;
     // LR_SCORE_MSAC runs only (null otherwise)
     unsigned long long *q64;  // per slot: quantised MSAC score
     int32_t *lo_L;            // inlier index list of the current LO round, ascending
@@ -465,7 +467,7 @@ __global__ void k_ctl_reset(Ctl *ctl)
         ctl->best_key = 0ULL;
         ctl->round_key = 0ULL;
         ctl->n_surv = 0;
-        ctl->n_flag = 0;
+        ctl->n_events = 0u;
         ctl->done = 0;
         ctl->iters_run = 0;
         ctl->n_scored = 0;
@@ -893,7 +895,7 @@ __global__ void k_round_end(Ctl *ctl, int64_t round_len, const int *__restrict__
     ctl->n_scored += ctl->n_surv;
     ctl->round_key = 0ULL;
     ctl->n_surv = 0;
-    ctl->n_flag = 0;
+    ctl->n_events = 0u;
     if (need) {
         long long cnt = (long long)(ctl->best_key >> 32) - 1;
         if (ctl->best_key != 0ULL && cnt >= (long long)need[round_idx]) ctl->done = 1;
@@ -1040,7 +1042,7 @@ k_resolve_end(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restr
     ctl->n_scored += (long long)scored;
     ctl->round_key = 0ULL;
     ctl->n_surv = 0;
-    ctl->n_flag = 0;
+    ctl->n_events = 0u;
     int done = err;
     if (a.need) {
         const long long c = (long long)(best >> 32) - 1;
@@ -1226,6 +1228,8 @@ __global__ void k_refit_solve(Ctl *ctl)
 // bit-reproducible run to run -- and solves the Kabsch problem:  H = sum q' p'^T - (sum q')(sum p')^T / k.
 // `host_out` (nullable, pinned + mapped): the control block is written there by the same block, so the caller
 // needs no copy after the kernel, only the stream synchronisation.
+constexpr unsigned kTcEventCap = 1024;  // in-band residuals an epilogue warp of the tensor sweep can list per round (one private
+                                       // list per warp and CTA: 148 x 16 x 16 KB); beyond it the warp decides on the spot
 constexpr int kFinVals = 17;
 constexpr int kFinBlocksMax = 512;
 __global__ void __launch_bounds__(256)
@@ -1401,6 +1405,8 @@ struct GrowthCache {
 };
 GrowthCache g_growth[64];
 
+size_t tc_regions() { return (size_t)lr::sm_count() * tcs::NEPI; }
+
 int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = false, int slot = lr::SLOT_RANSAC,
              bool gc = false)
 {
@@ -1416,7 +1422,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
                    lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1)) +
                    lr::padded((size_t)((slots + tcs::TM - 1) / tcs::TM) * tcs::A_BLOCK_BYTES) +
                    lr::padded((size_t)ws.n_pad * 64) + lr::padded(sizeof(float) * slots) +
-                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals);
+                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals) + lr::padded(sizeof(int4) * (size_t)kTcEventCap * tc_regions()) + lr::padded(sizeof(unsigned) * tc_regions());
     if (gc)
         bytes += lr::padded(sizeof(unsigned long long) * slots) + lr::padded(sizeof(int32_t) * (n > 0 ? n : 1)) +
                  lr::padded(sizeof(double) * 12 * kGcMaxTrials) + lr::padded(sizeof(unsigned long long) * kGcMaxTrials) +
@@ -1451,6 +1457,8 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     ws.Bimg = reinterpret_cast<uint4 *>(cv.take<char>((size_t)ws.n_pad * 64));
     ws.band = cv.take<float>(slots);
     ws.partial = cv.take<double>((size_t)kFinBlocksMax * kFinVals);
+    ws.events = cv.take<int4>((size_t)kTcEventCap * tc_regions());
+    ws.ev_count = cv.take<unsigned>(tc_regions());
     ws.q64 = gc ? cv.take<unsigned long long>(slots) : nullptr;
     ws.lo_L = gc ? cv.take<int32_t>(n > 0 ? n : 1) : nullptr;
     ws.tr_T = gc ? cv.take<double>(12 * kGcMaxTrials) : nullptr;
@@ -1583,7 +1591,9 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
             // persistent CTAs, one per SM (TMEM: 4 x 96 accumulator columns; 57 KB of operand staging)
             LR_CUDA_TRY(tc_smem_attr());
             tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl,
-                                                                                 ws.m64, ws.band, ws.cnt, thr2, nullptr);
+                                                                                 ws.m64, ws.band, ws.cnt, thr2, nullptr,
+                                                                                 ws.events, ws.ev_count, kTcEventCap);
+            tcs::k_tc_events<<<sms, 32 * tcs::NEPI, 0, st>>>(ws.P8, ws.ctl, ws.m64, ws.cnt, thr2, ws.events, ws.ev_count, kTcEventCap);
         } else if (g_score_mode == 2) {
             // fp32 sweep: 16 resident one-warp CTAs per SM (128 registers per thread fill the register file; 12 KB of
             // staging each): no CTA-level barrier couples warps whose early-out rates differ
@@ -1849,7 +1859,10 @@ __global__ void k_probe_install(const double *__restrict__ models, int H, const 
                                 int *__restrict__ cnt, double *__restrict__ E_out)
 {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h == 0) ctl->n_surv = H;
+    if (h == 0) {
+        ctl->n_surv = H;
+        ctl->n_events = 0u;
+    }
     if (h >= H) return;
     double cen[3], cenq[3], T[12], tt[3];
     tcs::tc_centre(P8, cen, cenq);
@@ -1871,6 +1884,16 @@ __global__ void k_probe_install(const double *__restrict__ models, int H, const 
 }
 
 }  // namespace
+
+#ifdef LR_TCS_TRACE
+// trace builds only (tools/tcs_trace.py): the pipeline timestamps CTA 0 of the last tensor sweep recorded
+LR_EXPORT int lr_debug_tcs_trace(long long *out, int64_t bytes)
+{
+    LR_REQUIRE(out && bytes == (int64_t)sizeof(tcs::g_tcs_trace), "buffer size mismatch");
+    LR_CUDA_TRY(cudaMemcpyFromSymbol(out, tcs::g_tcs_trace, sizeof(tcs::g_tcs_trace)));
+    return LR_OK;
+}
+#endif
 
 LR_EXPORT int lr_ransac_set_mode(int mode)
 {
@@ -2032,10 +2055,11 @@ LR_EXPORT int lr_ransac_tc_probe(const float *src, const float *tgt, int64_t n, 
                                                            ws.cnt, E_out);
     if (d_out)
         tcs::k_score_tc<true><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl, ws.m64,
-                                                                            ws.band, ws.cnt, thr2, d_out);
+                                                                            ws.band, ws.cnt, thr2, d_out, ws.events, ws.ev_count, kTcEventCap);
     if (counts_out) {
         tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl, ws.m64,
-                                                                             ws.band, ws.cnt, thr2, nullptr);
+                                                                             ws.band, ws.cnt, thr2, nullptr, ws.events, ws.ev_count, kTcEventCap);
+        tcs::k_tc_events<<<sms, 32 * tcs::NEPI, 0, st>>>(ws.P8, ws.ctl, ws.m64, ws.cnt, thr2, ws.events, ws.ev_count, kTcEventCap);
         LR_CUDA_TRY(cudaMemcpyAsync(counts_out, ws.cnt, sizeof(int32_t) * H, cudaMemcpyDeviceToDevice, st));
     }
     LR_CUDA_TRY(cudaGetLastError());

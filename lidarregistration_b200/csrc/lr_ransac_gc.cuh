@@ -185,7 +185,7 @@ __global__ void k_round_end_msac(Ctl *ctl, int64_t round_len, const int *__restr
     g.round_q = 0ULL;
     g.round_pick = ~0ULL;
     ctl->n_surv = 0;
-    ctl->n_flag = 0;
+    ctl->n_events = 0u;
     if (need && g.has_model && g.best_inl >= (long long)need[round_idx]) ctl->done = 1;
 }
 

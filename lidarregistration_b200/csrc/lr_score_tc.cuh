@@ -6,7 +6,7 @@
 // GCRANSAC::run behind GC-RANSAC/src/pygcransac/src/gcransac_python.cpp:507-533) for LR_SCORE_COUNT runs.
 //
 // The three components of a residual, d_a = sum_b R_ab p_b + t_a - q_a, are K <= 16 dot products between a
-// per-hypothesis row and a per-correspondence column, i.e. three [128 hypotheses] x [16] x [32 correspondences]
+// per-hypothesis row and a per-correspondence column, i.e. three [128 hypotheses] x [16] x [64 correspondences]
 // MMAs per tile.  Unlike the bilinear form of r^2 itself nothing cancels: every term is at most a coordinate
 // (~100 m), so fp16 operand pieces and the fp32 accumulator leave d_a within E ~ 1e-4 m of the canonical fp64
 // value, a band of ~4e-4 m^2 around thr^2 -- about one residual per hypothesis and 30k correspondences falls
@@ -23,36 +23,52 @@
 //              a tile share core0: 64 B per correspondence instead of 96.
 //              Coordinates are taken relative to (c, c') = the first correspondence rounded to 1024 m
 //              (t~ = t + R c - c'), so map-frame offsets do not eat the fp16 range.
-//   staging    cp.async.bulk (UBLKCP): 12 KB hypothesis block per work item (double buffered), 8 KB stages of
+//   staging    cp.async.bulk (UBLKCP): 12 KB hypothesis block per segment (double buffered), 8 KB stages of
 //              128 correspondences (4-deep ring), completion on mbarriers
-//   MMA        one elected lane: tcgen05.mma.cta_group::1.kind::f16, M 128, N 32, K 16, three per tile (a = 0,1,2)
-//              into a 96-column TMEM stage; four stages
-//   epilogue   16 warps = 4 classes x 4 TMEM lane quadrants; class k owns TMEM stage k = sub-tile k of every
-//              128-correspondence stage.  Thread = hypothesis: tcgen05.ld 32x32b.x16 of the three regions,
+//   MMA        one elected lane: tcgen05.mma.cta_group::1.kind::f16, M 128, N 64, K 16, three per tile (a = 0,1,2)
+//              into a 192-column TMEM buffer; two buffers (sub-tile j of every 128-correspondence stage -> buffer j).
+//              The issue loop is unrolled over the four stages of the B ring: addresses, parities and descriptor
+//              offsets are static.
+//   epilogue   16 warps = 4 TMEM lane quadrants x 4 slices of 16 columns; EVERY warp takes its slice of EVERY tile,
+//              so each warp has two tiles of look-ahead (the other buffer is filled while it computes).
+//              Thread = hypothesis: tcgen05.ld 32x32b.x16 of the three regions, buffer handed back at once,
 //              u = d0^2 + d1^2 + d2^2 - thr^2 as three packed fma.rn.f32x2 per two residuals,
-//              count += sign bit (LEA.HI), running min |u| (FMNMX3): 3 issue slots per residual.
+//              count += sign bit (LEA.HI), running min |u| (FMNMX3): 3.25 issue slots per residual.
 //              min |u| < delta_h somewhere in the warp -> the 16 columns are checked one by one and the in-band
-//              ones decided with the canonical fp64 residual (rare: ~5e-5 of the residuals).
-// Work item = (128 survivors) x (range of 128-correspondence stages), round-robin over persistent CTAs; partial
-// counts merge through integer atomics.
+//              ones decided with the canonical fp64 residual (rare: ~1e-4 of the residuals).
+//              (First version: N 32, four single-buffered 96-column stages each owned by one class of warps -- the
+//              arrive -> issue -> MMA -> commit -> wake -> tcgen05.ld round trip of a class was exposed every tile and
+//              the issue loop cost ~240 cycles per tile: 41 % issue utilisation, tensor pipe 12 % active,
+//              profiles/r2_ncu_k_score_tc_v1.txt.)
+// Work of a CTA = an equal share (+-1 stage) of the linearised (128-survivor block, 128-correspondence stage) space,
+// persistent CTAs, one per SM; partial counts merge through integer atomics.
 #pragma once
 // (cuda_fp16.h is included by lr_ransac.cu at file scope: this header sits inside its anonymous namespace)
 
 namespace tcs {
 
 constexpr int TM = 128;                 // hypotheses per row block (UMMA M)
-constexpr int TN = 32;                  // correspondences per MMA tile (UMMA N)
+#ifndef LR_TCS_TN
+#define LR_TCS_TN 32
+#endif
+constexpr int TN = LR_TCS_TN;           // correspondences per MMA tile (UMMA N): 16, 32 or 64
 constexpr int BROWS = 128;              // correspondences per shared-memory stage (== kChunk)
-constexpr int TILES_PER_STAGE = BROWS / TN;   // 4 == number of epilogue classes == TMEM stages
+constexpr int TILES_PER_STAGE = BROWS / TN;   // == number of TMEM buffers: sub-tile j of every stage lives in buffer j
 constexpr int B_GROUP_BYTES = 512;      // 8 correspondences: core0 + 3 x core1_a
 constexpr int B_STAGE_BYTES = BROWS / 8 * B_GROUP_BYTES;  // 8 KB
 constexpr int B_STAGES = 4;
 constexpr int A_PART_BYTES = TM / 8 * 256;     // one residual component: 16 groups x (core0 + core1) = 4 KB
 constexpr int A_BLOCK_BYTES = 3 * A_PART_BYTES;  // 12 KB per 128 hypotheses
-constexpr int NCLASS = TILES_PER_STAGE;
-constexpr int TMEM_STAGE_COLS = 3 * TN;  // 96
-constexpr int WARP_PRODUCER = 4 * NCLASS, WARP_MMA = 4 * NCLASS + 1;
-constexpr int NTHREADS = 32 * (4 * NCLASS + 2);
+constexpr int NBUF = TILES_PER_STAGE;
+constexpr int TMEM_BUF_COLS = 3 * TN;   // the three residual components of a tile (NBUF x 3 x TN = 384 columns in all)
+constexpr int NEPI = 16;                // epilogue warps: 4 TMEM lane quadrants x NGROUP tile groups x NSLICE column slices
+constexpr int NSLICE = TN / 16;         // a warp takes 16 columns of a tile (48 accumulator registers)
+constexpr int NGROUP = 4 / NSLICE;      // group g takes the tiles j = g (mod NGROUP) of every stage: while one group
+                                        // computes, another is free to pick the next tile up the moment it is ready
+static_assert(TN == 16 || TN == 32 || TN == 64, "tile width");
+constexpr int NMMA = TILES_PER_STAGE;    // MMA-issuing warps: warp WARP_MMA + j owns sub-tile j / TMEM buffer j of every stage
+constexpr int WARP_PRODUCER = NEPI, WARP_MMA = NEPI + 1;
+constexpr int NTHREADS = 32 * (NEPI + 1 + NMMA);
 constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr float kRangeLimit = 15000.f;  // |p~|, |q~| above this: the fp16 pieces could overflow -> fp64 fallback
 constexpr double kAccKappa = 16.0;      // tensor-core accumulation error <= kappa * 2^-24 * sum |terms|
@@ -110,26 +126,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 {
     return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
-// one tile: D_a = A_a . B_a for a = 0,1,2 (no accumulate), then the accumulator-ready commit
-__device__ __forceinline__ void tc_issue_tile(uint32_t d, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t b0, uint64_t b1,
-                                              uint64_t b2, uint32_t bar_full)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred e, f;\n\t"
-        ".reg .b32 d1, d2;\n\t"
-        "elect.sync _|e, 0xffffffff;\n\t"
-        "setp.ne.b32 f, 0, 0;\n\t"
-        "add.u32 d1, %0, 32;\n\t"
-        "add.u32 d2, %0, 64;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %7, {%8, %8, %8, %8}, f;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [d1], %2, %5, %7, {%8, %8, %8, %8}, f;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [d2], %3, %6, %7, {%8, %8, %8, %8}, f;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-        "}" ::"r"(d),
-        "l"(a0), "l"(a1), "l"(a2), "l"(b0), "l"(b1), "l"(b2), "r"(IDESC), "r"(0u), "r"(bar_full)
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
@@ -153,6 +149,37 @@ __device__ __forceinline__ void tmem_ld_wait3(uint32_t (&a)[16], uint32_t (&b)[1
                    "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
                  :
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait3x8(uint32_t (&a)[8], uint32_t (&b)[8], uint32_t (&c)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                   "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(c[0]), "+r"(c[1]),
+                   "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])
+                 :
+                 : "memory");
+}
+// non-blocking probe of a barrier phase (the result is consumed later: its latency hides under the work in between)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t addr, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok;
 }
 __device__ __forceinline__ u64 pk2(uint32_t lo, uint32_t hi)
 {
@@ -264,23 +291,49 @@ __device__ __forceinline__ double tc_err_bound(double P2, double Q, double tinf)
 }
 
 // ---------------------------------------------------------------- the sweep
+// -DLR_TCS_TRACE: CTA 0 records clock64() of its warps' pipeline events for stages [kTraceFrom, kTraceFrom + kTraceLen)
+// (tools/tcs_trace.py reads them back through lr_debug_tcs_trace)
+#ifdef LR_TCS_TRACE
+constexpr int kTraceFrom = 160, kTraceLen = 24;
+__device__ long long g_tcs_trace[NEPI + 1 + NMMA][kTraceLen][TILES_PER_STAGE][4];
+#define TCS_TRACE(stage, j, ev)                                                                       \
+    do {                                                                                              \
+        const int ts_ = (int)(stage) - kTraceFrom;                                                    \
+        if (blockIdx.x == 0 && lane == 0 && ts_ >= 0 && ts_ < kTraceLen) g_tcs_trace[warp][ts_][j][ev] = clock64(); \
+    } while (0)
+#else
+#define TCS_TRACE(stage, j, ev)
+#endif
+
 struct __align__(8) Smem {
-    uint64_t a_full[2], a_empty[2], b_full[B_STAGES], b_empty[B_STAGES], t_full[NCLASS], t_empty[NCLASS];
+    uint64_t a_full[2], a_empty[2], b_full[B_STAGES], b_empty[B_STAGES], t_full[NBUF], t_empty[NBUF];
     uint32_t tmem_base;
 };
 
-struct Split {
-    int nhb, nps, cpp, nitems;
+// Work of a CTA = a contiguous range of the linearised (hypothesis block, correspondence stage) space, so every CTA
+// gets the same number of stages (+-1); a range is walked as segments = (one hypothesis block) x (stage range).
+struct Range {
+    long long pos, end;   // linear stage index hb * nchunks + c
 };
-__device__ __forceinline__ Split make_split(int nsurv, int nchunks, int grid)
+__device__ __forceinline__ Range cta_range(int nsurv, int nchunks)
 {
-    Split s;
-    s.nhb = (nsurv + TM - 1) / TM;
-    int nps = s.nhb > 0 ? (6 * grid + s.nhb - 1) / s.nhb : 1;
-    nps = nps < 1 ? 1 : (nps > nchunks ? nchunks : nps);
-    s.cpp = (nchunks + nps - 1) / nps;  // 128-correspondence stages per item
-    s.nps = (nchunks + s.cpp - 1) / s.cpp;
-    s.nitems = s.nhb * s.nps;
+    const long long nhb = (nsurv + TM - 1) / TM;
+    const long long W = nhb * nchunks;
+    Range r;
+    r.pos = W * blockIdx.x / gridDim.x;
+    r.end = W * (blockIdx.x + 1) / gridDim.x;
+    return r;
+}
+struct Seg {
+    int hb, c_lo, c_hi;
+};
+__device__ __forceinline__ Seg seg_at(long long pos, long long end, int nchunks)
+{
+    Seg s;
+    s.hb = (int)(pos / nchunks);
+    s.c_lo = (int)(pos - (long long)s.hb * nchunks);
+    const long long left = end - pos;
+    s.c_hi = (long long)(nchunks - s.c_lo) <= left ? nchunks : s.c_lo + (int)left;
     return s;
 }
 
@@ -294,13 +347,59 @@ __device__ __noinline__ int tc_exact_inlier(const float4 *__restrict__ P8, int64
     return res2_f64(T, p[0], p[1], p[2], q[0], q[1], q[2]) < thr2 ? 1 : 0;
 }
 
+// one tile (TN correspondences): D_a = A_a . B_a for a = 0,1,2 (no accumulate) into three TN-column regions of a TMEM
+// buffer, then the accumulator-ready commit
+__device__ __forceinline__ void tc_issue_tile(uint32_t d, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t b0, uint64_t b1,
+                                              uint64_t b2, uint32_t bar_full)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e, f;\n\t"
+        ".reg .b32 d1, d2;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 f, 0, 0;\n\t"
+        "add.u32 d1, %0, %10;\n\t"
+        "add.u32 d2, %0, %11;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %7, {%8, %8, %8, %8}, f;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [d1], %2, %5, %7, {%8, %8, %8, %8}, f;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [d2], %3, %6, %7, {%8, %8, %8, %8}, f;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+        "}" ::"r"(d),
+        "l"(a0), "l"(a1), "l"(a2), "l"(b0), "l"(b1), "l"(b2), "r"(IDESC), "r"(0u), "r"(bar_full), "n"(TN), "n"(2 * TN)
+        : "memory");
+}
+// the MMA warps' wait: suspending by default; LR_TCS_SPIN=1 polls instead (A/B: polling steals issue slots from the
+// epilogue warps of the same sub-partition, whose slowest member gates every buffer release)
+#ifndef LR_TCS_SPIN
+#define LR_TCS_SPIN 0
+#endif
+__device__ __forceinline__ void mbar_wait_mma(uint32_t addr, uint32_t parity)
+{
+#if LR_TCS_SPIN
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "TCS_SPIN_LOOP:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni TCS_SPIN_DONE;\n\t"
+        "bra.uni TCS_SPIN_LOOP;\n\t"
+        "TCS_SPIN_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity)
+        : "memory");
+#else
+    mbar_wait(addr, parity);
+#endif
+}
+
 // DUMP: write the three tensor-core residual components of every (slot, correspondence) to `dump`
 // ([slot][n_pad][3] floats) instead of counting -- the error-bound probe of tests/test_gpu_score_tc.py
 template <bool DUMP>
+// (21 warps are allocated as 24 -- the register file is handed out four warps at a time -- so TN = 32 with its four MMA
+// warps gets 80 registers per thread; __maxnreg__(96) compiles but the launch fails)
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const float4 *__restrict__ P8, int64_t n,
            int64_t n_pad, Ctl *ctl, const double *__restrict__ m64, const float *__restrict__ band, int *__restrict__ cnt,
-           double thr2, float *__restrict__ dump)
+           double thr2, float *__restrict__ dump, int4 *__restrict__ events, unsigned *__restrict__ ev_count, unsigned ev_cap)
 {
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
@@ -334,21 +433,21 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
     uint8_t *sA = smem_raw;                             // 2 x 12 KB
     uint8_t *sB = smem_raw + 2 * A_BLOCK_BYTES;         // B_STAGES x 8 KB
     Smem *sm = reinterpret_cast<Smem *>(smem_raw + 2 * A_BLOCK_BYTES + B_STAGES * B_STAGE_BYTES);
-    const Split sp = make_split(nsurv, nchunks, (int)gridDim.x);
+    const Range rg = cta_range(nsurv, nchunks);
 
     if (warp == WARP_MMA) {
         if (lane == 0) {
             for (int k = 0; k < 2; ++k) {
                 mbar_init(&sm->a_full[k], 1);
-                mbar_init(&sm->a_empty[k], 1);
+                mbar_init(&sm->a_empty[k], NMMA);
             }
             for (int k = 0; k < B_STAGES; ++k) {
                 mbar_init(&sm->b_full[k], 1);
-                mbar_init(&sm->b_empty[k], 1);
+                mbar_init(&sm->b_empty[k], NMMA);
             }
-            for (int k = 0; k < NCLASS; ++k) {
+            for (int k = 0; k < NBUF; ++k) {
                 mbar_init(&sm->t_full[k], 1);
-                mbar_init(&sm->t_empty[k], 4);  // the four warps (lane quadrants) of class k
+                mbar_init(&sm->t_empty[k], 4 * NSLICE);  // the warps (quadrant x slice) that read this tile
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -367,16 +466,15 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
         // ===== producer: bulk copies of the hypothesis block and the correspondence stages =====
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
-            for (int item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
-                const int hb = item / sp.nps, ps = item - hb * sp.nps;
-                const int c_lo = ps * sp.cpp, c_hi = min(nchunks, c_lo + sp.cpp);
+            for (long long pos = rg.pos; pos < rg.end;) {
+                const Seg sg = seg_at(pos, rg.end, nchunks);
                 const uint32_t ab = a_it & 1u;
                 mbar_wait(smem_u32(&sm->a_empty[ab]), ((a_it >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(smem_u32(&sm->a_full[ab]), A_BLOCK_BYTES);
-                bulk_g2s(smem_u32(sA + ab * A_BLOCK_BYTES), reinterpret_cast<const uint8_t *>(Aimg) + (size_t)hb * A_BLOCK_BYTES,
+                bulk_g2s(smem_u32(sA + ab * A_BLOCK_BYTES), reinterpret_cast<const uint8_t *>(Aimg) + (size_t)sg.hb * A_BLOCK_BYTES,
                          A_BLOCK_BYTES, smem_u32(&sm->a_full[ab]));
                 ++a_it;
-                for (int c = c_lo; c < c_hi; ++c) {
+                for (int c = sg.c_lo; c < sg.c_hi; ++c) {
                     const uint32_t s = b_it % B_STAGES;
                     mbar_wait(smem_u32(&sm->b_empty[s]), ((b_it / B_STAGES) & 1u) ^ 1u);
                     mbar_expect_tx(smem_u32(&sm->b_full[s]), B_STAGE_BYTES);
@@ -384,83 +482,128 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                              B_STAGE_BYTES, smem_u32(&sm->b_full[s]));
                     ++b_it;
                 }
+                pos += sg.c_hi - sg.c_lo;
             }
         }
-    } else if (warp == WARP_MMA) {
-        // ===== MMA issuer: warp-uniform loop, elect.sync picks the lane =====
-        const uint32_t a_full = smem_u32(&sm->a_full[0]), a_empty = smem_u32(&sm->a_empty[0]);
-        const uint32_t b_full = smem_u32(&sm->b_full[0]), b_empty = smem_u32(&sm->b_empty[0]);
-        const uint32_t t_full = smem_u32(&sm->t_full[0]), t_empty = smem_u32(&sm->t_empty[0]);
-        uint32_t a_it = 0, b_it = 0;
-        for (int item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
-            const int ps = item % sp.nps;
-            const int c_lo = ps * sp.cpp, c_hi = min(nchunks, c_lo + sp.cpp);
-            const uint32_t ab = a_it & 1u;
-            mbar_wait(a_full + ab * 8u, (a_it >> 1) & 1u);
-            const uint32_t a_addr = smem_u32(sA + ab * A_BLOCK_BYTES);
-            const uint64_t ad0 = smem_desc(a_addr, 128, 256), ad1 = smem_desc(a_addr + A_PART_BYTES, 128, 256),
-                           ad2 = smem_desc(a_addr + 2 * A_PART_BYTES, 128, 256);
-            for (int c = c_lo; c < c_hi; ++c) {
-                const uint32_t s = b_it % B_STAGES;
-                mbar_wait(b_full + s * 8u, (b_it / B_STAGES) & 1u);
-                const uint32_t b_addr = smem_u32(sB + s * B_STAGE_BYTES);
+    } else if (warp >= WARP_MMA) {
+        // ===== MMA issuers: warp WARP_MMA + j issues sub-tile j of every stage into TMEM buffer j.  Warp-uniform loops,
+        // elect.sync picks the lane; unrolled over the four stages of the B ring, so stage, barrier addresses, parities
+        // and descriptors are static.  One issuing warp was the sweep's bottleneck (tools/tcs_trace.py,
+        // profiles/r2_tcs_trace_*.txt): every barrier operation of a warp costs ~100 cycles of latency, and a stage
+        // needs a b_full wait + per tile (t_empty wait, issue, commit) -- ~1100 cycles per stage in series whatever the
+        // tile width.  One warp per tile runs those chains side by side.
+        static_assert(B_STAGES == 4, "the issue loop is unrolled over the 4 stages of the B ring");
+        const int j = warp - WARP_MMA;
+        if (rg.pos < rg.end) {
+            const uint32_t a_full = smem_u32(&sm->a_full[0]), a_empty = smem_u32(&sm->a_empty[0]);
+            const uint32_t b_full = smem_u32(&sm->b_full[0]), b_empty = smem_u32(&sm->b_empty[0]);
+            const uint32_t t_full = smem_u32(&sm->t_full[j]), t_empty = smem_u32(&sm->t_empty[j]);
+            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB) + j * (TN / 8) * B_GROUP_BYTES;
+            const uint32_t d_tmem = tmem_base + j * TMEM_BUF_COLS;
+            // B: K-adjacent cores core0 -> core1_a are 128 (1 + a) bytes apart, 8-correspondence groups 512 bytes apart
+            const uint64_t bd0 = smem_desc(b_addr, 128, B_GROUP_BYTES), bd1 = smem_desc(b_addr, 256, B_GROUP_BYTES),
+                           bd2 = smem_desc(b_addr, 384, B_GROUP_BYTES);
+            uint64_t ad0 = smem_desc(a_addr, 128, 256), ad1 = smem_desc(a_addr + A_PART_BYTES, 128, 256),
+                     ad2 = smem_desc(a_addr + 2 * A_PART_BYTES, 128, 256);
+            uint32_t a_it = 0, pb = 0;
+            long long pos = rg.pos;
+            Seg sg = seg_at(pos, rg.end, nchunks);
+            int left = sg.c_hi - sg.c_lo;
+#ifdef LR_TCS_TRACE
+            int st_no = 0;
+#endif
+            mbar_wait_mma(a_full, 0u);
+            bool done = false;
+            while (!done) {
 #pragma unroll
-                for (int j = 0; j < TILES_PER_STAGE; ++j) {
-                    // TMEM stage j is free once class j has loaded the previous stage's sub-tile j into registers
-                    mbar_wait(t_empty + j * 8u, (b_it & 1u) ^ 1u);
+                for (int s = 0; s < B_STAGES; ++s) {
+                    // descriptors of this stage: the 14-bit address field counts 16-byte units, a plain add
+                    const uint64_t off = (uint64_t)((s * B_STAGE_BYTES) >> 4);
+                    const uint64_t x0 = bd0 + off, x1 = bd1 + off, x2 = bd2 + off;
+                    TCS_TRACE(st_no, j, 0);
+                    mbar_wait_mma(b_full + s * 8u, pb);
+                    // TMEM buffer j is free once its readers hold the previous stage's sub-tile j in registers
+                    mbar_wait_mma(t_empty, (uint32_t)(s & 1) ^ 1u);
+                    TCS_TRACE(st_no, j, 1);
                     tc_fence_after();
-                    const uint32_t bj = b_addr + j * (TN / 8) * B_GROUP_BYTES;
-                    tc_issue_tile(tmem_base + j * TMEM_STAGE_COLS, ad0, ad1, ad2, smem_desc(bj, 128, B_GROUP_BYTES),
-                                  smem_desc(bj, 256, B_GROUP_BYTES), smem_desc(bj, 384, B_GROUP_BYTES), t_full + j * 8u);
+                    tc_issue_tile(d_tmem, ad0, ad1, ad2, x0, x1, x2, t_full);
+                    tc_commit_elect(b_empty + s * 8u);  // the stage's bytes are reusable once the MMAs of all tiles have read them
+                    TCS_TRACE(st_no, j, 2);
+#ifdef LR_TCS_TRACE
+                    ++st_no;
+#endif
+                    if (--left == 0) {
+                        tc_commit_elect(a_empty + (a_it & 1u) * 8u);
+                        ++a_it;
+                        pos += sg.c_hi - sg.c_lo;
+                        if (pos >= rg.end) {
+                            done = true;
+                            break;
+                        }
+                        sg = seg_at(pos, rg.end, nchunks);
+                        left = sg.c_hi - sg.c_lo;
+                        mbar_wait_mma(a_full + (a_it & 1u) * 8u, (a_it >> 1) & 1u);
+                        const uint32_t aa = a_addr + (a_it & 1u) * A_BLOCK_BYTES;
+                        ad0 = smem_desc(aa, 128, 256);
+                        ad1 = smem_desc(aa + A_PART_BYTES, 128, 256);
+                        ad2 = smem_desc(aa + 2 * A_PART_BYTES, 128, 256);
+                    }
                 }
-                tc_commit_elect(b_empty + s * 8u);  // the stage's bytes are reusable once these MMAs have read them
-                ++b_it;
+                pb ^= 1u;
             }
-            tc_commit_elect(a_empty + ab * 8u);
-            ++a_it;
         }
     } else {
         // ===== epilogue: TMEM -> registers -> counts =====
-        const int q = warp & 3;    // TMEM lane quadrant this warp may read
-        const int cls = warp >> 2;  // class = TMEM stage = sub-tile of every correspondence stage
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cls * TMEM_STAGE_COLS;
-        const uint32_t full_addr = smem_u32(&sm->t_full[cls]), empty_addr = smem_u32(&sm->t_empty[cls]);
+        // (Tried and dropped: 8-column units whose registers ping-pong so that the next tcgen05.ld is in flight while
+        // the current unit is counted, with an early non-blocking probe of the next t_full phase -- 0.57 ms instead of
+        // 0.36 ms at cfg 3: the longer serial code per slice cost more than the hidden latencies saved.)
+        const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+        const int grp = (warp >> 2) % NGROUP;    // which tiles of a stage
+        const int cs = (warp >> 2) / NGROUP;     // which 16 of a tile's columns
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cs * 16;
+        const uint32_t t_full = smem_u32(&sm->t_full[0]), t_empty = smem_u32(&sm->t_empty[0]);
         const float nthr2 = -(float)thr2;
         const u64 nthr2p = pk2(__float_as_uint(nthr2), __float_as_uint(nthr2));
         unsigned long long *n_rechecked = reinterpret_cast<unsigned long long *>(&ctl->n_rechecked);
-        uint32_t t_it = 0;
-        for (int item = blockIdx.x; item < sp.nitems; item += gridDim.x) {
-            const int hb = item / sp.nps, ps = item - hb * sp.nps;
-            const int c_lo = ps * sp.cpp, c_hi = min(nchunks, c_lo + sp.cpp);
-            const int slot = hb * TM + q * 32 + lane;
+        uint32_t t_it = 0;  // stages consumed (each stage = one use of each TMEM buffer)
+        // this warp's private list of in-band residuals (slot, correspondence)
+        const int region = blockIdx.x * NEPI + warp;
+        int4 *ev_mine = events + (size_t)region * ev_cap;
+        unsigned ev_n = 0;
+        for (long long pos = rg.pos; pos < rg.end;) {
+            const Seg sg = seg_at(pos, rg.end, nchunks);
+            const int slot = sg.hb * TM + q * 32 + lane;
             const bool valid = slot < nsurv;
             const float delta = valid ? band[slot] : -1.f;  // rows past the survivor count hold stale models
-            int count = 0;
+            int count = 0, count_b = 0;
             unsigned evals = 0;
-            for (int c = c_lo; c < c_hi; ++c) {
-                mbar_wait(full_addr, t_it & 1u);
-                tc_fence_after();
-                const int64_t col0 = (int64_t)c * BROWS + cls * TN;
+            for (int c = sg.c_lo; c < sg.c_hi; ++c) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int jj = 0; jj < TILES_PER_STAGE / NGROUP; ++jj) {
+                    const int j = grp + jj * NGROUP;
+                    TCS_TRACE(t_it, j, 0);
+                    mbar_wait(t_full + j * 8u, t_it & 1u);
+                    TCS_TRACE(t_it, j, 1);
+                    tc_fence_after();
+                    const int64_t col0 = (int64_t)c * BROWS + j * TN + cs * 16;
                     uint32_t d0[16], d1[16], d2[16];
-                    tmem_ld16_issue(taddr + half * 16, d0);
-                    tmem_ld16_issue(taddr + TN + half * 16, d1);
-                    tmem_ld16_issue(taddr + 2 * TN + half * 16, d2);
+                    tmem_ld16_issue(taddr + j * TMEM_BUF_COLS, d0);
+                    tmem_ld16_issue(taddr + j * TMEM_BUF_COLS + TN, d1);
+                    tmem_ld16_issue(taddr + j * TMEM_BUF_COLS + 2 * TN, d2);
                     tmem_ld_wait3(d0, d1, d2);
-                    if (half == 1) {  // everything of this tile is in registers: hand the TMEM stage back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty_addr);
-                    }
+                    // this warp's share of the tile is in registers: hand the TMEM buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + j * 8u);
+                    TCS_TRACE(t_it, j, 2);
                     if (DUMP) {
                         if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float *o = dump + ((size_t)slot * n_pad + (col0 + half * 16 + j)) * 3;
-                                o[0] = __uint_as_float(d0[j]);
-                                o[1] = __uint_as_float(d1[j]);
-                                o[2] = __uint_as_float(d2[j]);
+                            for (int k = 0; k < 16; ++k) {
+                                float *o = dump + ((size_t)slot * n_pad + (col0 + k)) * 3;
+                                o[0] = __uint_as_float(d0[k]);
+                                o[1] = __uint_as_float(d1[k]);
+                                o[2] = __uint_as_float(d2[k]);
                             }
                         }
                         continue;
@@ -468,43 +611,60 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                     u64 u[8];
                     float mn = INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const u64 e0 = pk2(d0[2 * j], d0[2 * j + 1]), e1 = pk2(d1[2 * j], d1[2 * j + 1]),
-                                  e2 = pk2(d2[2 * j], d2[2 * j + 1]);
-                        u[j] = fma2(e2, e2, fma2(e1, e1, fma2(e0, e0, nthr2p)));
+                    for (int k = 0; k < 8; ++k) {
+                        const u64 e0 = pk2(d0[2 * k], d0[2 * k + 1]), e1 = pk2(d1[2 * k], d1[2 * k + 1]),
+                                  e2 = pk2(d2[2 * k], d2[2 * k + 1]);
+                        u[k] = fma2(e2, e2, fma2(e1, e1, fma2(e0, e0, nthr2p)));
                         float ua, ub;
-                        upk2(u[j], ua, ub);
-                        count += (int)(__float_as_uint(ua) >> 31) + (int)(__float_as_uint(ub) >> 31);
+                        upk2(u[k], ua, ub);
+                        count += (int)(__float_as_uint(ua) >> 31);      // two chains: the LEA.HI adds of a tile do not
+                        count_b += (int)(__float_as_uint(ub) >> 31);    // form one 16-long dependency
                         mn = min3abs(mn, ua, ub);
                     }
                     if (__any_sync(0xffffffffu, mn < delta)) {
-                        // rare: some residual of these 16 columns is within the error band of some hypothesis
+                        // rare: some residual of these 16 columns is within the error band of some hypothesis.  The warp
+                        // only RECORDS which (bit k: |u_k| < delta) and what the tensor-core sign said, one 16-byte
+                        // record per affected lane in the warp's private list -- no loads, no atomics, no divergent
+                        // loop: a warp that is late for its next tile stalls every warp behind the same TMEM buffer
+                        // (58 % of the tiles had such a straggler at cfg 3 when this path decided in fp64 on the spot).
+                        // k_tc_events decides the listed residuals in fp64 and adds (exact - sign) to the count.
+                        unsigned bm = 0u, sg_bits = 0u;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
+                        for (int k = 0; k < 16; ++k) {
                             float ua, ub;
-                            upk2(u[j], ua, ub);
-                            if (fabsf(ua) < delta) {
-                                count -= (int)(__float_as_uint(ua) >> 31);
-                                count += tc_exact_inlier(P8, col0 + half * 16 + 2 * j, m64 + (size_t)slot * 12, thr2);
-                                ++evals;
-                            }
-                            if (fabsf(ub) < delta) {
-                                count -= (int)(__float_as_uint(ub) >> 31);
-                                count += tc_exact_inlier(P8, col0 + half * 16 + 2 * j + 1, m64 + (size_t)slot * 12, thr2);
-                                ++evals;
+                            upk2(u[k >> 1], ua, ub);
+                            const float uk = (k & 1) ? ub : ua;
+                            bm |= (fabsf(uk) < delta ? 1u : 0u) << k;
+                            sg_bits |= (__float_as_uint(uk) >> 31) << k;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, bm != 0u);
+                        if (bm != 0u) {
+                            const unsigned e = ev_n + __popc(m & ((1u << lane) - 1u));
+                            if (e < ev_cap) ev_mine[e] = make_int4(slot, (int)col0, (int)bm, (int)sg_bits);
+                            else {  // list full: decide on the spot (same result, only slower)
+                                for (unsigned b = bm; b; b &= b - 1u) {
+                                    const int k = __ffs(b) - 1;
+                                    count += tc_exact_inlier(P8, col0 + k, m64 + (size_t)slot * 12, thr2) - (int)((sg_bits >> k) & 1u);
+                                    ++evals;
+                                }
                             }
                         }
+                        ev_n += __popc(m);
                     }
+                    TCS_TRACE(t_it, j, 3);
                 }
                 ++t_it;
             }
             if (!DUMP && valid) {
-                // the four classes (sub-tiles) of a quadrant hold partial counts of the same slot: always merge
-                // (k_kabsch / k_probe_models zero cnt[] before the sweep)
+                // the column slices of a quadrant (and the CTAs that share a hypothesis block) hold partial counts of the
+                // same slot: always merge (k_kabsch / k_probe_install zero cnt[] before the sweep)
+                count += count_b;
                 if (count) atomicAdd(&cnt[slot], count);
                 if (evals) atomicAdd(n_rechecked, (unsigned long long)evals);
             }
+            pos += sg.c_hi - sg.c_lo;
         }
+        if (!DUMP && lane == 0) ev_count[region] = ev_n < ev_cap ? ev_n : ev_cap;
     }
 
     tc_fence_before();
@@ -513,6 +673,35 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// the in-band residuals the sweep listed (record = slot, first column, in-band mask, tensor-core sign bits of 16 columns),
+// decided with the canonical fp64 arithmetic; the count receives (exact - sign).  One warp per list
+// (grid = the sweep's grid, block = NEPI warps: block b reads the lists CTA b of the sweep wrote)
+__global__ void __launch_bounds__(32 * NEPI)
+k_tc_events(const float4 *__restrict__ P8, Ctl *ctl, const double *__restrict__ m64, int *__restrict__ cnt, double thr2,
+            const int4 *__restrict__ events, const unsigned *__restrict__ ev_count, unsigned ev_cap)
+{
+    if (ctl->done || ctl->n_surv <= 0) return;
+    // the sweep wrote no lists when it took its out-of-range fallback
+    if (!(__uint_as_float(ctl->pt2max_bits) < kRangeLimit && __uint_as_float(ctl->qtmax_bits) < kRangeLimit)) return;
+    const int region = blockIdx.x * NEPI + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const unsigned ne = ev_count[region];
+    const int4 *ev = events + (size_t)region * ev_cap;
+    unsigned evals = 0;
+    for (unsigned e = lane; e < ne; e += 32) {
+        const int4 v = ev[e];
+        int d = 0;
+        for (unsigned b = (unsigned)v.z; b; b &= b - 1u) {
+            const int k = __ffs(b) - 1;
+            d += tc_exact_inlier(P8, (int64_t)v.y + k, m64 + (size_t)v.x * 12, thr2) - (int)(((unsigned)v.w >> k) & 1u);
+            ++evals;
+        }
+        if (d) atomicAdd(&cnt[v.x], d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
+    if (lane == 0 && evals) atomicAdd(reinterpret_cast<unsigned long long *>(&ctl->n_rechecked), (unsigned long long)evals);
 }
 
 constexpr size_t kSmemBytes = 2 * A_BLOCK_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(Smem) + 1024 + 64;
