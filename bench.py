@@ -42,15 +42,18 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-elc", action="store_true", help="headline regime without edge-length rejection")
     ap.add_argument("--skip-extras", action="store_true", help="only the headline line (used under ncu)")
+    ap.add_argument("--mode", default="pairs", choices=["pairs", "hyp"],
+                    help="pairs: the rank's pairs, no collective (weak scaling, the default headline); hyp: the hypotheses "
+                         "of ONE pair split over the ranks (BASELINE cfg 3 as worded, strong scaling) as the headline")
     return ap.parse_args()
 
 
-def config_dict(use_elc):
+def config_dict(use_elc, pairs_per_step=PAIRS_PER_STEP):
     return {"workload": "cfg3: RANSAC --iters 1000000 on one 30k-correspondence synthetic pair, 30%% inliers, "
                         "3-point samples, ELC %s, fixed budget (confidence exit off), count scoring + LSQ refit"
                         % ("on (reference default --fast_rejection ELC)" if use_elc else "off (every hypothesis scored)"),
             "n_correspondences": N_CORR, "iters": ITERS, "inlier_ratio": INLIER_RATIO, "threshold_m": THRESH,
-            "pairs_per_step": PAIRS_PER_STEP, "elc": bool(use_elc),
+            "pairs_per_step": pairs_per_step, "elc": bool(use_elc),
             "l2": "a 512 MB buffer is written between timed steps (L2 flush); inputs are 0.72 MB per pair"}
 
 
@@ -78,7 +81,7 @@ def run_reference(args):
     if rank != 0:
         return
     use_elc = not args.no_elc
-    pairs = make_pairs(1, CFG_SEED)
+    pairs = make_pairs(PAIRS_PER_STEP, CFG_SEED)  # the same pairs rank 0 of the CUDA arm runs
     from oracle import lr_oracle as O
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
     try:
@@ -86,20 +89,20 @@ def run_reference(args):
     except (AttributeError, OSError):
         O.set_threads(os.cpu_count() or 1)
     cores = O.num_threads()
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         cpu_ransac_rate(pairs, use_elc)
     times = []
     for _ in range(args.steps):
         _, _, dt = cpu_ransac_rate(pairs, use_elc)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = 1e3 / ms
+    value = PAIRS_PER_STEP * 1e3 / ms
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(use_elc),
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": "1 pair per step at the full 1M-hypothesis budget, oracle/lr_oracle.c "
+                             "sample": "%d pairs per step at the full 1M-hypothesis budget, oracle/lr_oracle.c " % PAIRS_PER_STEP +
                                        "(OpenMP over hypotheses, fp64); the reference's native RANSAC "
                                        "(pygcransac / Open3D) is un-vendored and cannot be built here"},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -245,14 +248,14 @@ def run_ours(args):
     value = pairs_total / (ms_res * 1e-3)
     e2e_value = pairs_total / (ms_e2e * 1e-3)
     n_scored = last["n_scored"]
-    # kernels launched by one lr_ransac_rigid call: reset + pack + per batch (gen, score, resolve, recount,
-    # round_end) + model_from_key + mask_sums + refit_H + refit_solve
-    launches_per_pair = 2 + 5 * ((ITERS + (1 << 20) - 1) >> 20) + 4
+    # kernels launched by one lr_ransac_rigid call: k_ctl_reset + k_pack + per batch of <= 2^20 hypotheses (k_gen,
+    # k_kabsch, k_score_tc, k_tc_events, k_resolve_end) + k_finish
+    launches_per_pair = 2 + 5 * ((ITERS + (1 << 20) - 1) >> 20) + 1
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (inlier sweep, bracketed) + f64 (models, recount)",
-            "data": "synthetic", "config": dict(config_dict(use_elc), parallelism="pairs sharded by rank (dp%d), "
-                                                "no collective in the timed region" % world),
+            "data": "synthetic", "config": config_dict(use_elc),
+            "parallelism": "pairs sharded by rank (dp%d), no collective in the timed region" % world,
             "h_scored_per_pair": n_scored, "h_rechecked_per_pair": last["n_rechecked"],
             "best_count": last["best_count"],
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e,
@@ -260,47 +263,75 @@ def run_ours(args):
                     "d2h_bytes_per_step": PAIRS_PER_STEP * (N_CORR + 2 * 128 + 120)},
             "gpu_launches": launches_per_pair * PAIRS_PER_STEP * args.steps}
 
-    # second multi-GPU mode of the north star: the hypotheses of ONE pair split across the ranks,
-    # one 8-byte NCCL MAX all-reduce of the packed (count, id) key per round
-    if world > 1:
-        from lidarregistration_b200 import parallel
-        a0, b0 = (t.clone() for t in resident[0])
-        for t in (a0, b0):
-            dist.broadcast(t, src=0)
-        for _ in range(3):
-            parallel.ransac_rigid_sharded(a0, b0, params)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            shard_res = parallel.ransac_rigid_sharded(a0, b0, params)
-        e1.record()
-        barrier()
-        hyp_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-        line["hypothesis_sharding"] = {"ms_per_pair": hyp_ms, "pairs_per_s": 1e3 / hyp_ms, "best_count": shard_res["best_count"],
-                                       "note": "one pair, 1M hypotheses split over %d ranks, 1 all-reduce(MAX, 8 B)" % world}
+    # the same call with what the reference interface really hands over (GC_RANSAC.py:10-11): pageable numpy arrays
+    host_np = [(d["src"], d["tgt"]) for d in pairs]
+
+    def step_e2e_numpy():
+        out = None
+        for a, b in host_np:
+            out = findRigidTransform(a, b, threshold=THRESH, conf=1.0, spatial_coherence_weight=0.0,
+                                     max_iters=ITERS, use_sprt=use_elc, min_inlier_ratio_for_sprt=-1,
+                                     sampler=0, neighborhood=0, neighborhood_size=20, seed=51)
+        return out
+
+    ms_e2e_np, _ = timed(step_e2e_numpy, max(2, args.steps // 2), 1)
+    line["e2e"]["pinned_torch_inputs"] = True
+    line["e2e_numpy"] = {"value": pairs_total / (ms_e2e_np * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e_np,
+                         "note": "same call, pageable numpy arrays in (staged by engine.to_dev_f32), numpy pose + mask out"}
+
+    # second multi-GPU mode of the north star (BASELINE cfg 3 as worded): the hypotheses of ONE pair split across the
+    # ranks; the round's packed (count, id) key is exchanged inside the kernel that ends the round, through peer
+    # mailboxes over NVLink (lr_comm_init / lr_ransac_rigid_sharded); every rank regenerates the winner from the id
+    hyp = bench_hypothesis_sharding(engine, torch, dist, resident, world, rank, barrier, max_over_ranks)
+    if hyp is not None:
+        line["hypothesis_sharding"] = hyp
+        if args.mode == "hyp":
+            h = hyp["elc_on"]
+            line.update({"value": 1e3 / h["ms_per_pair"], "ms_per_step": h["ms_per_pair"], "scaling": "strong",
+                         "steps": h["reps"], "warmup": 3,
+                         "parallelism": "hypotheses of one pair sharded over %d ranks (peer-mailbox key exchange "
+                                        "inside the round-end kernel)" % world})
+            line["config"] = dict(line["config"], pairs_per_step=1)
     if rank == 0:
         line["clocks"] = clocks
-        # ---- roofline of the dominant kernel (k_score, the inlier sweep): SM FP32-bound
+        # ---- roofline of the dominant kernel: k_score_tc, the inlier sweep on tcgen05 (csrc/lr_score_tc.cuh)
         calls = prof_steps * PAIRS_PER_STEP
-        flops_per_launch = (n_scored * calls / max(score_launches, 1)) * N_CORR * FLOPS_PER_TEST
+        h_per_launch = n_scored * calls / max(score_launches, 1)
+        flops_per_launch = h_per_launch * N_CORR * FLOPS_PER_TEST          # 27 per residual test
+        n_pad = (N_CORR + 127) // 128 * 128
+        mma_flops_per_launch = ((h_per_launch + 127) // 128 * 128) * n_pad * 3 * 16 * 2  # three M128 x N x K16 MMAs per tile
         avg_ms = score_ms / max(score_launches, 1)
         achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-        peak = engine.peak_fp32(0)
-        peak2 = engine.peak_fp32(1)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tensor_peak = peaks.get("bf16_tflops_sustained", 1369.0) if peaks else 1590.0
+        fp32_peak = engine.peak_fp32(0)
+        sm_hz = (clocks["sm_mhz"] or 1965.0) * 1e6
+        # the epilogue is what the sweep is made of: 3.25 issue slots per residual (3 packed FMAs per two residuals,
+        # one sign-bit add, half a 3-input min), 32 residuals per warp instruction, 4 schedulers per SM
+        issue_frac = (h_per_launch * N_CORR * 3.25 / 32) / (148 * 4 * sm_hz * avg_ms * 1e-3) if avg_ms > 0 else None
         line["roofline"] = {
-            "kernel": "k_score (inlier sweep)", "bound": "fp32",
-            "note": "SM FP32-FMA bound (SURVEY 8(d)); neither HBM nor tensor: 24 B/correspondence live in "
-                    "shared memory and are reused by every hypothesis",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-            "peak_source": "FFMA probe measured in this run (lr_peak_fp32 mode 0); packed fma.rn.f32x2 probe: "
-                           "%.1f TFLOP/s; nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.1f" %
-                           (peak2, clocks["sm_max_mhz"] or 1965, 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965) / 1e6),
-            "traffic": ncu_traffic("r1_ncu_k_score.txt"),
-            "traffic_note": "DRAM bytes of one ncu --set full launch (profiles/r1_ncu_k_score.txt); the kernel is not "
-                            "memory bound: algorithmic bytes per launch = n x 48 B of correspondences + H_scored x 64 B of "
-                            "models",
+            "kernel": "k_score_tc (inlier sweep: tcgen05 residual components, TMEM -> register epilogue, banded fp64 recheck)"
+                      " + k_tc_events",
+            "bound": "tensor",
+            "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+            "peak_source": ("bf16_tflops_sustained of MEASURED_PEAKS.json (kernel timed inside a step)" if peaks else
+                            "fallback of B200_PROFILING.md"),
+            "note": "achieved counts the ALGORITHMIC 27 FLOP per residual test (SURVEY 8(d)); the MMAs execute 96 "
+                    "(K padded to 16, three fp16 pieces) -> mma_tflops.  Neither figure is the limiter: the sweep is bound "
+                    "by the issue slots of its TMEM -> register epilogue (issue_frac) and by the TMEM round trip "
+                    "(DESIGN.md 5.1); fp32_equiv_frac compares with the CUDA-core FP32 roofline round 1 was bound by",
+            "mma_tflops": mma_flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else None,
+            "mma_frac": mma_flops_per_launch / (avg_ms * 1e-3) / 1e12 / tensor_peak if avg_ms > 0 else None,
+            "issue_frac": issue_frac,
+            "fp32_equiv_frac": achieved / fp32_peak if fp32_peak else None, "fp32_peak_probe": fp32_peak,
+            "traffic": ncu_traffic("r2_ncu_k_score_tc.txt"),
+            "traffic_note": "DRAM bytes of one ncu --set full launch (profiles/r2_ncu_k_score_tc.txt); algorithmic bytes per "
+                            "launch = n x 64 B of correspondence operands + H_scored x (96 B operand image + 96 B fp64 model "
+                            "+ 8 B band / count), every CTA re-reads the correspondences from L2",
             "avg_launch_ms": avg_ms, "launches": score_launches,
             "share_of_step": score_ms / (ms_single * prof_steps) if ms_single else None,
             "gen_share_of_step": gen_ms / (ms_single * prof_steps) if ms_single else None,
@@ -324,10 +355,227 @@ def run_ours(args):
                                     "sample": "8 passes over one cfg-3 pair at the full 1M-hypothesis budget (%.1f s wall, "
                                               "%.0f core-seconds), oracle/lr_oracle.c, OpenMP over hypotheses, fp64"
                                               % (secs, secs * cores)}
+            line["speedup_vs_cpu"] = {"e2e": e2e_value / world / v, "resident": value / world / v, "cores": cores,
+                                      "note": "per GPU, this run's own cpu_baseline; the >= 100x target is host dependent "
+                                              "(round 1: 143x on a 16-core box, 82x on a 32-core box)"}
+            line["reference_faithful"] = bench_faithful_regime(engine, torch, resident, pairs[0])
+            line["fr_e2e"] = bench_fr(torch)
+            line["reference_libraries"] = probe_reference_libraries(pairs[0])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_hypothesis_sharding(engine, torch, dist, resident, world, rank, barrier, max_over_ranks):
+    """one cfg-3 pair, 1M hypotheses split over the ranks; ELC on (the headline regime) and off (every hypothesis
+    scored).  Rank 0 also runs the same pair through the 1-GPU entry: the N-rank result must be identical
+    (best id, best count, T, T_refit bit for bit) and the ratio of the two times is the strong-scaling speed-up."""
+    if world < 2:
+        return None
+    from lidarregistration_b200 import parallel
+    a0, b0 = (t.clone() for t in resident[0])
+    for t in (a0, b0):
+        dist.broadcast(t, src=0)
+    p2p = parallel.init_comm()
+    out = {"transport": "p2p (cudaIpc peer mailboxes, exchange fused into k_resolve_end)" if p2p else
+           "allreduce (torch.distributed MAX over NCCL)", "world": world}
+    for name, elc in (("elc_on", True), ("elc_off", False)):
+        params = engine.make_params(threshold=THRESH, confidence=1.0, max_iters=ITERS, seed=51, sample_size=3,
+                                    sampler=engine.SAMPLER_UNIFORM, use_elc=elc, refit=True)
+        reps = 20 if elc else 5
+        for _ in range(3):
+            parallel.ransac_rigid_sharded(a0, b0, params)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            res = parallel.ransac_rigid_sharded(a0, b0, params)
+        e1.record()
+        barrier()
+        hyp_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        # the 1-GPU entry on the same pair, timed on rank 0 while the other ranks wait at the barrier
+        single_ms, same = 0.0, True
+        if rank == 0:
+            for _ in range(3):
+                ref = engine.ransac_rigid(a0, b0, params)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                ref = engine.ransac_rigid(a0, b0, params)
+            e1.record()
+            torch.cuda.synchronize()
+            single_ms = e0.elapsed_time(e1) / reps
+            same = bool(res["best_id"] == ref["best_id"] and res["best_count"] == ref["best_count"] and
+                        res["iters_run"] == ref["iters_run"] and (res["T"] == ref["T"]).all() and
+                        (res["T_refit"] == ref["T_refit"]).all())
+        barrier()
+        single_ms = max_over_ranks(single_ms)
+        ok = torch.tensor([1 if same else 0], device=a0.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        assert int(ok.item()) == 1, "hypothesis sharding over %d ranks differs from the 1-GPU result (%s)" % (world, name)
+        out[name] = {"ms_per_pair": hyp_ms, "pairs_per_s": 1e3 / hyp_ms, "ms_per_pair_1gpu": single_ms,
+                     "speedup": single_ms / hyp_ms, "efficiency": single_ms / hyp_ms / world, "reps": reps,
+                     "identical_to_1gpu": True, "best_count": res["best_count"], "best_id": res["best_id"],
+                     "h_scored_all_ranks": res["n_scored"]}
+    return out
+
+
+def bench_faithful_regime(engine, torch, resident, pair0):
+    """SURVEY 8(d) cfg 3, "reference-faithful": the confidence exit on (0.9995) on both sides, and the Open3D branch's
+    semantics (FR.py:122-139: ransac_n = 4 drawn with replacement, edge-length checker) timed on the CPU in its two
+    forms -- *faithful* (copy and transform the whole source cloud per surviving hypothesis, as upstream) and *lean*
+    (transform the correspondences only)."""
+    from oracle import lr_oracle as O
+    a, b = resident[0]
+    out = {}
+    for name, kw in (("gc_count_m3", dict(sample_size=3, sampler=engine.SAMPLER_UNIFORM)),
+                     ("open3d_m4_replace", dict(sample_size=4, sampler=engine.SAMPLER_REPLACE))):
+        params = engine.make_params(threshold=THRESH, confidence=0.9995, max_iters=ITERS, seed=51, use_elc=True,
+                                    refit=True, **kw)
+        for _ in range(3):
+            res = engine.ransac_rigid(a, b, params)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            res = engine.ransac_rigid(a, b, params)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        row = {"gpu_ms_per_pair": ms, "gpu_pairs_per_s": 1e3 / ms, "iters_run": res["iters_run"],
+               "best_count": res["best_count"], "best_id": res["best_id"]}
+        okw = dict(m=kw["sample_size"], sampler=0 if kw["sampler"] == engine.SAMPLER_UNIFORM else 2, use_elc=True,
+                   thr=THRESH, conf=0.9995, max_iters=ITERS, round_size=65536, seed=51, refit=True)
+        for variant, faithful in (("cpu_lean", False), ("cpu_faithful", True)):
+            if faithful and kw["sample_size"] == 3:
+                continue
+            O.set_o3d_faithful(faithful)
+            try:
+                O.ransac(pair0["src"], pair0["tgt"], **okw)  # warm
+                t0 = time.perf_counter()
+                n = 5
+                for _ in range(n):
+                    o = O.ransac(pair0["src"], pair0["tgt"], **okw)
+                dt = (time.perf_counter() - t0) / n
+            finally:
+                O.set_o3d_faithful(False)
+            row[variant] = {"ms_per_pair": dt * 1e3, "pairs_per_s": 1.0 / dt, "cores": O.num_threads(),
+                            "same_selection": bool(o["best_id"] == res["best_id"] and o["best_count"] == res["best_count"]
+                                                   and o["iters_run"] == res["iters_run"])}
+        out[name] = row
+    # the fixed-budget Open3D-semantics CPU variants (the >= 100x denominator of SURVEY 8(d) is the faster of the two)
+    okw = dict(m=4, sampler=2, use_elc=True, thr=THRESH, conf=1.0, max_iters=ITERS, round_size=65536, seed=51, refit=True)
+    fixed = {}
+    for variant, faithful in (("cpu_lean", False), ("cpu_faithful", True)):
+        O.set_o3d_faithful(faithful)
+        try:
+            t0 = time.perf_counter()
+            O.ransac(pair0["src"], pair0["tgt"], **okw)
+            dt = time.perf_counter() - t0
+        finally:
+            O.set_o3d_faithful(False)
+        fixed[variant] = {"ms_per_pair": dt * 1e3, "pairs_per_s": 1.0 / dt, "cores": O.num_threads()}
+    out["open3d_m4_replace_fixed_budget"] = fixed
+    return out
+
+
+def bench_fr(torch):
+    """The drop-in entry itself (FR.py:16-119): one 25k-point synthetic pair, --mode MMN --iters 1000000, host tensors in,
+    T out; stage breakdown from CUDA events around the same calls FR() makes."""
+    from types import SimpleNamespace
+    from lidarregistration_b200 import engine, synthetic
+    from lidarregistration_b200.algorithms import FR
+    p = synthetic.make_pair(25000, seed=51 + 5000, overlap=0.6)
+    t = [torch.from_numpy(p[k]) for k in ("xyz0", "xyz1", "feat0", "feat1")]
+    args = SimpleNamespace(mode="MMN", iters=ITERS, codebase="GC", prosac=True, spatial_coherence_weight=0.0, GC_conf=1.0,
+                           fast_rejection="ELC", GC_LO=True, GPF_factor=2.0, GPF_grid_wid=10, GPF_max_matches=10 ** 9, seed=51)
+    for _ in range(3):
+        out = FR(*t, args, p["T_gt"])
+    torch.cuda.synchronize()
+    reps = 10
+    t0 = time.perf_counter()
+    model_time = 0.0
+    for _ in range(reps):
+        out = FR(*t, args, p["T_gt"])
+        model_time += out[1]
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    # stages on device tensors
+    f0, f1 = engine.to_dev_f32(t[2]), engine.to_dev_f32(t[3])
+    x0, x1 = engine.to_dev_f32(t[0]), engine.to_dev_f32(t[1])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    stage = [0.0, 0.0, 0.0, 0.0]
+    for _ in range(reps):
+        ev[0].record()
+        i1, i2 = engine.match_nn(f0, f1, want_2nd=True)
+        ev[1].record()
+        mi, mj = engine.match_mutual(f0, f1, i1)
+        ev[2].record()
+        src, tgt = engine.gather_xyz(x0, mi), engine.gather_xyz(x1, mj)
+        q = engine.match_ratio(f0, f1, mi, mj, i2[mi])
+        order = torch.argsort(q, stable=True)
+        src, tgt = src[order].contiguous(), tgt[order].contiguous()
+        ev[3].record()
+        params = engine.make_params(threshold=THRESH, confidence=1.0, max_iters=ITERS, seed=51, sample_size=3,
+                                    sampler=engine.SAMPLER_PROSAC, use_elc=True, refit=True)
+        res = engine.ransac_rigid(src, tgt, params)
+        ev[4].record()
+        torch.cuda.synchronize()
+        for k in range(4):
+            stage[k] += ev[k].elapsed_time(ev[k + 1]) / reps
+    from lidarregistration_b200 import metrics
+    return {"workload": "FR(A, B, A_feat, B_feat, args, T_gt): 25k-point pair, --mode MMN --iters 1000000 --prosac True, "
+                        "host torch tensors in, numpy T out", "wall_ms_per_pair": wall * 1e3,
+            "model_time_ms": model_time / reps * 1e3, "pairs_per_s": 1.0 / wall,
+            "stages_ms": {"find_2nn (one sweep, both neighbours)": stage[0], "nn_to_mutual": stage[1],
+                          "gather + ratio quality + PROSAC sort": stage[2], "RANSAC + refit": stage[3]},
+            "mutual_pairs": int(mi.shape[0]), "h_scored": res["n_scored"],
+            "registration_success": bool(metrics.registration_success(out[0], p["T_gt"]))}
+
+
+def probe_reference_libraries(pair0):
+    """SURVEY 8(c), last row: when the reference's third-party engines are importable on the box, time the real thing."""
+    out = {}
+    for mod in ("open3d", "pygcransac"):
+        try:
+            __import__(mod)
+            out[mod] = "importable"
+        except Exception as e:
+            out[mod] = "absent (%s)" % type(e).__name__
+    if out.get("pygcransac") == "importable":
+        try:
+            import numpy as np
+            import pygcransac
+            t0 = time.perf_counter()
+            pose, mask = pygcransac.findRigidTransform(np.ascontiguousarray(pair0["src"]), np.ascontiguousarray(pair0["tgt"]),
+                                                       threshold=THRESH, conf=0.9995, spatial_coherence_weight=0.0,
+                                                       max_iters=ITERS, use_sprt=True, min_inlier_ratio_for_sprt=-1,
+                                                       sampler=0, neighborhood=0, neighborhood_size=20)
+            out["pygcransac_ms_per_pair"] = (time.perf_counter() - t0) * 1e3
+            out["pygcransac_inliers"] = int(mask.sum())
+        except Exception as e:
+            out["pygcransac_error"] = repr(e)
+    if out.get("open3d") == "importable":
+        try:
+            import numpy as np
+            import open3d as o3d
+            pc0, pc1 = o3d.geometry.PointCloud(), o3d.geometry.PointCloud()
+            pc0.points = o3d.utility.Vector3dVector(pair0["src"].astype(np.float64))
+            pc1.points = o3d.utility.Vector3dVector(pair0["tgt"].astype(np.float64))
+            n = len(pair0["src"])
+            corres = o3d.utility.Vector2iVector(np.stack([np.arange(n), np.arange(n)], 1).astype(np.int32))
+            reg = o3d.pipelines.registration
+            t0 = time.perf_counter()
+            r = reg.registration_ransac_based_on_correspondence(
+                pc0, pc1, corres, THRESH, reg.TransformationEstimationPointToPoint(False), 4,
+                [reg.CorrespondenceCheckerBasedOnEdgeLength(0.9)], reg.RANSACConvergenceCriteria(ITERS, 0.9995))
+            out["open3d_ms_per_pair"] = (time.perf_counter() - t0) * 1e3
+            out["open3d_fitness"] = float(r.fitness)
+        except Exception as e:
+            out["open3d_error"] = repr(e)
+    return out
 
 
 def ncu_traffic(summary):
@@ -434,6 +682,14 @@ def bench_matching(engine, torch, dev):
     engine.prof_enable(False)
     ms = e0.elapsed_time(e1) / reps
     nn_ms, nn_l = engine.prof_read(engine.PROF_NN)
+    # find_nn alone (operand image + sweep + exact re-rank), one direction
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        engine.match_nn(f0, f1, want_2nd=False)
+    e1.record()
+    torch.cuda.synchronize()
+    find_nn_ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * MATCH_N * MATCH_N * 32  # per sweep; MNN = forward + reverse sweep
     peaks = {}
     try:
@@ -453,8 +709,11 @@ def bench_matching(engine, torch, dev):
     return {"ms": ms, "cpu_baseline": {"ms": cpu_mnn_ms, "cores": O.num_threads(), "kind": "port",
                                        "sample": "oracle find_nn, %d of %d query rows x all targets (%.2f s), scaled to "
                                                  "two full sweeps" % (rows, MATCH_N, cpu_s)}, "unit": "ms per mutual-NN match (forward + reverse sweep + intersection), N=M=50000, D=32",
-            "mutual_pairs": int(mi.shape[0]), "sweep_ms": nn_ms / max(nn_l, 1),
-            "roofline": {"kernel": "k_nn_tc (tcgen05 sweep: fp16 operands, fp16 accumulators in TMEM, chunk-maximum events) + k_rerank (exact fp32)", "bound": "tensor", "achieved": ach,
+            "mutual_pairs": int(mi.shape[0]), "sweep_ms": nn_ms / max(nn_l, 1), "find_nn_ms": find_nn_ms,
+            "fractions_of_tensor_peak": {"sweep (k_nn_tc alone)": ach / tensor_peak if ach else None,
+                                         "find_nn (prep + sweep + re-rank)": flops / (find_nn_ms * 1e-3) / 1e12 / tensor_peak,
+                                         "mutual match (two sweeps of 2 N M D + intersection)": 2 * flops / (ms * 1e-3) / 1e12 / tensor_peak},
+            "roofline": {"kernel": "k_nn_tc alone (tcgen05 sweep: fp16 operands, fp16 accumulators in TMEM, chunk-maximum events); the library brackets this kernel only", "bound": "tensor", "achieved": ach,
                          "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak if ach else None,
                          "peak_source": "bf16_tflops of MEASURED_PEAKS.json (burst)" if peaks else "fallback 1590",
                          "traffic": ncu_traffic("r1_ncu_k_nn_tc.txt")}}
