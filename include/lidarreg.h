@@ -93,7 +93,8 @@ int lr_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int lr_shutdown(void);
 
 /* ---- measurement hooks (used by bench.py only) -------------------------- */
-enum { LR_PROF_SCORE = 0, LR_PROF_GEN = 1, LR_PROF_NN = 2, LR_PROF_RECOUNT = 3 };
+enum { LR_PROF_SCORE = 0, LR_PROF_GEN = 1, LR_PROF_NN = 2, LR_PROF_RECOUNT = 3,
+       LR_PROF_PACK = 4 /* reset + pack */, LR_PROF_END = 5 /* round end (+ key exchange) */, LR_PROF_FIN = 6 /* mask + refit */ };
 /* bracket the heavy kernels with CUDA events on their stream (off by default) */
 int lr_prof_enable(int on);
 /* [host] device milliseconds and launch count of one kernel class since the last read */

@@ -55,7 +55,7 @@ struct Lock {
 };
 
 // optional device-time accounting (lr_prof.cu); tokens are -1 when disabled
-enum ProfKind { PROF_SCORE = 0, PROF_GEN = 1, PROF_NN = 2, PROF_RECOUNT = 3 };
+enum ProfKind { PROF_SCORE = 0, PROF_GEN = 1, PROF_NN = 2, PROF_RECOUNT = 3, PROF_PACK = 4, PROF_END = 5, PROF_FIN = 6 };
 int prof_begin(int kind, cudaStream_t st);
 void prof_end(int token, cudaStream_t st);
 

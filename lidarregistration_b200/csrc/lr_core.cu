@@ -45,6 +45,14 @@ void *arena_get(int slot, size_t bytes)
             a.ptr = nullptr;
             return nullptr;
         }
+        // control blocks at the head of an arena rely on zeroed "last block" tickets
+        e = cudaMemset(a.ptr, 0, want < (size_t(1) << 16) ? want : (size_t(1) << 16));
+        if (e != cudaSuccess) {
+            set_error("cudaMemset of a fresh arena failed: %s", cudaGetErrorString(e));
+            cudaFree(a.ptr);
+            a.ptr = nullptr;
+            return nullptr;
+        }
         a.cap = want;
         ++a.gen;
     }

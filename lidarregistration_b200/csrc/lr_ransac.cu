@@ -57,7 +57,9 @@ struct Ctl {
     double H[9];
     double err2;  // sum of squared residuals over the inliers (ICP rmse)
     unsigned int ticket_end, ticket_fin;  // "last block finishes" counters of k_resolve_end / k_finish
-    int comm_error, pad1;                 // hypothesis sharding: a peer did not answer in time
+    int comm_error;                       // hypothesis sharding: a peer did not answer in time
+    unsigned int ticket_pack;             // k_pack's counter: zero whenever no k_pack is running (its last block re-zeroes
+                                          // it; a fresh arena block is zero-filled), never touched by ctl_reset_fields
     // LR_SCORE_MSAC runs only (lr_ransac_gc.cuh); q = quantised MSAC score (include/lidarreg.h)
     struct Gc {
         unsigned long long round_q;     // highest q of the current round
@@ -92,7 +94,8 @@ struct Ws {
     float *band;      // per slot: half-width of the r^2 band that is decided in fp64
     double *partial;  // k_finish: kFinBlocksMax x kFinVals per-block sums
     int4 *events;     // records of the residuals inside the tensor sweep's error band, one list per epilogue warp and CTA
-    unsigned *ev_count;
+    unsigned long long *blockbest;  // k_resolve_end: per-block (key, slot)
+    float *packmax;   // k_pack: per-block maxima (|p|_1, |p - c|_2, |q - c'|_inf), reduced by its last block
     // LR_SCORE_MSAC runs only (null otherwise)
     unsigned long long *q64;  // per slot: quantised MSAC score
     int32_t *lo_L;            // inlier index list of the current LO round, ascending
@@ -417,9 +420,48 @@ __device__ __forceinline__ u64 mul2(u64 a, u64 b)
 // negated: the sweep then only adds).  Padded to a multiple of kChunk with
 // far-away points that can never be inliers.  Also the coordinate bound that
 // enters the fp32 error band.
-__global__ void k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, int64_t n_pad,
-                       float4 *__restrict__ P12, float4 *__restrict__ P8, uint4 *__restrict__ Bimg, Ctl *ctl)
+__device__ void ctl_reset_fields(Ctl *ctl)
 {
+    ctl->best_key = 0ULL;
+    ctl->round_key = 0ULL;
+    ctl->n_surv = 0;
+    ctl->n_events = 0u;
+    ctl->done = 0;
+    ctl->iters_run = 0;
+    ctl->n_scored = 0;
+    ctl->n_rechecked = 0;
+    ctl->p1max_bits = 0u;
+    ctl->qmax_bits = 0u;
+    ctl->pt2max_bits = 0u;
+    ctl->qtmax_bits = 0u;
+    ctl->ticket_end = ctl->ticket_fin = 0u;
+    ctl->comm_error = 0;
+    ctl->refit_count = 0;
+    ctl->gc.round_q = ctl->gc.best_q = ctl->gc.cur_q = ctl->gc.lo_q = 0ULL;
+    ctl->gc.round_pick = ~0ULL;
+    ctl->gc.best_id = -1;
+    ctl->gc.best_inl = 0;
+    ctl->gc.has_model = ctl->gc.lo_active = ctl->gc.lsq_active = 0;
+    ctl->gc.lo_improved = ctl->gc.lsq_improved = 0;
+    ctl->gc.lo_I = ctl->gc.lo_s = 0;
+    ctl->gc.mode = 0;
+    for (int k = 0; k < 12; ++k) {
+        ctl->gc.cur[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        ctl->T[k] = (k % 5 == 0) ? 1.0 : 0.0;  // no selection (or a 0-inlier one) leaves the identity
+    }
+}
+
+// The first kernel of a run.  Block 0 resets the control block (nothing else of this kernel reads or writes it until
+// the last block), every block leaves its coordinate maxima in packmax[], and the last block to finish (ticket)
+// reduces them into the control block -- one launch instead of reset + pack, and no same-address atomics
+// (3 per warp serialised in L2: the pair of launches took 15 us at cfg 3).
+// WANT12: also the duplicated-value copy the fp32 sweeps read (lr_ransac_set_mode 1 / 2, LR_SCORE_MSAC).
+__global__ void __launch_bounds__(256)
+k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, int64_t n_pad,
+       float4 *__restrict__ P12, float4 *__restrict__ P8, uint4 *__restrict__ Bimg, Ctl *ctl, float *__restrict__ packmax,
+       int want12)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl_reset_fields(ctl);
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     float p1 = 0.f, pt2 = 0.f, qt = 0.f;
     double c[3] = {0, 0, 0}, cq[3] = {0, 0, 0};
@@ -427,9 +469,11 @@ __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ 
     if (i < n) {
         float px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
         float qx = tgt[3 * i], qy = tgt[3 * i + 1], qz = tgt[3 * i + 2];
-        P12[3 * i + 0] = make_float4(px, px, py, py);
-        P12[3 * i + 1] = make_float4(pz, pz, -qx, -qx);
-        P12[3 * i + 2] = make_float4(-qy, -qy, -qz, -qz);
+        if (want12) {
+            P12[3 * i + 0] = make_float4(px, px, py, py);
+            P12[3 * i + 1] = make_float4(pz, pz, -qx, -qx);
+            P12[3 * i + 2] = make_float4(-qy, -qy, -qz, -qz);
+        }
         P8[2 * i + 0] = make_float4(px, py, pz, qx);
         P8[2 * i + 1] = make_float4(qy, qz, 0.f, 0.f);
         p1 = fabsf(px) + fabsf(py) + fabsf(pz);
@@ -440,9 +484,11 @@ __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ 
         pt2 = __double2float_ru(sqrt((pt[0] * pt[0] + pt[1] * pt[1]) + pt[2] * pt[2])) * 1.000001f;
         qt = __double2float_ru(fmax(fabs(qq[0]), fmax(fabs(qq[1]), fabs(qq[2]))));
     } else if (i < n_pad) {
-        P12[3 * i + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        P12[3 * i + 1] = make_float4(0.f, 0.f, -1e18f, -1e18f);
-        P12[3 * i + 2] = make_float4(-1e18f, -1e18f, -1e18f, -1e18f);
+        if (want12) {
+            P12[3 * i + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            P12[3 * i + 1] = make_float4(0.f, 0.f, -1e18f, -1e18f);
+            P12[3 * i + 2] = make_float4(-1e18f, -1e18f, -1e18f, -1e18f);
+        }
         // padding: 60 km away from wherever a model can send the origin (|t~| <= 2 x tcs::kRangeLimit)
         const double pt[3] = {0.0, 0.0, 0.0}, qq[3] = {60000.0, 60000.0, 60000.0};
         tcs::tc_write_corr(Bimg, i, pt, qq);
@@ -453,42 +499,50 @@ __global__ void k_pack(const float *__restrict__ src, const float *__restrict__ 
         pt2 = fmaxf(pt2, __shfl_xor_sync(0xffffffffu, pt2, o));
         qt = fmaxf(qt, __shfl_xor_sync(0xffffffffu, qt, o));
     }
-    // round up a little: the fp32 sum above is itself rounded
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&ctl->p1max_bits, __float_as_uint(p1 * 1.000001f));
-        atomicMax(&ctl->pt2max_bits, __float_as_uint(pt2));
-        atomicMax(&ctl->qtmax_bits, __float_as_uint(qt));
+    __shared__ float s_max[3][8];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_max[0][w] = p1;
+        s_max[1][w] = pt2;
+        s_max[2][w] = qt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float m = 0.f;
+        for (int k = 0; k < 8; ++k) m = fmaxf(m, s_max[threadIdx.x][k]);
+        packmax[3 * blockIdx.x + threadIdx.x] = m;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket_pack, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) return;
+    __threadfence();
+    float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+        m0 = fmaxf(m0, __ldcg(packmax + 3 * b));
+        m1 = fmaxf(m1, __ldcg(packmax + 3 * b + 1));
+        m2 = fmaxf(m2, __ldcg(packmax + 3 * b + 2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) {
+        // round up a little: the fp32 sum of |p|_1 is itself rounded
+        ctl->p1max_bits = __float_as_uint(m0 * 1.000001f);
+        ctl->pt2max_bits = __float_as_uint(m1);
+        ctl->qtmax_bits = __float_as_uint(m2);
+        ctl->ticket_pack = 0u;
     }
 }
 
 __global__ void k_ctl_reset(Ctl *ctl)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        ctl->best_key = 0ULL;
-        ctl->round_key = 0ULL;
-        ctl->n_surv = 0;
-        ctl->n_events = 0u;
-        ctl->done = 0;
-        ctl->iters_run = 0;
-        ctl->n_scored = 0;
-        ctl->n_rechecked = 0;
-        ctl->p1max_bits = 0u;
-        ctl->qmax_bits = 0u;
-        ctl->pt2max_bits = 0u;
-        ctl->qtmax_bits = 0u;
-        ctl->ticket_end = ctl->ticket_fin = 0u;
-        ctl->comm_error = 0;
-        ctl->refit_count = 0;
-        ctl->gc.round_q = ctl->gc.best_q = ctl->gc.cur_q = ctl->gc.lo_q = 0ULL;
-        ctl->gc.round_pick = ~0ULL;
-        ctl->gc.best_id = -1;
-        ctl->gc.best_inl = 0;
-        ctl->gc.has_model = ctl->gc.lo_active = ctl->gc.lsq_active = 0;
-        ctl->gc.lo_improved = ctl->gc.lsq_improved = 0;
-        ctl->gc.lo_I = ctl->gc.lo_s = 0;
-        ctl->gc.mode = 0;
-        for (int k = 0; k < 12; ++k) ctl->gc.cur[k] = (k % 5 == 0) ? 1.0 : 0.0;
-    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctl_reset_fields(ctl);
 }
 
 // fp32 models are stored so that the sweep can load ready-made f32x2 operands:
@@ -913,6 +967,7 @@ struct Mail {
     unsigned long long aux;  // survivors the sender scored in the round
     unsigned long long seq;  // exchange number the entry belongs to (written last, release)
     unsigned long long pad;
+    double T[12];            // the fp64 model behind `key` (the sender computed it in k_kabsch: nobody re-derives it)
 };
 struct Comm {
     int rank, world;
@@ -936,8 +991,21 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned l
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// one warp: all-gather of (key, aux) through the peers' mailboxes, MAX / SUM reduced; every rank gets the same
-__device__ __forceinline__ void comm_exchange(Comm *cm, unsigned long long &key, unsigned long long &aux, int &err)
+__device__ __forceinline__ double ld_acquire_sys_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+// one warp: all-gather of (key, aux, model) through the peers' mailboxes; key MAX / aux SUM reduced, T = the model of
+// the winning key (valid in lane 0); every rank gets the same
+__device__ __forceinline__ void comm_exchange(Comm *cm, unsigned long long &key, unsigned long long &aux, double (&T)[12],
+                                              int &err)
 {
     const int lane = threadIdx.x & 31;
     const int G = cm->world, me = cm->rank;
@@ -948,6 +1016,8 @@ __device__ __forceinline__ void comm_exchange(Comm *cm, unsigned long long &key,
         Mail *dst = cm->peer[lane] + (size_t)(ep & 1ULL) * kMaxRanks + me;
         st_relaxed_sys(&dst->key, key);
         st_relaxed_sys(&dst->aux, aux);
+#pragma unroll
+        for (int j = 0; j < 12; ++j) st_relaxed_sys_f64(&dst->T[j], T[j]);
         __threadfence_system();
         st_release_sys(&dst->seq, ep);
         const Mail *src = cm->peer[me] + (size_t)(ep & 1ULL) * kMaxRanks + lane;
@@ -962,7 +1032,17 @@ __device__ __forceinline__ void comm_exchange(Comm *cm, unsigned long long &key,
         a = ld_acquire_sys(&src->aux);
     }
     bad = __any_sync(0xffffffffu, bad);
-    k = warp_max_u64(k);
+    const unsigned long long kmax = warp_max_u64(k);
+    // keys are unique (the id is part of them) unless they are 0: the lowest lane holding the maximum wins
+    const unsigned who = __ballot_sync(0xffffffffu, lane < G && k == kmax);
+    const int wl = who ? __ffs(who) - 1 : 0;
+    if (lane == wl) {
+        const Mail *src = cm->peer[me] + (size_t)(ep & 1ULL) * kMaxRanks + lane;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) T[j] = ld_acquire_sys_f64(&src->T[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) T[j] = __shfl_sync(0xffffffffu, T[j], wl);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     __syncwarp();
@@ -970,7 +1050,7 @@ __device__ __forceinline__ void comm_exchange(Comm *cm, unsigned long long &key,
         cm->epoch = ep;
         if (bad) cm->error = 1;
     }
-    key = k;
+    key = kmax;
     aux = a;
     err = bad;
 }
@@ -979,64 +1059,94 @@ struct EndArgs {
     int64_t round_len;     // hypotheses of the whole round (all ranks together)
     const int *need;       // confidence exit table (nullable)
     int round_idx;
-    int is_last;           // last enqueued round: the selected model is materialised in ctl->T
     Comm *comm;            // hypothesis sharding: exchange the round's key with the peers (nullable)
-    uint64_t seed;
-    int sampler;
-    int64_t n;
-    const uint32_t *growth;
-    const float4 *P8;
 };
 
-// key -> fp64 model of the selected hypothesis (identity when none / zero inliers), sample read from the packed records
-template <int M>
-__device__ void model_from_key(unsigned long long key, const EndArgs &a, double (&T)[12])
-{
-#pragma unroll
-    for (int k = 0; k < 12; ++k) T[k] = (k % 5 == 0) ? 1.0 : 0.0;
-    const long long cnt = (long long)(key >> 32) - 1;
-    if (key != 0ULL && cnt > 0) {
-        const uint64_t id = (uint64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFULL));
-        int32_t s[M];
-        sample_ids<M>(a.seed, id, a.sampler, a.n, a.growth, s);
-        double P[M][3], Q[M][3];
-#pragma unroll
-        for (int d = 0; d < M; ++d) load_pq(a.P8, (int64_t)s[d], P[d], Q[d]);
-        kabsch_small<M>(P, Q, T);
-    }
-}
-
-// k_resolve + k_round_end (+ the peer exchange + the winner's model) in one launch: the last block to finish
-// (ticket) ends the round.  Used by the count-scoring runs; the fed-sample hook keeps the two-kernel form.
-template <int M>
+// k_resolve + k_round_end (+ the peer exchange) in one launch: every block leaves its best (key, slot) in
+// blockbest[], the last block to finish (ticket) ends the round.  The winner's model is COPIED from m64[] (k_kabsch
+// computed it; across ranks it travels in the mailbox) whenever a round improves the selection -- re-deriving it from
+// the id cost a single-thread fp64 Jacobi (~10 us) at the end of every run.
+// Used by the count-scoring runs; the fed-sample hook keeps the two-kernel form.
+constexpr int kEndBlocksMax = 512;
 __global__ void __launch_bounds__(256)
-k_resolve_end(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restrict__ cnt, EndArgs a)
+k_resolve_end(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restrict__ cnt, const double *__restrict__ m64,
+              unsigned long long *__restrict__ blockbest, EndArgs a)
 {
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
     unsigned long long key = 0ULL;
+    int bslot = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < nsurv; slot += gridDim.x * blockDim.x) {
         const unsigned long long k = make_key(cnt[slot], slot_id[slot]);
-        key = k > key ? k : key;
+        if (k > key) {
+            key = k;
+            bslot = slot;
+        }
     }
-    key = warp_max_u64(key);
-    if ((threadIdx.x & 31) == 0 && key) atomicMax(&ctl->round_key, key);
+    __shared__ unsigned long long s_key[8];
+    __shared__ int s_slot[8];
     __shared__ int s_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    auto warp_argmax = [&](unsigned long long &k, int &sl) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, k, o);
+            const int s2 = __shfl_xor_sync(0xffffffffu, sl, o);
+            if (k2 > k) {
+                k = k2;
+                sl = s2;
+            }
+        }
+    };
+    warp_argmax(key, bslot);
+    if (lane == 0) {
+        s_key[w] = key;
+        s_slot[w] = bslot;
+    }
+    __syncthreads();
+    if (w == 0) {
+        key = lane < 8 ? s_key[lane] : 0ULL;
+        bslot = lane < 8 ? s_slot[lane] : 0;
+        warp_argmax(key, bslot);
+        if (lane == 0) {
+            blockbest[2 * blockIdx.x] = key;
+            blockbest[2 * blockIdx.x + 1] = (unsigned long long)bslot;
+        }
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(&ctl->ticket_end, 1u) == gridDim.x - 1 ? 1 : 0;
     __syncthreads();
     if (!s_last || threadIdx.x >= 32) return;
     __threadfence();
-    unsigned long long rkey = __ldcg(&ctl->round_key);
+    unsigned long long rkey = 0ULL;
+    int rslot = 0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+        const unsigned long long k = __ldcg(blockbest + 2 * b);
+        if (k > rkey) {
+            rkey = k;
+            rslot = (int)__ldcg(blockbest + 2 * b + 1);
+        }
+    }
+    warp_argmax(rkey, rslot);
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = rkey ? __ldcg(m64 + (size_t)rslot * 12 + k) : 0.0;
     unsigned long long scored = (unsigned long long)nsurv;
     int err = 0;
-    if (a.comm) comm_exchange(a.comm, rkey, scored, err);
+    if (a.comm) comm_exchange(a.comm, rkey, scored, T, err);
     if (threadIdx.x != 0) return;
     ctl->ticket_end = 0u;
     if (err) ctl->comm_error = 1;
     unsigned long long best = ctl->best_key;
-    if (rkey > best) best = rkey;
+    if (rkey > best) {
+        best = rkey;
+        // a 0-inlier selection never replaces the identity
+        if ((long long)(rkey >> 32) - 1 > 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) ctl->T[k] = T[k];
+        }
+    }
     ctl->best_key = best;
     ctl->iters_run += a.round_len;
     ctl->n_scored += (long long)scored;
@@ -1049,12 +1159,6 @@ k_resolve_end(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restr
         if (best != 0ULL && c >= (long long)a.need[a.round_idx]) done = 1;
     }
     if (done) ctl->done = 1;
-    if (done || a.is_last) {
-        double T[12];
-        model_from_key<M>(best, a, T);
-#pragma unroll
-        for (int k = 0; k < 12; ++k) ctl->T[k] = T[k];
-    }
 }
 
 // key -> model of the selected hypothesis (identity when none / zero inliers)
@@ -1277,10 +1381,24 @@ k_finish(const float *__restrict__ a, const float *__restrict__ b, const int64_t
                 for (int c = 0; c < 3; ++c) v[8 + 3 * r + c] += q[r] * p[c];
         }
     }
+    // first stage, fixed order: shuffle tree inside each warp, then thread k adds the 8 warp sums of value k in order
+    // (one barrier instead of 34: the 17 values used to go through block_sum one after the other)
+    __shared__ double s_part[8][kFinVals];
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < kFinVals; ++k) {
-        const double r = block_sum(v[k], sh);
-        if (threadIdx.x == 0) partial[(size_t)blockIdx.x * kFinVals + k] = r;
+        for (int k = 0; k < kFinVals; ++k) {
+            double x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) s_part[w][k] = x;
+        }
+        __syncthreads();
+        if (threadIdx.x < kFinVals) {
+            double r = 0.0;
+            for (int ww = 0; ww < (int)(blockDim.x >> 5); ++ww) r += s_part[ww][threadIdx.x];
+            partial[(size_t)blockIdx.x * kFinVals + threadIdx.x] = r;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -1288,15 +1406,24 @@ k_finish(const float *__restrict__ a, const float *__restrict__ b, const int64_t
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // second stage: thread t adds blocks t, t + 256, ... in order, then the fixed tree of block_sum
-    double tot[kFinVals];
+    // second stage, fixed order: warp w owns the values k = w, w + 8, ...; lane l adds blocks l, l + 32, ... in order,
+    // then the shuffle tree -- the 17 sums run side by side instead of 17 block-wide reductions in a row
+    __shared__ double s_tot[kFinVals];
+    {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        for (int k = w; k < kFinVals; k += (int)(blockDim.x >> 5)) {
+            double x = 0.0;
+            for (int blk = lane; blk < (int)gridDim.x; blk += 32) x += __ldcg(&partial[(size_t)blk * kFinVals + k]);
 #pragma unroll
-    for (int k = 0; k < kFinVals; ++k) {
-        double x = 0.0;
-        for (int blk = threadIdx.x; blk < (int)gridDim.x; blk += blockDim.x) x += __ldcg(&partial[(size_t)blk * kFinVals + k]);
-        tot[k] = block_sum(x, sh);
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) s_tot[k] = x;
+        }
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        double tot[kFinVals];
+#pragma unroll
+        for (int k = 0; k < kFinVals; ++k) tot[k] = s_tot[k];
         const long long k = (long long)(tot[0] + 0.5);
         double Tr[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         if (k > 0 && want_refit) {
@@ -1422,7 +1549,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
                    lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1)) +
                    lr::padded((size_t)((slots + tcs::TM - 1) / tcs::TM) * tcs::A_BLOCK_BYTES) +
                    lr::padded((size_t)ws.n_pad * 64) + lr::padded(sizeof(float) * slots) +
-                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals) + lr::padded(sizeof(int4) * (size_t)kTcEventCap * tc_regions()) + lr::padded(sizeof(unsigned) * tc_regions());
+                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals) + lr::padded(sizeof(int4) * (size_t)kTcEventCap * tc_regions()) + lr::padded(sizeof(float) * 3 * (size_t)(ws.n_pad / 256 + 1)) + lr::padded(sizeof(unsigned long long) * 2 * kEndBlocksMax);
     if (gc)
         bytes += lr::padded(sizeof(unsigned long long) * slots) + lr::padded(sizeof(int32_t) * (n > 0 ? n : 1)) +
                  lr::padded(sizeof(double) * 12 * kGcMaxTrials) + lr::padded(sizeof(unsigned long long) * kGcMaxTrials) +
@@ -1458,7 +1585,8 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     ws.band = cv.take<float>(slots);
     ws.partial = cv.take<double>((size_t)kFinBlocksMax * kFinVals);
     ws.events = cv.take<int4>((size_t)kTcEventCap * tc_regions());
-    ws.ev_count = cv.take<unsigned>(tc_regions());
+    ws.packmax = cv.take<float>(3 * (size_t)(ws.n_pad / 256 + 1));
+    ws.blockbest = cv.take<unsigned long long>(2 * (size_t)kEndBlocksMax);
     ws.q64 = gc ? cv.take<unsigned long long>(slots) : nullptr;
     ws.lo_L = gc ? cv.take<int32_t>(n > 0 ? n : 1) : nullptr;
     ws.tr_T = gc ? cv.take<double>(12 * kGcMaxTrials) : nullptr;
@@ -1546,11 +1674,12 @@ cudaError_t tc_smem_attr()
     return cudaSuccess;
 }
 
-int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cudaStream_t st)
+int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cudaStream_t st, bool want12 = true)
 {
-    k_ctl_reset<<<1, 32, 0, st>>>(ws.ctl);
+    const int tok = lr::prof_begin(lr::PROF_PACK, st);
     int blocks = (int)((ws.n_pad + 255) / 256);
-    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.Bimg, ws.ctl);
+    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.Bimg, ws.ctl, ws.packmax, want12 ? 1 : 0);
+    lr::prof_end(tok, st);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1592,8 +1721,7 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
             LR_CUDA_TRY(tc_smem_attr());
             tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl,
                                                                                  ws.m64, ws.band, ws.cnt, thr2, nullptr,
-                                                                                 ws.events, ws.ev_count, kTcEventCap);
-            tcs::k_tc_events<<<sms, 32 * tcs::NEPI, 0, st>>>(ws.P8, ws.ctl, ws.m64, ws.cnt, thr2, ws.events, ws.ev_count, kTcEventCap);
+                                                                                 ws.events, kTcEventCap);
         } else if (g_score_mode == 2) {
             // fp32 sweep: 16 resident one-warp CTAs per SM (128 registers per thread fill the register file; 12 KB of
             // staging each): no CTA-level barrier couples warps whose early-out rates differ
@@ -1607,8 +1735,10 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     if (rblocks > sms * 2) rblocks = sms * 2;
     if (rblocks < 1) rblocks = 1;
     if (end) {
-        if (p.sample_size == 3) k_resolve_end<3><<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, *end);
-        else k_resolve_end<4><<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, *end);
+        const int tok = lr::prof_begin(lr::PROF_END, st);
+        k_resolve_end<<<rblocks < kEndBlocksMax ? rblocks : kEndBlocksMax, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, ws.m64,
+                                                                                         ws.blockbest, *end);
+        lr::prof_end(tok, st);
     } else {
         k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, counts_out, lo);
     }
@@ -1660,8 +1790,10 @@ int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacP
         else
             k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, 0, ws.ctl);
     }
+    const int tok = lr::prof_begin(lr::PROF_FIN, st);
     k_finish<<<finish_blocks(n), 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl, mask, ws.partial, want_refit ? 1 : 0,
                                                host_out);
+    lr::prof_end(tok, st);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1791,7 +1923,7 @@ int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacPar
     if (rc) return rc;
     rc = upload_growth(ws, n, p.sample_size, st, slot);
     if (rc) return rc;
-    rc = launch_pack(src, tgt, n, ws, st);
+    rc = launch_pack(src, tgt, n, ws, st, gc || g_score_mode != 0);  // the tensor sweep reads the fp16 image only
     if (rc) return rc;
     if (gc) k_gc_mode<<<1, 32, 0, st>>>(ws.ctl);
     // confidence exit: need[r] = smallest best-count that lets the loop stop
@@ -1826,13 +1958,7 @@ int enqueue_run(const float *src, const float *tgt, int64_t n, const LrRansacPar
         ea.round_len = hi - lo;
         ea.need = use_conf ? ws.need : nullptr;
         ea.round_idx = (int)r;
-        ea.is_last = r == nrounds - 1 ? 1 : 0;
         ea.comm = world > 1 ? comm : nullptr;
-        ea.seed = p.seed;
-        ea.sampler = p.sampler;
-        ea.n = n;
-        ea.growth = ws.growth;
-        ea.P8 = ws.P8;
         // this rank's contiguous slice of the round's ids
         const int64_t a = lo + ((hi - lo) * rank) / world, b = lo + ((hi - lo) * (rank + 1)) / world;
         rc = launch_round(src, tgt, n, p, ws, a, b, nullptr, nullptr, st, nullptr, &ea);
@@ -2055,11 +2181,10 @@ LR_EXPORT int lr_ransac_tc_probe(const float *src, const float *tgt, int64_t n, 
                                                            ws.cnt, E_out);
     if (d_out)
         tcs::k_score_tc<true><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl, ws.m64,
-                                                                            ws.band, ws.cnt, thr2, d_out, ws.events, ws.ev_count, kTcEventCap);
+                                                                            ws.band, ws.cnt, thr2, d_out, ws.events, kTcEventCap);
     if (counts_out) {
         tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl, ws.m64,
-                                                                             ws.band, ws.cnt, thr2, nullptr, ws.events, ws.ev_count, kTcEventCap);
-        tcs::k_tc_events<<<sms, 32 * tcs::NEPI, 0, st>>>(ws.P8, ws.ctl, ws.m64, ws.cnt, thr2, ws.events, ws.ev_count, kTcEventCap);
+                                                                             ws.band, ws.cnt, thr2, nullptr, ws.events, kTcEventCap);
         LR_CUDA_TRY(cudaMemcpyAsync(counts_out, ws.cnt, sizeof(int32_t) * H, cudaMemcpyDeviceToDevice, st));
     }
     LR_CUDA_TRY(cudaGetLastError());

@@ -71,7 +71,7 @@ constexpr int WARP_PRODUCER = NEPI, WARP_MMA = NEPI + 1;
 constexpr int NTHREADS = 32 * (NEPI + 1 + NMMA);
 constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr float kRangeLimit = 15000.f;  // |p~|, |q~| above this: the fp16 pieces could overflow -> fp64 fallback
-constexpr double kAccKappa = 16.0;      // tensor-core accumulation error <= kappa * 2^-24 * sum |terms|
+constexpr double kAccKappa = 4.0;       // tensor-core accumulation error <= kappa * 2^-24 * sum |terms|
                                         // (measured through lr_ransac_tc_probe: tests/test_gpu_score_tc.py)
 
 static_assert(BROWS == kChunk, "the correspondence padding of k_pack is the stage size of the tensor sweep");
@@ -399,7 +399,7 @@ template <bool DUMP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const float4 *__restrict__ P8, int64_t n,
            int64_t n_pad, Ctl *ctl, const double *__restrict__ m64, const float *__restrict__ band, int *__restrict__ cnt,
-           double thr2, float *__restrict__ dump, int4 *__restrict__ events, unsigned *__restrict__ ev_count, unsigned ev_cap)
+           double thr2, float *__restrict__ dump, int4 *__restrict__ events, unsigned ev_cap)
 {
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
@@ -569,7 +569,7 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
         // this warp's private list of in-band residuals (slot, correspondence)
         const int region = blockIdx.x * NEPI + warp;
         int4 *ev_mine = events + (size_t)region * ev_cap;
-        unsigned ev_n = 0;
+        unsigned ev_n = 0, evals_tail = 0;
         for (long long pos = rg.pos; pos < rg.end;) {
             const Seg sg = seg_at(pos, rg.end, nchunks);
             const int slot = sg.hb * TM + q * 32 + lane;
@@ -627,7 +627,7 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                         // record per affected lane in the warp's private list -- no loads, no atomics, no divergent
                         // loop: a warp that is late for its next tile stalls every warp behind the same TMEM buffer
                         // (58 % of the tiles had such a straggler at cfg 3 when this path decided in fp64 on the spot).
-                        // k_tc_events decides the listed residuals in fp64 and adds (exact - sign) to the count.
+                        // The warp decides its listed residuals in fp64 after its last tile (end of this role).
                         unsigned bm = 0u, sg_bits = 0u;
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
@@ -664,7 +664,25 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
             }
             pos += sg.c_hi - sg.c_lo;
         }
-        if (!DUMP && lane == 0) ev_count[region] = ev_n < ev_cap ? ev_n : ev_cap;
+        if (!DUMP && ev_n) {
+            // this warp's own list, decided with the canonical fp64 arithmetic: the count receives (exact - sign).
+            // (A separate kernel did this first; as the tail of the sweep it costs one launch less per round.)
+            __syncwarp();
+            const unsigned ne = ev_n < ev_cap ? ev_n : ev_cap;
+            for (unsigned e = lane; e < ne; e += 32) {
+                const int4 v = __ldcg(ev_mine + e);
+                int d = 0;
+                for (unsigned b = (unsigned)v.z; b; b &= b - 1u) {
+                    const int k = __ffs(b) - 1;
+                    d += tc_exact_inlier(P8, (int64_t)v.y + k, m64 + (size_t)v.x * 12, thr2) - (int)(((unsigned)v.w >> k) & 1u);
+                    ++evals_tail;
+                }
+                if (d) atomicAdd(&cnt[v.x], d);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) evals_tail += __shfl_xor_sync(0xffffffffu, evals_tail, o);
+            if (lane == 0 && evals_tail) atomicAdd(n_rechecked, (unsigned long long)evals_tail);
+        }
     }
 
     tc_fence_before();
@@ -673,35 +691,6 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
-}
-
-// the in-band residuals the sweep listed (record = slot, first column, in-band mask, tensor-core sign bits of 16 columns),
-// decided with the canonical fp64 arithmetic; the count receives (exact - sign).  One warp per list
-// (grid = the sweep's grid, block = NEPI warps: block b reads the lists CTA b of the sweep wrote)
-__global__ void __launch_bounds__(32 * NEPI)
-k_tc_events(const float4 *__restrict__ P8, Ctl *ctl, const double *__restrict__ m64, int *__restrict__ cnt, double thr2,
-            const int4 *__restrict__ events, const unsigned *__restrict__ ev_count, unsigned ev_cap)
-{
-    if (ctl->done || ctl->n_surv <= 0) return;
-    // the sweep wrote no lists when it took its out-of-range fallback
-    if (!(__uint_as_float(ctl->pt2max_bits) < kRangeLimit && __uint_as_float(ctl->qtmax_bits) < kRangeLimit)) return;
-    const int region = blockIdx.x * NEPI + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const unsigned ne = ev_count[region];
-    const int4 *ev = events + (size_t)region * ev_cap;
-    unsigned evals = 0;
-    for (unsigned e = lane; e < ne; e += 32) {
-        const int4 v = ev[e];
-        int d = 0;
-        for (unsigned b = (unsigned)v.z; b; b &= b - 1u) {
-            const int k = __ffs(b) - 1;
-            d += tc_exact_inlier(P8, (int64_t)v.y + k, m64 + (size_t)v.x * 12, thr2) - (int)(((unsigned)v.w >> k) & 1u);
-            ++evals;
-        }
-        if (d) atomicAdd(&cnt[v.x], d);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
-    if (lane == 0 && evals) atomicAdd(reinterpret_cast<unsigned long long *>(&ctl->n_rechecked), (unsigned long long)evals);
 }
 
 constexpr size_t kSmemBytes = 2 * A_BLOCK_BYTES + B_STAGES * B_STAGE_BYTES + sizeof(Smem) + 1024 + 64;

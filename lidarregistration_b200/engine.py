@@ -340,7 +340,7 @@ def key_pack(count, hid):
 
 
 # ------------------------------------------------------------- measurement
-PROF_SCORE, PROF_GEN, PROF_NN, PROF_RECOUNT = 0, 1, 2, 3
+PROF_SCORE, PROF_GEN, PROF_NN, PROF_RECOUNT, PROF_PACK, PROF_END, PROF_FIN = 0, 1, 2, 3, 4, 5, 6
 
 
 def prof_enable(on=True):

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""BASELINE cfg 5 at its stated size: an Apollo-Southbay-Balanced-shaped batch of synthetic pairs (~25k points each,
++-20 %, overlap 0.15-0.9, feature noise 0.05-0.14) through the drop-in FR() (--algo RANSAC --mode MMN), sharded by pair
+over the ranks with no collective, and the CPU oracle pipeline with the same parameters on a fixed
+subsample (every `--oracle_every`-th pair, spread over the ranks' host cores); RRE / RTE / recall by the reference's
+definitions (Experiments/libs/loss.py:44-51, 5 deg / 60 cm).  Checker script (imports oracle/): lives under tests/.
+
+    torchrun --nproc-per-node 8 tests/eval_cfg5.py --pairs 5000 --oracle_every 25 --out profiles/r2_cfg5_8gpu_5000pairs.json
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from lidarregistration_b200 import metrics, parallel, synthetic  # noqa: E402
+from lidarregistration_b200.algorithms import FR  # noqa: E402
+from eval_pairs import oracle_fr  # noqa: E402
+
+
+def make(p, points):
+    rng = np.random.default_rng(51 + 5000 + p)
+    n = int(points * rng.uniform(0.8, 1.2))
+    return synthetic.make_pair(n, seed=51 + 5000 + p, sigma_f=float(rng.uniform(0.05, 0.14)),
+                               overlap=float(rng.uniform(0.15, 0.9)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pairs", type=int, default=5000)
+    ap.add_argument("--points", type=int, default=25000)
+    ap.add_argument("--iters", type=int, default=1000000)
+    ap.add_argument("--conf", type=float, default=0.9995)
+    ap.add_argument("--oracle_every", type=int, default=25)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        torch.distributed.init_process_group("nccl")
+    args = SimpleNamespace(mode="MMN", iters=a.iters, codebase="GC", prosac=True, spatial_coherence_weight=0.0,
+                           GC_conf=a.conf, fast_rejection="ELC", GC_LO=True, GPF_factor=2.0, GPF_grid_wid=10,
+                           GPF_max_matches=10 ** 9, seed=51)
+    mine = parallel.shard_pairs(a.pairs, rank, world)
+    rows = []
+    t_start = time.time()
+    gpu_wall = 0.0
+    for p in mine:
+        d = make(p, a.points)
+        t = [torch.from_numpy(d[k]) for k in ("xyz0", "xyz1", "feat0", "feat1")]
+        t0 = time.time()
+        out = FR(*t, args, d["T_gt"])
+        torch.cuda.synchronize()
+        gpu_wall += time.time() - t0
+        T = out[0]
+        rows.append([p, metrics.rotation_error_deg(T, d["T_gt"]), metrics.translation_error_cm(T, d["T_gt"]), out[1],
+                     out[4], out[6]] + list(T[:3, :].reshape(-1)))
+    gpu_phase = time.time() - t_start
+    # the oracle on the subsample (pairs p with p % every == 0), spread over the ranks' host cores
+    from oracle import lr_oracle as O
+    try:
+        O.set_threads(max(1, len(os.sched_getaffinity(0)) // world))
+    except (AttributeError, OSError):
+        pass
+    sub = [p for p in range(0, a.pairs, a.oracle_every)]
+    orows = []
+    t0 = time.time()
+    for p in sub[rank::world]:
+        d = make(p, a.points)
+        To = oracle_fr(d, a.iters, a.conf, True)
+        orows.append([p, metrics.rotation_error_deg(To, d["T_gt"]), metrics.translation_error_cm(To, d["T_gt"])] +
+                     list(To[:3, :].reshape(-1)))
+    cpu_phase = time.time() - t0
+    rows = parallel.gather_rows(np.asarray(rows, dtype=np.float64).reshape(-1, 18))
+    orows = parallel.gather_rows(np.asarray(orows, dtype=np.float64).reshape(-1, 15))
+    tw = torch.tensor([gpu_wall, gpu_phase, cpu_phase], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(tw, op=torch.distributed.ReduceOp.MAX)
+    if rank == 0:
+        rows = rows[np.argsort(rows[:, 0])]
+        orows = orows[np.argsort(orows[:, 0])]
+        ok = (rows[:, 1] < 5.0) & (rows[:, 2] < 60.0)
+        g_all = dict(recall=float(ok.mean()), RRE_deg=float(rows[ok, 1].mean()), RTE_cm=float(rows[ok, 2].mean()), n=len(rows))
+        gs = rows[np.isin(rows[:, 0], orows[:, 0])]
+        okg = (gs[:, 1] < 5.0) & (gs[:, 2] < 60.0)
+        oko = (orows[:, 1] < 5.0) & (orows[:, 2] < 60.0)
+        both = okg & oko
+        dT = np.abs(gs[:, 6:18] - orows[:, 3:15]).reshape(-1, 3, 4)
+        res = dict(
+            workload="cfg5: %d synthetic pairs, ~%d points (+-20%%), --mode MMN --iters %d --GC_conf %g --prosac True, "
+                     "ELC on, pairs sharded over %d GPUs (no collective)" % (a.pairs, a.points, a.iters, a.conf, world),
+            world=world, gpu_all_pairs=g_all,
+            model_time_mean_s=float(rows[:, 3].mean()), model_time_p99_s=float(np.quantile(rows[:, 3], 0.99)),
+            pairs_per_s_model_time=float(world / rows[:, 3].mean()),
+            pairs_per_s_wall_FR_calls=float(a.pairs / float(tw[0])), wall_s_incl_synthetic_data=float(tw[1]),
+            mean_filtered_pairs=float(rows[:, 5].mean()),
+            subsample=dict(n=len(orows),
+                           gpu=dict(recall=float(okg.mean()), RRE_deg=float(gs[both, 1].mean()), RTE_cm=float(gs[both, 2].mean())),
+                           cpu_oracle=dict(recall=float(oko.mean()), RRE_deg=float(orows[both, 1].mean()),
+                                           RTE_cm=float(orows[both, 2].mean())),
+                           max_abs_rotation_entry_diff=float(dT[:, :, :3].max()),
+                           max_abs_translation_diff_m=float(dT[:, :, 3].max()),
+                           cpu_oracle_seconds_max_over_ranks=float(tw[2])))
+        rel = lambda x, y: abs(x - y) / max(abs(y), 1e-12)  # noqa: E731
+        s = res["subsample"]
+        res["within_0p1_percent"] = bool(rel(s["gpu"]["recall"], s["cpu_oracle"]["recall"]) <= 1e-3 and
+                                         rel(s["gpu"]["RRE_deg"], s["cpu_oracle"]["RRE_deg"]) <= 1e-3 and
+                                         rel(s["gpu"]["RTE_cm"], s["cpu_oracle"]["RTE_cm"]) <= 1e-3)
+        print(json.dumps(res))
+        if a.out:
+            json.dump(res, open(a.out, "w"), indent=1)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -3,7 +3,7 @@
 (FR, --algo RANSAC --mode MNN) and through the CPU oracle pipeline with the same parameters;
 reports RRE / RTE / recall (reference definitions, Experiments/libs/loss.py:44-51) of both.
 
-    python tools/eval_pairs.py --pairs 40 --points 8000 --iters 100000 --out profiles/r1_cfg5_accuracy.json
+    python tests/eval_pairs.py --pairs 40 --points 8000 --iters 100000 --out profiles/r1_cfg5_accuracy.json
 """
 import argparse
 import json

@@ -1,6 +1,6 @@
 """CPU estimate of the early-out rate of k_score under different orderings of the surviving
 hypotheses: fraction of (warp of 64 hypotheses, correspondence) pairs in which some hypothesis has |d0| < c.
-Uses the oracle's sampler / ELC / Kabsch, numpy for the first residual component.  usage: python tools/sim_early_out.py"""
+Uses the oracle's sampler / ELC / Kabsch, numpy for the first residual component.  usage: python tests/sim_early_out.py"""
 import os
 import sys
 
