@@ -28,7 +28,7 @@ INLIER_RATIO = 0.3
 ITERS = 1000000
 THRESH = 0.6
 CFG_SEED = 51 + 3000
-PAIRS_PER_STEP = 4
+PAIRS_PER_STEP = 16  # (4 in round 1: a 1.3 ms step left the 8-rank run at the mercy of host launch jitter)
 MATCH_N = 50000
 FLOPS_PER_TEST = 27  # 12 FMA + 3 for R p + t - q and |.|^2, compare excluded
 METRIC = "pairs/sec @1M RANSAC iters"

@@ -86,7 +86,7 @@ typedef struct LrRansacStats {
 
 /* ---- library ---------------------------------------------------------- */
 const char *lr_last_error(void);
-int lr_version(void); /* 120: lr_comm_*, lr_ransac_rigid_sharded, lr_ransac_tc_probe, three sweep modes (110: LR_SCORE_MSAC) */
+int lr_version(void); /* 130: lr_gpf_filter, LR_PROF_PACK / END / FIN; 120: lr_comm_*, lr_ransac_rigid_sharded, lr_ransac_tc_probe, three sweep modes (110: LR_SCORE_MSAC) */
 /* [host] outputs; number of SMs and compute capability of the current device */
 int lr_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* release every device workspace held by the library */
@@ -131,6 +131,14 @@ int lr_match_ratio(const float *f0, const float *f1, int D, int64_t K, const int
 /* xyz[idx] gather that builds the correspondence arrays (FR.py:72-73):
  * out[k,:] = xyz[idx[k],:], fp32 [.,3]. */
 int lr_gather_xyz(const float *xyz, const int64_t *idx, int64_t K, float *out, void *stream);
+
+/* Grid_Prioritized_Filter (matching.py:100-205, --mode GPF), the part after best-buddy marking and the
+ * ratio quality.  ratio[n] = lr_match_ratio of the candidate pairs, is_bb[n] 1 for mutual pairs (nullable: the BB_first
+ * variant has no offset), xyz0[.,3] source cloud, idx0[n] source index per pair (nullable = identity), total_num =
+ * GPF_factor * #best buddies (or GPF_max_matches).  Out: keep[n] 0 / 1, norm[n] = (ratio - min) / (max - min), - 1 for
+ * best buddies: the value the reference returns for the kept pairs (PROSAC quality, FR.py:75-76).  All device. */
+int lr_gpf_filter(const float *ratio, const uint8_t *is_bb, const float *xyz0, const int64_t *idx0, int64_t n, int grid_wid,
+                  double total_num, uint8_t *keep, float *norm, void *stream);
 
 /* ---- RANSAC rigid motion ---------------------------------------------- */
 

@@ -15,8 +15,8 @@ import torch
 
 from .. import engine
 from .GC_RANSAC import GC_RANSAC, gc_options
-from .matching import (Grid_Prioritized_Filter, calc_distance_ratio_in_feature_space, find_2nn,  # noqa: F401
-                       find_2nn_dev, measure_inlier_ratio, measure_inlier_ratio_dev, nn_to_mutual, nn_to_mutual_dev)
+from .matching import (Grid_Prioritized_Filter, Grid_Prioritized_Filter_dev, calc_distance_ratio_in_feature_space,  # noqa: F401
+                       find_2nn, find_2nn_dev, measure_inlier_ratio, measure_inlier_ratio_dev, nn_to_mutual, nn_to_mutual_dev)
 
 __doc__ = (__doc__ or "") + "\nFast RANSAC algorithms\n"
 
@@ -65,8 +65,7 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
     mode = "MNN" if args.mode == "MMN" else args.mode
 
     # The index tensors stay in HBM from the sweep to the RANSAC call (the reference moves them to the CPU after
-    # every step, matching.py:62-65); only counts come back to the host.  --mode GPF still runs its host-side
-    # bookkeeping (matching.Grid_Prioritized_Filter) and converts at its boundary.
+    # every step, matching.py:62-65); only counts come back to the host (--mode GPF included: csrc/lr_gpf.cu).
     with torch.no_grad():
         # 1. Coarse correspondences
         corres_idx1, idx1_2nd, additional_time_for_finding_2nd_closest = find_2nn_dev(fcgf_feats0, fcgf_feats1)
@@ -83,8 +82,7 @@ def FR(A, B, A_feat, B_feat, args, T_gt):
             corres_idx0, corres_idx1, idx1_2nd = nn_to_mutual_dev(fcgf_feats0, fcgf_feats1, corres_idx1, idx1_2nd)
         elif mode == "GPF":
             corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, _, norm_feat_dist = \
-                Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0.cpu(), corres_idx1.cpu(), idx1_2nd.cpu(),
-                                        xyz0, args)
+                Grid_Prioritized_Filter_dev(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0_d, args)
         elif mode == "no_filter":
             corres_idx0_orig, corres_idx1_orig = corres_idx0, corres_idx1
         else:

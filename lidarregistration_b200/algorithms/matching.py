@@ -123,81 +123,38 @@ def mark_best_buddies(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1):
     return is_bb, is_bb.sum()
 
 
-def Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args,
-                            BB_first=False):
-    """matching.py:100-205 (--mode GPF): best-buddy marking, 10x10 xy grid, water-filling quota,
-    per-cell selection by normalised ratio.  Host-side bookkeeping on top of the CUDA
-    mutual / ratio kernels."""
-    corres_idx0_orig = deepcopy(corres_idx0)
-    corres_idx1_orig = deepcopy(corres_idx1)
-    idx1_2nd_orig = deepcopy(idx1_2nd)
-    GRID_WID = args.GPF_grid_wid
-
+def Grid_Prioritized_Filter_dev(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args, BB_first=False):
+    """Grid_Prioritized_Filter with everything in HBM (device tensors in and out): best-buddy marking from the mutual
+    sweep, the ratio quality, then lr_gpf_filter (cells, water-filling, per-cell selection by rank counting).
+    Returns what the reference returns (matching.py:205)."""
+    f0, f1 = engine.to_dev_f32(fcgf_feats0), engine.to_dev_f32(fcgf_feats1)
+    i0, i1 = engine.to_dev_i64(corres_idx0), engine.to_dev_i64(corres_idx1)
+    i2 = engine.to_dev_i64(idx1_2nd)
+    orig = (i0, i1, i2)
+    assert len(i0) == len(f0), "GPF starts from the full nearest-neighbour set (matching.py:207-220 relies on it)"
+    bb_i, bb_j = engine.match_mutual(f0, f1, i1)
     if BB_first:
         TOTAL_NUM = args.GPF_max_matches
-        corres_idx0, corres_idx1, idx1_2nd = nn_to_mutual(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
-                                                          idx1_2nd, force_return_2nd=True)
-        if TOTAL_NUM >= corres_idx0.shape[0]:
-            return corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, idx1_2nd_orig, None
+        i0, i1, i2 = bb_i, bb_j, i2[bb_i]
+        if TOTAL_NUM >= i0.shape[0]:
+            return i0, i1, i2, orig[0], orig[1], orig[2], None
+        is_bb = None
     else:
-        is_bb, num_bb = mark_best_buddies(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1)
-        TOTAL_NUM = args.GPF_factor * num_bb
+        is_bb = torch.zeros(i0.shape[0], dtype=torch.uint8, device=i0.device)
+        is_bb[bb_i] = 1
+        TOTAL_NUM = args.GPF_factor * int(bb_i.shape[0])
+    ratio = engine.match_ratio(f0, f1, i0, i1, i2)
+    keep, norm = engine.gpf_filter(ratio, is_bb, xyz0, i0, args.GPF_grid_wid, TOTAL_NUM)
+    sel = torch.nonzero(keep).squeeze(1)  # the one size read-back of the filter (as nn_to_mutual has)
+    return i0[sel], i1[sel], i2[sel], orig[0], orig[1], orig[2], norm[sel]
 
-    feat_dist = calc_distance_ratio_in_feature_space(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1,
-                                                     idx1_2nd).cpu()
-    m, M = torch.min(feat_dist), torch.max(feat_dist)
-    norm_feat_dist = (feat_dist - m) / (M - m)
-    if not BB_first:
-        norm_feat_dist[torch.from_numpy(is_bb)] -= 1  # best buddies sort first (matching.py:126-134)
 
-    def to_quads(X):
-        EPS = 10 ** -3
-        lo, hi = torch.min(X), torch.max(X)
-        return torch.floor(GRID_WID * ((X - lo) / (hi - lo + EPS)))
-
-    xyz0_c = xyz0.detach().cpu() if torch.is_tensor(xyz0) else torch.from_numpy(np.asarray(xyz0))
-    quadrant_i = to_quads(xyz0_c[corres_idx0, 0]).numpy()
-    quadrant_j = to_quads(xyz0_c[corres_idx0, 1]).numpy()
-    cell = (quadrant_i * GRID_WID + quadrant_j).astype(np.int64)
-    max_per_quad = np.bincount(cell, minlength=GRID_WID * GRID_WID).astype(np.float64).reshape(GRID_WID, GRID_WID)
-
-    def apply_height(height):
-        is_dwarf = max_per_quad < height
-        return is_dwarf * max_per_quad + (~is_dwarf) * height
-
-    max_height, min_height = TOTAL_NUM, 0
-    curr_height = (max_height + min_height) / 2
-    while np.abs(max_height - min_height) > 2:
-        cur_total = apply_height(curr_height).sum()
-        if cur_total == TOTAL_NUM:
-            break
-        elif cur_total < TOTAL_NUM:
-            min_height = curr_height
-        else:
-            max_height = curr_height
-        curr_height = (max_height + min_height) / 2
-    per_quad = apply_height(np.round(curr_height))
-
-    keep = np.zeros(len(norm_feat_dist), dtype=bool)
-    nfd = norm_feat_dist.numpy()
-    for qi in range(GRID_WID):
-        for qj in range(GRID_WID):
-            quota = int(per_quad[qi, qj])
-            if quota <= 0:
-                continue
-            cand = np.nonzero(cell == qi * GRID_WID + qj)[0]
-            if per_quad[qi, qj] == max_per_quad[qi, qj]:
-                keep[cand] = True
-            else:
-                order = torch.argsort(norm_feat_dist[cand]).numpy()  # same sort as matching.py:192
-                keep[cand[order[:quota]]] = True
-    del nfd
-
-    corres_idx0 = corres_idx0[keep]
-    corres_idx1 = corres_idx1[keep]
-    norm_feat_dist = norm_feat_dist[keep]
-    idx1_2nd = idx1_2nd[keep] if idx1_2nd is not None else None
-    return corres_idx0, corres_idx1, idx1_2nd, corres_idx0_orig, corres_idx1_orig, idx1_2nd_orig, norm_feat_dist
+def Grid_Prioritized_Filter(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args,
+                            BB_first=False):
+    """matching.py:100-205 (--mode GPF): best-buddy marking, 10x10 xy grid, water-filling quota, per-cell selection by
+    normalised ratio -- on the device (csrc/lr_gpf.cu); int64 / fp32 CPU tensors out like the reference."""
+    out = Grid_Prioritized_Filter_dev(fcgf_feats0, fcgf_feats1, corres_idx0, corres_idx1, idx1_2nd, xyz0, args, BB_first)
+    return tuple(None if t is None else t.cpu() for t in out)
 
 
 def measure_inlier_ratio(corres_idx0, corres_idx1, pcd0, pcd1, T_gt, voxel_size):

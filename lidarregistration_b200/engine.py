@@ -101,6 +101,24 @@ def gather_xyz(xyz, idx):
     return out
 
 
+def gpf_filter(ratio, is_bb, xyz0, idx0, grid_wid, total_num):
+    """lr_gpf_filter -> (keep[n] bool CUDA, norm[n] fp32 CUDA): the Grid-Prioritised Filter's selection on the device."""
+    ratio, xyz0 = to_dev_f32(ratio), to_dev_f32(xyz0)
+    n = ratio.shape[0]
+    keep = torch.zeros(n, dtype=torch.uint8, device=ratio.device)
+    norm = torch.empty(n, dtype=torch.float32, device=ratio.device)
+    if n == 0:
+        return keep.bool(), norm
+    if is_bb is not None:
+        is_bb = is_bb.to(ratio.device).to(torch.uint8).contiguous()
+    idx0 = to_dev_i64(idx0) if idx0 is not None else None
+    rc = _lib.lib().lr_gpf_filter(_lib.ptr(ratio), _lib.ptr(is_bb), _lib.ptr(xyz0), _lib.ptr(idx0), ctypes.c_int64(n),
+                                  int(grid_wid), ctypes.c_double(float(total_num)), _lib.ptr(keep), _lib.ptr(norm),
+                                  _lib.stream_ptr())
+    _lib.check(rc, "lr_gpf_filter")
+    return keep.bool(), norm
+
+
 # ------------------------------------------------------------------ RANSAC
 def make_params(threshold=0.6, confidence=1.0, max_iters=500000, seed=51, sample_size=3,
                 sampler=SAMPLER_UNIFORM, use_elc=True, elc_ratio=0.9, round_size=DEFAULT_ROUND, refit=True,

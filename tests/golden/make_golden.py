@@ -116,6 +116,38 @@ def gpf_case():
     print("gpf_ref.npz:", len(k0), "of", N, "pairs kept")
 
 
+def gpf_cases_ieee():
+    """The same filter with torch.sqrt replaced by a correctly rounded square root for the duration of the call.
+    Why: the reference computes the ratio quality on its GPU (FR.py:32-34 moves the features to the device; CUDA's
+    sqrtf is correctly rounded), while torch's CPU sqrt (MKL VML) is off by one ulp in ~0.5 % of the values -- enough to
+    swap two pairs at a cell's quota boundary.  With an IEEE sqrt the reference's unmodified Grid_Prioritized_Filter is
+    reproducible bit for bit, and the CUDA path is tested for exact equality against it (gpf_ref_ieee.npz)."""
+    from types import SimpleNamespace
+    orig_sqrt = torch.sqrt
+    torch.sqrt = lambda x, *a, **k: torch.from_numpy(np.sqrt(x.detach().cpu().numpy()))
+    try:
+        out = {}
+        import gpf_inputs
+        cases = gpf_inputs.CASES
+        for c, cs in enumerate(cases):
+            f0, f1, xyz0 = gpf_inputs.make(cs)
+            N = cs["N"]
+            t0, t1 = torch.from_numpy(f0), torch.from_numpy(f1)
+            i0, i1, i2 = RM.find_nn(t0, t1, return_2nd=True)
+            args = SimpleNamespace(GPF_factor=cs["phi"], GPF_grid_wid=10, GPF_max_matches=cs["cap"])
+            k0, k1, k2, o0, o1, o2, nfd = RM.Grid_Prioritized_Filter(t0, t1, i0, i1, i2, torch.from_numpy(xyz0), args,
+                                                                     BB_first=cs["bb_first"])
+            out.update({"keep0_%d" % c: k0.numpy(), "keep1_%d" % c: k1.numpy(), "keep2_%d" % c: k2.numpy(),
+                        "nfd_%d" % c: nfd.numpy() if nfd is not None else np.zeros(0, np.float32),
+                        "checksum_%d" % c: np.float64(f0.astype(np.float64).sum() + f1.astype(np.float64).sum() +
+                                                      xyz0.astype(np.float64).sum())})
+            print("gpf_ref_ieee case", c, ":", len(k0), "of", N, "pairs kept")
+        out["cases"] = np.int64(len(cases))
+        np.savez_compressed(os.path.join(OUT, "gpf_ref_ieee.npz"), **out)
+    finally:
+        torch.sqrt = orig_sqrt
+
+
 def refit_cases():
     """Refit over the inliers of a coarse model (FR.py:99-111): the reference's weighted_procrustes with 0/1
     weights = the inlier mask at 0.6 m.  Stored per case: correspondences, the coarse model, the mask, R, t."""
@@ -185,10 +217,14 @@ if __name__ == "__main__":
     if "--only-metrics" in sys.argv:
         metrics_cases()
         sys.exit(0)
+    if "--only-gpf-ieee" in sys.argv:
+        gpf_cases_ieee()
+        sys.exit(0)
     if "--only-refit" not in sys.argv:  # the older fixtures are kept byte-identical unless regenerated on purpose
         matching_cases()
         kabsch_cases()
         gpf_case()
+        gpf_cases_ieee()
     refit_cases()
     if "--only-refit" not in sys.argv:
         metrics_cases()

@@ -105,7 +105,7 @@ def test_cli_entry_runs():
 
 def test_batch_metrics_match_oracle_pipeline():
     """cfg 5 in miniature: RRE / RTE / recall of a batch equal the CPU oracle pipeline's (north star: within 0.1 %)."""
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "eval_pairs.py"), "--pairs", "6", "--points", "3000",
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "eval_pairs.py"), "--pairs", "6", "--points", "3000",
                           "--iters", "30000"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     import json
@@ -157,6 +157,31 @@ def test_gpf_matches_reference_golden(golden_dir):
     assert len(got) == len(ref) and len(got ^ ref) <= 4, (len(got), len(ref), len(got ^ ref))
     common = np.isin(k0.numpy(), g["keep0"])
     assert np.allclose(np.sort(nfd.numpy()[common])[:50], np.sort(g["nfd"])[:50], atol=1e-6)
+
+
+def test_gpf_exact_against_reference_with_ieee_sqrt(golden_dir):
+    """--mode GPF on the device (csrc/lr_gpf.cu) against the reference's UNMODIFIED Grid_Prioritized_Filter run with a
+    correctly rounded sqrt (what it computes with on its own GPU path; tests/golden/make_golden.py::gpf_cases_ieee):
+    kept pairs, their order, the 2nd neighbours and the returned normalised distances, bit for bit; RANSAC and TEASER
+    (BB_first) variants, a quota that bites / does not bite, clustered cells."""
+    sys.path.insert(0, golden_dir)
+    import gpf_inputs
+    from lidarregistration_b200.algorithms import Grid_Prioritized_Filter
+    g = np.load(os.path.join(golden_dir, "gpf_ref_ieee.npz"))
+    assert int(g["cases"]) == len(gpf_inputs.CASES)
+    for c, cs in enumerate(gpf_inputs.CASES):
+        f0, f1, xyz0 = gpf_inputs.make(cs)
+        chk = f0.astype(np.float64).sum() + f1.astype(np.float64).sum() + xyz0.astype(np.float64).sum()
+        assert chk == float(g["checksum_%d" % c]), "fixture inputs are not the ones the golden was made from"
+        t0, t1 = torch.from_numpy(f0), torch.from_numpy(f1)
+        i0, i1, i2 = find_nn(t0, t1, return_2nd=True)
+        args = make_args(GPF_factor=cs["phi"], GPF_max_matches=cs["cap"])
+        k0, k1, k2, o0, o1, o2, nfd = Grid_Prioritized_Filter(t0, t1, i0, i1, i2, torch.from_numpy(xyz0), args,
+                                                              BB_first=cs["bb_first"])
+        assert np.array_equal(k0.numpy(), g["keep0_%d" % c]), c
+        assert np.array_equal(k1.numpy(), g["keep1_%d" % c]) and np.array_equal(k2.numpy(), g["keep2_%d" % c]), c
+        assert np.array_equal(nfd.numpy(), g["nfd_%d" % c]), c  # fp32 values, exact
+        assert torch.equal(o0, i0) and torch.equal(o1, i1) and torch.equal(o2, i2)
 
 
 def test_icp_refinement_matches_oracle_and_improves():
