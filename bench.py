@@ -477,6 +477,21 @@ def bench_faithful_regime(engine, torch, resident, pair0):
         finally:
             O.set_o3d_faithful(False)
         fixed[variant] = {"ms_per_pair": dt * 1e3, "pairs_per_s": 1.0 / dt, "cores": O.num_threads()}
+    params = engine.make_params(threshold=THRESH, confidence=1.0, max_iters=ITERS, seed=51, use_elc=True, refit=True,
+                                sample_size=4, sampler=engine.SAMPLER_REPLACE)
+    for _ in range(3):
+        res = engine.ransac_rigid(a, b, params)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        res = engine.ransac_rigid(a, b, params)
+    e1.record()
+    torch.cuda.synchronize()
+    fixed["gpu_ms_per_pair"] = e0.elapsed_time(e1) / 10
+    fixed["gpu_h_scored"] = res["n_scored"]
+    fixed["gpu_over_faster_cpu_variant"] = min(fixed["cpu_lean"]["ms_per_pair"], fixed["cpu_faithful"]["ms_per_pair"]) / \
+        fixed["gpu_ms_per_pair"]
     out["open3d_m4_replace_fixed_budget"] = fixed
     return out
 

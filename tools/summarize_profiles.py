@@ -48,39 +48,57 @@ def launches(src, dst):
 
 
 def kernel(src, dst):
+    """one summary per profiled launch (distinct kernel names) of the report"""
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    h, units, vals = rows[0], rows[1], rows[2]
+    h, units = rows[0], rows[1]
+    seen = set()
     with open(dst, "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on (one launch).  source: %s\n" % src)
-        f.write("kernel: %s\n" % vals[h.index("Kernel Name")])
-        for i, n in enumerate(h):
-            if any(n.startswith(k) for k in KEYS) and ".min" not in n and ".max" not in n and ".sum.p" not in n \
-                    and "peak_sustained_elapsed" not in n.replace("sm__throughput", "").replace("gpu__dram", ""):
-                f.write("%-86s %s %s\n" % (n, vals[i], units[i]))
-        # top stall sites from the source page
-        srcp = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-        srows = list(csv.reader(srcp.splitlines()))
-        sh = srows[1]
-        isrc, ismp, iex = sh.index("Source"), sh.index("# Samples"), sh.index("Instructions Executed")
-        names = [n for n in sh if n.startswith("stall_") and "Not Issued" not in n]
-        data = []
-        for r in srows[2:]:
-            try:
-                data.append((int(r[ismp]), int(r[iex]), r[isrc], r))
-            except (ValueError, IndexError):
-                pass
-        tot = sum(d[0] for d in data) or 1
-        agg = collections.Counter()
-        for d in data:
-            for n in names:
-                v = d[3][sh.index(n)]
-                if v not in ("0", ""):
-                    agg[n] += int(v)
-        f.write("\nwarp-stall samples by reason (all warps): " + ", ".join("%s %.1f%%" % (k[6:], 100 * v / tot) for k, v in agg.most_common(8)) + "\n")
-        f.write("top sampled SASS instructions:\n")
-        for d in sorted(data, key=lambda x: -x[0])[:12]:
-            f.write("  %5.1f%%  executed %10d  %s\n" % (100 * d[0] / tot, d[1], d[2][:90]))
+        f.write("# ncu --set full --clock-control none --import-source on.  source: %s\n" % src)
+        for vals in rows[2:]:
+            name = vals[h.index("Kernel Name")]
+            if name in seen:
+                continue
+            seen.add(name)
+            f.write("\nkernel: %s\n" % name)
+            for i, n in enumerate(h):
+                if any(n.startswith(k) for k in KEYS) and ".min" not in n and ".max" not in n and ".sum.p" not in n \
+                        and "peak_sustained_elapsed" not in n.replace("sm__throughput", "").replace("gpu__dram", ""):
+                    f.write("%-86s %s %s\n" % (n, vals[i], units[i]))
+            short = name.split("(")[0].split("::")[-1].replace("void ", "").split("<")[0]
+            # top stall sites from the source page of this kernel
+            srcp = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--kernel-name", "regex:" + short],
+                                  capture_output=True, text=True).stdout
+            srows = list(csv.reader(srcp.splitlines()))
+            sh = None
+            for k, r in enumerate(srows[:6]):
+                if "Source" in r and "# Samples" in r:
+                    sh, first = r, k + 1
+                    break
+            if sh is None:
+                continue
+            isrc, ismp, iex = sh.index("Source"), sh.index("# Samples"), sh.index("Instructions Executed")
+            names = [n for n in sh if n.startswith("stall_") and "Not Issued" not in n]
+            data = []
+            for r in srows[first:]:
+                if r and r[0] == sh[0]:
+                    break  # the next launch's listing
+                try:
+                    data.append((int(r[ismp]), int(r[iex]), r[isrc], r))
+                except (ValueError, IndexError):
+                    pass
+            tot = sum(d[0] for d in data) or 1
+            agg = collections.Counter()
+            for d in data:
+                for n in names:
+                    v = d[3][sh.index(n)]
+                    if v not in ("0", ""):
+                        agg[n] += int(v)
+            f.write("warp-stall samples by reason (all warps): " +
+                    ", ".join("%s %.1f%%" % (k[6:], 100 * v / tot) for k, v in agg.most_common(8)) + "\n")
+            f.write("top sampled SASS instructions:\n")
+            for d in sorted(data, key=lambda x: -x[0])[:12]:
+                f.write("  %5.1f%%  executed %10d  %s\n" % (100 * d[0] / tot, d[1], d[2][:90]))
     print(open(dst).read())
 
 
