@@ -266,6 +266,38 @@ int lr_transform_pad8(const float *xyz, int64_t n, const double *T_in, float *ou
 int lr_icp_step(const float *xyz0, const float *xyz1, const int64_t *i0, const int64_t *i1, int64_t K,
                 const double *T_in, double threshold, double *T_out, int64_t *count, double *err2, void *stream);
 
+/* The whole refinement on the device (replaces the Open3D call of Experiments/test.py:183-188,
+ * registration_icp(src, tgt, max_dist, T_init, TransformationEstimationPointToPoint()), Open3D defaults
+ * max_iteration 30, relative_fitness = relative_rmse = 1e-6): the target is binned once into a hashed uniform grid of
+ * max_dist-sized cells; every iteration is ONE kernel (transform, nearest target inside max_dist -- strict, ties ->
+ * lowest index --, sums, Kabsch, stopping rule) and all iterations are enqueued up front.
+ * src [n,3], tgt [m,3] fp32 [device]; T_init[16] [host, nullable = identity]; T_out[16], *fitness (= pairs / n),
+ * *inlier_rmse, *iterations [host, nullable except T_out].  Synchronises `stream`. */
+int lr_icp_refine(const float *src, int64_t n, const float *tgt, int64_t m, double max_dist, const double *T_init,
+                  int max_iteration, double rel_fitness, double rel_rmse, double *T_out, double *fitness,
+                  double *inlier_rmse, int *iterations, void *stream);
+
+/* The search of one ICP iteration on its own (parity hook): idx[i] [device, int64] = nearest row of tgt to
+ * T_in * src[i] with squared distance < radius^2 (-1 = none), d2[i] [device, nullable] that squared distance. */
+int lr_nn3d_radius(const float *src, int64_t n, const float *tgt, int64_t m, const double *T_in, double radius,
+                   int64_t *idx, double *d2, void *stream);
+
+/* ---- PointDSC seed scoring, SURVEY 8(f4) (Experiments/models/PointDSC.py:293-336) --------------------- */
+
+/* rigid_transform_3d over S neighbourhoods (Experiments/models/common.py:7-45, the call of PointDSC.py:318):
+ * A, B [S,k,3] fp32, w [S,k] fp32 (nullable = ones) -> T_out [S,16] fp64 (4x4 row-major, column-vector
+ * convention), all [device].  Centroids divide by (sum w + 1e-6) as the reference does.  Asynchronous. */
+int lr_kabsch_weighted_batch(const float *A, const float *B, const float *w, int64_t S, int k, double *T_out,
+                             void *stream);
+
+/* PointDSC.py:319-331: every seed transform (models [S,16] fp64 [device]) against all n correspondences on the
+ * tensor-core inlier sweep: counts[S] [device, nullable] = #(|T p - q| < threshold) (fitness = counts / n),
+ * *best [host] = arg-max (first maximum), T_best[16] [host] = its transform, labels[n] [device, nullable] =
+ * its inlier mask, T_refit[16] [host, nullable] = Kabsch over those inliers.  Synchronises `stream`. */
+int lr_seeds_score(const float *src, const float *tgt, int64_t n, const double *models, int64_t S, double threshold,
+                   int32_t *counts, uint8_t *labels, int64_t *best, int64_t *best_count, double *T_best,
+                   double *T_refit, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,10 +2,11 @@
 `o3d.pipelines.registration.registration_icp(src, tgt, 0.6, T_init, TransformationEstimationPointToPoint())`
 (Experiments/test.py:183-188; Open3D defaults: 30 iterations, relative fitness / rmse 1e-6).
 
-Composed from the hot path's own kernels: the source is transformed and padded to 8 floats
-(lr_transform_pad8), its nearest target point comes from the exact fp32 sweep (lr_match_nn, D = 8),
-and one lr_icp_step keeps the pairs closer than the threshold, accumulates fitness / rmse and
-solves Kabsch on them.
+The whole refinement runs on the device (lr_icp_refine): the target is binned once into a hashed uniform grid of
+max_correspondence_distance-sized cells -- the role of Open3D's KD-tree --, every iteration is one kernel (transform,
+nearest target inside the distance, sums, Kabsch, stopping rule), all iterations are enqueued up front and there is
+one synchronisation per call.  `registration_icp_bruteforce` keeps round 2's first composition (exact fp32 sweep,
+lr_match_nn with D = 8, one lr_icp_step per iteration) for A/B timing.
 """
 import numpy as np
 
@@ -19,11 +20,22 @@ class RegistrationResult:
         self.transformation, self.fitness, self.inlier_rmse, self.iterations = transformation, fitness, inlier_rmse, iterations
 
 
+def _cloud(x):
+    return engine.to_dev_f32(np.asarray(x.points, dtype=np.float32) if hasattr(x, "points") else x)
+
+
 def registration_icp(source, target, max_correspondence_distance, init=None, max_iteration=30, relative_fitness=1e-6,
                      relative_rmse=1e-6):
     """source / target: [n,3] / [m,3] arrays, tensors or point clouds with `.points`."""
-    src = engine.to_dev_f32(np.asarray(source.points, dtype=np.float32) if hasattr(source, "points") else source)
-    tgt = engine.to_dev_f32(np.asarray(target.points, dtype=np.float32) if hasattr(target, "points") else target)
+    T, fitness, rmse, it = engine.icp_refine(_cloud(source), _cloud(target), max_correspondence_distance, init, max_iteration,
+                                             relative_fitness, relative_rmse)
+    return RegistrationResult(T, fitness, rmse, it)
+
+
+def registration_icp_bruteforce(source, target, max_correspondence_distance, init=None, max_iteration=30,
+                                relative_fitness=1e-6, relative_rmse=1e-6):
+    """the same loop with the nearest neighbour taken from the exact fp32 sweep over ALL target points"""
+    src, tgt = _cloud(source), _cloud(target)
     T = np.eye(4) if init is None else np.asarray(init, dtype=np.float64).copy()
     n = src.shape[0]
     tgt8 = engine.transform_pad8(tgt, np.eye(4))

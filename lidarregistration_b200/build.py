@@ -11,9 +11,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(CSRC, "liblidarreg.so")
+# LIDARREG_SO: load (and build into) another file than the product library -- A/B builds of a kernel (tools/build_variants.py)
+SO = os.environ.get("LIDARREG_SO") or os.path.join(CSRC, "liblidarreg.so")
 SOURCES = ["lr_core.cu", "lr_prof.cu", "lr_ransac.cu", "lr_match.cu", "lr_match_tc.cu", "lr_gpf.cu"]
-HEADERS = ["lr_common.cuh", "lr_match_tc.cuh", "lr_ransac_gc.cuh", "lr_score_tc.cuh", os.path.join("..", "..", "include", "lidarreg.h")]
+HEADERS = ["lr_common.cuh", "lr_match_tc.cuh", "lr_ransac_gc.cuh", "lr_score_tc.cuh", "lr_icp.cuh", "lr_icp_api.cuh", os.path.join("..", "..", "include", "lidarreg.h")]
 
 # -fmad=false: the canonical fp64/fp32 arithmetic must not be contracted behind
 # our back; every FMA the kernels want is written as fmaf()/fma() explicitly.

@@ -98,7 +98,7 @@ int sm_count()
 
 LR_EXPORT const char *lr_last_error(void) { return lr::g_err; }
 
-LR_EXPORT int lr_version(void) { return 130; }  // 130: lr_gpf_filter; 120: lr_comm_*, lr_ransac_rigid_sharded, lr_ransac_tc_probe
+LR_EXPORT int lr_version(void) { return 140; }  // 140: lr_icp_refine, lr_nn3d_radius, lr_seeds_score, lr_kabsch_weighted_batch; 130: lr_gpf_filter; 120: lr_comm_*, lr_ransac_rigid_sharded, lr_ransac_tc_probe
 
 LR_EXPORT int lr_device_info(int *sms, int *major, int *minor)
 {

@@ -38,6 +38,7 @@ constexpr int kGroup = 4;           // points whose first residual component is 
 constexpr int kBlock = 32;          // points between two checks of the "some residual is in the band" flag
 constexpr int kGenThreads = 128;
 constexpr int kGcMaxTrials = 64;    // inner LO draws scored by one launch
+int g_dbg_rank = 0, g_dbg_world = 1;  // lr_debug_slice
 int g_score_mode = 0;               // lr_ransac_set_mode: 0 = tensor-core sweep, 1 = fp32 sweep in full, 2 = fp32 sweep with
                                     // the first-component early-out (A/B)
 
@@ -2009,6 +2010,8 @@ __global__ void k_probe_install(const double *__restrict__ models, int H, const 
     if (E_out) E_out[h] = Et;
 }
 
+#include "lr_icp.cuh"
+
 }  // namespace
 
 #ifdef LR_TCS_TRACE
@@ -2053,9 +2056,19 @@ LR_EXPORT int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, con
     const LrRansacParams &p = *params;
     if (n < p.sample_size) return identity_result(n, T_out, T_refit, mask, stats, st);  // Open3D: |corres| < ransac_n (App. B)
     Ws ws;
-    rc = enqueue_run(src, tgt, n, p, lr::SLOT_RANSAC, ws, st);
+    rc = enqueue_run(src, tgt, n, p, lr::SLOT_RANSAC, ws, st, nullptr, g_dbg_rank, g_dbg_world);
     if (rc) return rc;
     return finish(src, tgt, n, p, ws, p.scoring == LR_SCORE_MSAC ? FIN_GC : FIN_MODEL_READY, 0, T_out, T_refit, mask, stats, st);
+}
+
+// timing aid (tools/pair_breakdown.py): lr_ransac_rigid then generates and scores only rank's slice of every round, with no
+// exchange -- what ONE rank of a hypothesis-sharded run executes, measurable on a single GPU.  (0, 1) restores the default.
+LR_EXPORT int lr_debug_slice(int rank, int world)
+{
+    LR_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank / world out of range");
+    g_dbg_rank = rank;
+    g_dbg_world = world;
+    return LR_OK;
 }
 
 // ---- hypothesis sharding with a library-owned communicator over NVLink peer memory --------------------------
@@ -2503,3 +2516,5 @@ LR_EXPORT int lr_refit_indexed(const float *xyz0, const float *xyz1, const int64
     if (count) *count = h.refit_count;
     return LR_OK;
 }
+
+#include "lr_icp_api.cuh"

@@ -413,3 +413,67 @@ def icp_step(xyz0, xyz1, i1, T, threshold):
                                 _lib.stream_ptr())
     _lib.check(rc, "lr_icp_step")
     return _lib.T_from16(Tout), int(cnt.value), float(err2.value)
+
+
+def nn3d_radius(src, tgt, T, radius):
+    """lr_nn3d_radius -> (idx[n] int64 CUDA, d2[n] fp64 CUDA): nearest row of tgt to T * src[i] inside the radius, -1 = none"""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    n, m = src.shape[0], tgt.shape[0]
+    idx = torch.empty(n, dtype=torch.int64, device=src.device)
+    d2 = torch.empty(n, dtype=torch.float64, device=src.device)
+    Tin = (ctypes.c_double * 16)(*np.asarray(T, dtype=np.float64).reshape(-1))
+    rc = _lib.lib().lr_nn3d_radius(_lib.ptr(src), ctypes.c_int64(n), _lib.ptr(tgt), ctypes.c_int64(m), Tin,
+                                   ctypes.c_double(radius), _lib.ptr(idx), _lib.ptr(d2), _lib.stream_ptr())
+    _lib.check(rc, "lr_nn3d_radius")
+    return idx, d2
+
+
+def icp_refine(src, tgt, max_dist, T_init=None, max_iteration=30, rel_fitness=1e-6, rel_rmse=1e-6):
+    """lr_icp_refine: the whole point-to-point ICP on the device -> (T[4,4], fitness, inlier_rmse, iterations)"""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    Tin = None if T_init is None else (ctypes.c_double * 16)(*np.asarray(T_init, dtype=np.float64).reshape(-1))
+    Tout = (ctypes.c_double * 16)()
+    fit, rmse, it = ctypes.c_double(0.0), ctypes.c_double(0.0), ctypes.c_int(0)
+    rc = _lib.lib().lr_icp_refine(_lib.ptr(src) if src.shape[0] else None, ctypes.c_int64(src.shape[0]),
+                                  _lib.ptr(tgt) if tgt.shape[0] else None, ctypes.c_int64(tgt.shape[0]),
+                                  ctypes.c_double(max_dist), Tin, int(max_iteration), ctypes.c_double(rel_fitness),
+                                  ctypes.c_double(rel_rmse), Tout, ctypes.byref(fit), ctypes.byref(rmse), ctypes.byref(it),
+                                  _lib.stream_ptr())
+    _lib.check(rc, "lr_icp_refine")
+    return _lib.T_from16(Tout), float(fit.value), float(rmse.value), int(it.value)
+
+
+# ------------------------------------------------------- PointDSC seed scoring
+def kabsch_weighted_batch(A, B, w=None):
+    """lr_kabsch_weighted_batch: A, B [S,k,3], w [S,k] | None -> [S,4,4] fp64 CUDA tensor"""
+    A, B = to_dev_f32(A), to_dev_f32(B)
+    w = None if w is None else to_dev_f32(w)
+    S, k = int(A.shape[0]), int(A.shape[1])
+    out = torch.empty((S, 4, 4), dtype=torch.float64, device=A.device)
+    if S == 0:
+        return out
+    rc = _lib.lib().lr_kabsch_weighted_batch(_lib.ptr(A), _lib.ptr(B), _lib.ptr(w), ctypes.c_int64(S), k, _lib.ptr(out),
+                                             _lib.stream_ptr())
+    _lib.check(rc, "lr_kabsch_weighted_batch")
+    return out
+
+
+def seeds_score(src, tgt, models, threshold, want_labels=True, want_refit=False):
+    """lr_seeds_score: models [S,4,4] -> dict(counts[S] int32 CUDA, best, best_count, T, labels[n] bool CUDA | None,
+    T_refit | None)"""
+    src, tgt = to_dev_f32(src), to_dev_f32(tgt)
+    if isinstance(models, np.ndarray):
+        models = torch.from_numpy(np.ascontiguousarray(models))
+    models = models.detach().to(src.device).to(torch.float64).reshape(-1, 16).contiguous()
+    n, S = int(src.shape[0]), int(models.shape[0])
+    counts = torch.empty(S, dtype=torch.int32, device=src.device)
+    labels = torch.empty(n, dtype=torch.uint8, device=src.device) if want_labels else None
+    T = (ctypes.c_double * 16)()
+    Tr = (ctypes.c_double * 16)() if want_refit else None
+    best, bc = ctypes.c_int64(-1), ctypes.c_int64(-1)
+    rc = _lib.lib().lr_seeds_score(_lib.ptr(src), _lib.ptr(tgt), ctypes.c_int64(n), _lib.ptr(models), ctypes.c_int64(S),
+                                   ctypes.c_double(threshold), _lib.ptr(counts), _lib.ptr(labels), ctypes.byref(best),
+                                   ctypes.byref(bc), T, Tr, _lib.stream_ptr())
+    _lib.check(rc, "lr_seeds_score")
+    return dict(counts=counts, best=int(best.value), best_count=int(bc.value), T=_lib.T_from16(T),
+                labels=labels.bool() if want_labels else None, T_refit=_lib.T_from16(Tr) if want_refit else None)

@@ -858,6 +858,81 @@ LRO_API int64_t lro_refit_indexed(const float *xyz0, const float *xyz1, const in
     return k;
 }
 
+/* ------------------------------------------------------------------------- */
+/* the consumers right after the path                          */
+/* ------------------------------------------------------------------------- */
+
+/* Weighted Kabsch of one neighbourhood -- Experiments/models/common.py:7-45 (rigid_transform_3d, the call of
+ * Experiments/models/PointDSC.py:318 with total_weight): centroids = sum w x / (sum w + 1e-6) (:24-25),
+ * H = Am^T diag(w) Bm (:32-33), R = V diag(1,1,det(V U^T)) U^T (:36-41), t = cB - R cA (:42).  Sums in index
+ * order, fp64 on the fp32 inputs.  A, B: k x 3; w: k (nullable = ones). */
+LRO_API void lro_kabsch_weighted(const float *A, const float *B, const float *w, int64_t k, double T[12])
+{
+    double sw = 0.0, ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+    for (int64_t i = 0; i < k; ++i) {
+        const double wi = w ? (double)w[i] : 1.0;
+        sw = sw + wi;
+        for (int c = 0; c < 3; ++c) {
+            ca[c] = ca[c] + wi * (double)A[3 * i + c];
+            cb[c] = cb[c] + wi * (double)B[3 * i + c];
+        }
+    }
+    const double den = sw + 1e-6;
+    for (int c = 0; c < 3; ++c) { ca[c] = ca[c] / den; cb[c] = cb[c] / den; }
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; /* sum w (b - cb)(a - ca)^T: the transpose of the reference's H */
+    for (int64_t i = 0; i < k; ++i) {
+        const double wi = w ? (double)w[i] : 1.0;
+        double da[3], db[3];
+        for (int c = 0; c < 3; ++c) { da[c] = (double)A[3 * i + c] - ca[c]; db[c] = (double)B[3 * i + c] - cb[c]; }
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) H[3 * r + c] = H[3 * r + c] + (wi * db[r]) * da[c];
+    }
+    double R[9];
+    lro_rot_from_H(H, R);
+    for (int r = 0; r < 3; ++r) {
+        T[4 * r + 0] = R[3 * r + 0];
+        T[4 * r + 1] = R[3 * r + 1];
+        T[4 * r + 2] = R[3 * r + 2];
+        T[4 * r + 3] = cb[r] - ((R[3 * r + 0] * ca[0] + R[3 * r + 1] * ca[1]) + R[3 * r + 2] * ca[2]);
+    }
+}
+
+/* Seed scoring -- Experiments/models/PointDSC.py:319-336: every seed's transform is applied to all n
+ * correspondences, fitness = #(|T p - q| < thr) / n (:323-324), the best seed is the arg-max (first maximum, :326),
+ * final labels = its inlier mask (:330-331).  models: S x 12 ([R|t] rows).  Returns the best seed. */
+LRO_API int64_t lro_seeds_score(const float *src, const float *tgt, int64_t n, const double *models, int64_t S,
+                                double thr, int32_t *counts, uint8_t *labels)
+{
+    int64_t best = 0, best_c = -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s) counts[s] = (int32_t)lro_count_inliers(src, tgt, n, models + 12 * s, thr, NULL);
+    for (int64_t s = 0; s < S; ++s)
+        if ((int64_t)counts[s] > best_c) { best_c = counts[s]; best = s; }
+    if (labels && S > 0) lro_count_inliers(src, tgt, n, models + 12 * best, thr, labels);
+    return S > 0 ? best : -1;
+}
+
+/* Nearest target point of every transformed source point within a radius -- what Open3D's registration_icp
+ * (Experiments/test.py:183-188) asks of its KD-tree (SearchHybrid(point, max_correspondence_distance, 1)): brute
+ * force over all m targets, canonical squared distance of lro_res2, strict d^2 < radius^2, ties -> lowest index.
+ * idx[i] = -1 when no target is inside the radius. */
+LRO_API void lro_nn3d_radius(const float *src, int64_t n, const float *tgt, int64_t m, const double T[12],
+                             double radius, int64_t *idx, double *d2)
+{
+    const double r2 = radius * radius;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double best = r2;
+        int64_t bj = -1;
+        for (int64_t j = 0; j < m; ++j) {
+            const double d = lro_res2(T, src + 3 * i, tgt + 3 * j);
+            if (d < best) { best = d; bj = j; }
+        }
+        idx[i] = bj;
+        if (d2) d2[i] = bj >= 0 ? best : 0.0;
+    }
+}
+
 LRO_API int lro_num_threads(void)
 {
 #ifdef _OPENMP

@@ -89,6 +89,7 @@ def lib():
         _lib.lro_score_samples_msac.restype = ctypes.c_int64
         _lib.lro_elc.restype = ctypes.c_int
         _lib.lro_num_threads.restype = ctypes.c_int
+        _lib.lro_seeds_score.restype = ctypes.c_int64
     return _lib
 
 
@@ -309,30 +310,55 @@ def refit_indexed(xyz0, xyz1, i0, i1, T, thr):
     return _T44(out), int(k)
 
 
+def kabsch_weighted(A, B, w=None):
+    """Experiments/models/common.py:7-45 (rigid_transform_3d) for one neighbourhood: A, B [k,3], w [k] -> 4x4."""
+    A, B = _f32(A), _f32(B)
+    w = None if w is None else _f32(w)
+    T = np.empty(12, np.float64)
+    lib().lro_kabsch_weighted(_p(A, c_f32p), _p(B, c_f32p), _p(w, c_f32p) if w is not None else None,
+                              ctypes.c_int64(A.shape[0]), _p(T, c_f64p))
+    return _T44(T)
+
+
+def seeds_score(src, tgt, models, thr, return_labels=False):
+    """Experiments/models/PointDSC.py:319-336: models [S,4,4] -> (counts[S], best seed[, labels of the best])."""
+    src, tgt = _f32(src), _f32(tgt)
+    M = np.ascontiguousarray(np.asarray(models, dtype=np.float64)[:, :3, :].reshape(len(models), 12))
+    counts = np.empty(len(M), np.int32)
+    labels = np.empty(src.shape[0], np.uint8) if return_labels else None
+    best = lib().lro_seeds_score(_p(src, c_f32p), _p(tgt, c_f32p), ctypes.c_int64(src.shape[0]), _p(M, c_f64p),
+                                 ctypes.c_int64(len(M)), ctypes.c_double(thr), _p(counts, c_i32p),
+                                 _p(labels, c_u8p) if return_labels else None)
+    return (counts, int(best), labels.astype(bool)) if return_labels else (counts, int(best))
+
+
+def nn3d_radius(src, tgt, T, radius):
+    """nearest target of every T-transformed source point with d^2 < radius^2 (brute force) -> (idx, d2); -1 = none"""
+    src, tgt = _f32(src), _f32(tgt)
+    T12 = np.ascontiguousarray(np.asarray(T, dtype=np.float64)[:3, :].reshape(-1))
+    idx = np.empty(src.shape[0], np.int64)
+    d2 = np.empty(src.shape[0], np.float64)
+    lib().lro_nn3d_radius(_p(src, c_f32p), ctypes.c_int64(src.shape[0]), _p(tgt, c_f32p), ctypes.c_int64(tgt.shape[0]),
+                          _p(T12, c_f64p), ctypes.c_double(radius), _p(idx, c_i64p), _p(d2, c_f64p))
+    return idx, d2
+
+
 def icp(src, tgt, max_dist, init=None, max_iteration=30, rel_fitness=1e-6, rel_rmse=1e-6):
     """Point-to-point ICP (Experiments/test.py:183-188 / Open3D registration_icp semantics) from the oracle's
-    own primitives: exact NN of the transformed source in the target (canonical fp32 distance on zero-padded
-    8-vectors), pairs closer than max_dist, Kabsch.  -> (T, fitness, inlier_rmse, iterations)"""
+    own primitives: nearest target of every transformed source point inside max_dist (brute force, canonical
+    fp64 squared distance, ties -> lowest index), Kabsch over those pairs, Open3D's relative fitness / rmse
+    stopping rule.  -> (T, fitness, inlier_rmse, iterations)"""
     src, tgt = _f32(src), _f32(tgt)
     T = np.eye(4) if init is None else np.asarray(init, dtype=np.float64).copy()
     n = len(src)
-    tgt8 = np.zeros((len(tgt), 8), np.float32)
-    tgt8[:, :3] = tgt
 
     def evaluate(T):
-        p = src.astype(np.float64)
-        moved = np.stack([((T[r, 0] * p[:, 0] + T[r, 1] * p[:, 1]) + T[r, 2] * p[:, 2]) + T[r, 3] for r in range(3)], 1)
-        src8 = np.zeros((n, 8), np.float32)
-        src8[:, :3] = moved.astype(np.float32)
-        _, idx, _ = find_nn(src8, tgt8)
-        q = tgt[idx].astype(np.float64)
-        d = moved - q
-        r2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
-        keep = r2 < max_dist * max_dist
-        cnt = int(keep.sum())
-        T_new, k = refit_indexed(src, tgt, np.arange(n), idx, T, max_dist)
+        idx, d2 = nn3d_radius(src, tgt, T, max_dist)
+        keep = np.nonzero(idx >= 0)[0]
+        cnt = len(keep)
+        T_new, k = refit_indexed(src, tgt, keep, idx[keep], T, max_dist)
         assert k == cnt
-        return T_new, cnt / n, float(np.sqrt(r2[keep].sum() / cnt)) if cnt else 0.0
+        return T_new, cnt / n, float(np.sqrt(d2[keep].sum() / cnt)) if cnt else 0.0
 
     T_next, fitness, rmse = evaluate(T)
     it = 0

@@ -45,3 +45,18 @@ def refit_golden(golden_dir):
         case, field = key.split("/")
         cases.setdefault(case, {})[field] = z[key]
     return [cases[k] for k in sorted(cases)]
+
+
+@pytest.fixture(scope="session")
+def seeds_golden(golden_dir):
+    """4 runs of the reference's PointDSC.cal_seed_trans (Experiments/models/PointDSC.py:234-336, unmodified, CPU):
+    neighbourhoods + weights handed to rigid_transform_3d, per-seed transforms, fitness, best transform, final labels
+    (tests/golden/make_golden.py::seeds_cases)"""
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "seeds_ref.npz"))
+    thr = float(z["threshold"])
+    cases = []
+    for c in range(int(z["num_cases"])):
+        cases.append({k[len("c%d_" % c):]: z[k] for k in z.files if k.startswith("c%d_" % c)})
+        cases[-1]["threshold"] = thr
+    return cases

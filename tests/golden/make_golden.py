@@ -10,6 +10,8 @@ Imports, unmodified:
                                                          inlier mask, FR.py:99-111 / SURVEY 8 a13-a14)
   /root/reference/Experiments/libs/loss.py              (TransformationLoss: the RE / TE / recall definitions
                                                          behind stats columns 0-2, Experiments/test.py:325-331)
+  /root/reference/Experiments/models/PointDSC.py        (PointDSC.cal_seed_trans, :234-336: per-seed weighted
+                                                         Kabsch + seed scoring -- the consumer of SURVEY 8(f4))
 on CPU torch and stores inputs + the reference's outputs as .npz.
 """
 import os
@@ -212,8 +214,56 @@ def metrics_cases():
     print("metrics_ref.npz: 60 cases,", int(np.sum(OKs)), "successes")
 
 
+def seeds_cases():
+    """PointDSC.cal_seed_trans (Experiments/models/PointDSC.py:234-336), run unmodified on CPU: the arguments it hands
+    to rigid_transform_3d (neighbourhoods + weights) are recorded through a wrapper, its outputs are the per-seed
+    transforms, the per-seed fitness, the best transform and the final labels."""
+    import models.PointDSC as PD
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from lidarregistration_b200 import synthetic
+    rec = {}
+    real = PD.rigid_transform_3d
+
+    def spy(A, B, w=None, weight_threshold=0):
+        rec["A"], rec["B"], rec["w"] = A.clone(), B.clone(), w.clone()
+        return real(A, B, w, weight_threshold)
+
+    PD.rigid_transform_3d = spy
+    out = {}
+    cases = [(3000, 0.4, 200, 40), (2000, 0.15, 128, 40), (4096, 0.6, 300, 24), (500, 0.3, 50, 40)]
+    for c, (n, inl, S, k) in enumerate(cases):
+        d = synthetic.make_correspondences(n, inl, seed=9100 + c)
+        torch.manual_seed(100 + c)
+        model = PD.PointDSC(inlier_threshold=0.6, sigma_d=1.2, k=k).eval()
+        src, tgt = torch.from_numpy(d["src"])[None], torch.from_numpy(d["tgt"])[None]
+        # correspondence features: inliers share a direction, so feature-space neighbourhoods of inlier seeds are
+        # mostly inliers (what the trained encoder is for); outliers get random unit vectors
+        g = torch.Generator().manual_seed(7 + c)
+        feat = torch.randn(n, 16, generator=g)
+        inl_mask = torch.from_numpy(d["is_inlier"])
+        if inl_mask is not None:
+            feat[inl_mask] = 0.35 * feat[inl_mask] + torch.tensor([1.0] + [0.0] * 15)
+        feat = torch.nn.functional.normalize(feat, dim=1)[None]
+        seeds = torch.randperm(n, generator=g)[:S][None]
+        with torch.no_grad():
+            trans, fitness, final_trans, final_labels = model.cal_seed_trans(seeds, feat, src, tgt)
+        out.update({"c%d_src" % c: d["src"], "c%d_tgt" % c: d["tgt"], "c%d_A" % c: rec["A"].numpy(),
+                    "c%d_B" % c: rec["B"].numpy(), "c%d_w" % c: rec["w"].numpy(), "c%d_trans" % c: trans[0].numpy(),
+                    "c%d_fitness" % c: fitness[0].numpy(), "c%d_final_trans" % c: final_trans[0].numpy(),
+                    "c%d_final_labels" % c: final_labels[0].numpy().astype(np.uint8)})
+        print("seeds case", c, "n", n, "S", S, "k", k, "best fitness %.4f" % float(fitness.max()),
+              "argmax", int(fitness.argmax()))
+    PD.rigid_transform_3d = real
+    out["num_cases"] = np.array(len(cases))
+    out["threshold"] = np.array(0.6)
+    np.savez_compressed(os.path.join(OUT, "seeds_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    if "--only-seeds" in sys.argv:
+        seeds_cases()
+        sys.exit(0)
     if "--only-metrics" in sys.argv:
         metrics_cases()
         sys.exit(0)

@@ -1,6 +1,6 @@
 """Where one cfg-3 pair's time goes on one GPU: library CUDA events around reset + pack, gen + Kabsch, the sweep, the
 round end, the finish kernel, against the wall time of the call (host launch + synchronisation included).
-usage: python tools/pair_breakdown.py [elc 0|1]"""
+usage: python tools/pair_breakdown.py [elc 0|1] [world]   (world > 1: rank 0's slice of a hypothesis-sharded run, no exchange)"""
 import json
 import os
 import sys
@@ -13,6 +13,11 @@ sys.path.insert(0, ROOT)
 from lidarregistration_b200 import engine, synthetic  # noqa: E402
 
 elc = bool(int(sys.argv[1])) if len(sys.argv) > 1 else True
+world = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if world > 1:
+    import ctypes
+    from lidarregistration_b200 import _lib
+    _lib.check(_lib.lib().lr_debug_slice(0, world), "lr_debug_slice")
 d = synthetic.make_correspondences(30000, 0.3, seed=51 + 3000)
 a, b = engine.to_dev_f32(d["src"]), engine.to_dev_f32(d["tgt"])
 p = engine.make_params(threshold=0.6, confidence=1.0, max_iters=1000000, seed=51, use_elc=elc)
@@ -32,7 +37,7 @@ engine.prof_enable(True)
 for _ in range(reps):
     engine.ransac_rigid(a, b, p)
 engine.prof_enable(False)
-out = {"wall_ms_per_pair": wall, "elc": elc}
+out = {"wall_ms_per_pair": wall, "elc": elc, "world": world}
 tot = 0.0
 for name, k in kinds.items():
     ms, n = engine.prof_read(k)
