@@ -192,6 +192,12 @@ def run_ours(args):
     def step_resident():  # the rank's pairs through the batched entry (two pairs in flight, one host sync)
         return engine.ransac_rigid_batch(resident, params)[-1]
 
+    def step_e2e_batch():
+        # the rank's pairs from pinned HOST memory through the C ABI's per-set entry (lr_ransac_rigid_batch = the loop of
+        # Experiments/test.py:108-167 over the rank's pairs): the library copies pair i + 1 in under the kernels of pair i;
+        # poses + statistics come back in pinned host memory, one synchronisation per step
+        return engine.ransac_rigid_batch(host, params)[-1]
+
     def step_e2e():
         out = None
         for a, b in host:  # pinned HOST buffers through the reference-facing call (GC_RANSAC.py:46-49)
@@ -240,7 +246,9 @@ def run_ours(args):
     ms_single, _ = timed(step_single, prof_steps, 1, prof=True)
     score_ms, score_launches = engine.prof_read(engine.PROF_SCORE)
     gen_ms, gen_launches = engine.prof_read(engine.PROF_GEN)
-    ms_e2e, last_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_call, last_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e, last_e2e_b = timed(step_e2e_batch, args.steps, args.warmup)
+    assert last_e2e_b["best_id"] == last["best_id"] and last_e2e_b["best_count"] == last["best_count"]
     sampler.stop()
     clocks = sampler.summary() if rank == 0 else None
 
@@ -260,7 +268,18 @@ def run_ours(args):
             "best_count": last["best_count"],
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": PAIRS_PER_STEP * 2 * N_CORR * 12,
-                    "d2h_bytes_per_step": PAIRS_PER_STEP * (N_CORR + 2 * 128 + 120)},
+                    "d2h_bytes_per_step": PAIRS_PER_STEP * 600,
+                    "api": "lr_ransac_rigid_batch (engine.ransac_rigid_batch): the step's pairs in pinned HOST memory in, "
+                           "poses + refits + statistics in host memory out (one 600-byte control block per pair, written "
+                           "by the last kernel); host->device copies by the copy engine inside the timed region, pair "
+                           "i + 1 under the kernels of pair i; one synchronisation per step.  The reference's loop reads "
+                           "only the pose of each pair (GC_RANSAC.py:46-55: the inlier mask is dropped)"},
+            "e2e_per_pair_call": {"value": pairs_total / (ms_e2e_call * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e_call,
+                                  "h2d_bytes_per_step": PAIRS_PER_STEP * 2 * N_CORR * 12,
+                                  "d2h_bytes_per_step": PAIRS_PER_STEP * (N_CORR + 2 * 128 + 120),
+                                  "api": "findRigidTransform() once per pair (the signature of pygcransac.findRigidTransform, "
+                                         "GC_RANSAC.py:46-49): pinned host arrays in, pose + inlier mask out, one "
+                                         "synchronisation per pair -- rounds 1 and 2 reported this one as e2e"},
             "gpu_launches": launches_per_pair * PAIRS_PER_STEP * args.steps}
 
     # the same call with what the reference interface really hands over (GC_RANSAC.py:10-11): pageable numpy arrays
@@ -360,6 +379,7 @@ def run_ours(args):
                                               "(round 1: 143x on a 16-core box, 82x on a 32-core box)"}
             line["reference_faithful"] = bench_faithful_regime(engine, torch, resident, pairs[0])
             line["fr_e2e"] = bench_fr(torch)
+            line["f4_consumers"] = bench_f4(engine, torch, pairs[0])
             line["reference_libraries"] = probe_reference_libraries(pairs[0])
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -493,6 +513,62 @@ def bench_faithful_regime(engine, torch, resident, pair0):
     fixed["gpu_over_faster_cpu_variant"] = min(fixed["cpu_lean"]["ms_per_pair"], fixed["cpu_faithful"]["ms_per_pair"]) / \
         fixed["gpu_ms_per_pair"]
     out["open3d_m4_replace_fixed_budget"] = fixed
+    return out
+
+
+def bench_f4(engine, torch, pair0):
+    """SURVEY 8(f4), the two consumers right after the path: the ICP refinement of Experiments/test.py:183-188 on a
+    25k-point pair (device-resident: hashed-grid nearest neighbour, one kernel per iteration) and PointDSC's seed scoring
+    (Experiments/models/PointDSC.py:319-336) on the cfg-3 pair with 3 000 seed transforms (ratio 0.1 of 30 000), each
+    beside the oracle on the host cores."""
+    import numpy as np
+    from lidarregistration_b200 import synthetic
+    from lidarregistration_b200.algorithms import registration_icp, registration_icp_bruteforce
+    from oracle import lr_oracle as O
+    out = {}
+    p = synthetic.make_pair(25000, seed=51 + 5000, overlap=0.6)
+    ang = np.deg2rad(1.0)
+    d = np.eye(4)
+    d[:2, :2] = [[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]
+    d[:3, 3] = [0.2, -0.15, 0.05]
+    T0 = d @ p["T_gt"]
+    a, b = engine.to_dev_f32(p["xyz0"]), engine.to_dev_f32(p["xyz1"])
+
+    def wall(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3, r
+
+    ms_grid, r = wall(lambda: registration_icp(a, b, 0.6, T0), 20)
+    ms_bf, rb = wall(lambda: registration_icp_bruteforce(a, b, 0.6, T0), 2)
+    t0 = time.perf_counter()
+    To, fo, ro, ito = O.icp(p["xyz0"], p["xyz1"], 0.6, T0, max_iteration=2)
+    cpu_eval_ms = (time.perf_counter() - t0) / 3 * 1e3
+    out["icp"] = {"workload": "registration_icp(src, tgt, 0.6, T_init): 25k-point pair, T_init = T_gt perturbed by 1 deg / 0.25 m",
+                  "ms": ms_grid, "iterations": r.iterations, "fitness": r.fitness, "inlier_rmse": r.inlier_rmse,
+                  "ms_per_iteration": ms_grid / (r.iterations + 1),
+                  "bruteforce_sweep_ms": ms_bf, "bruteforce_iterations": rb.iterations,
+                  "cpu_oracle_ms_per_iteration": cpu_eval_ms, "cpu_cores": O.num_threads(),
+                  "cpu_note": "oracle/lr_oracle.c brute-force radius search + Kabsch, 3 evaluations timed"}
+    src, tgt = pair0["src"], pair0["tgt"]
+    rng = np.random.default_rng(7)
+    S = 3000
+    models = np.tile(pair0["T_gt"], (S, 1, 1))
+    models[:, :3, 3] += rng.normal(0, 0.5, (S, 3)) * (rng.random(S) < 0.7)[:, None]
+    ds, dt = engine.to_dev_f32(src), engine.to_dev_f32(tgt)
+    dm = torch.from_numpy(models).to(ds.device)
+    ms_seed, res = wall(lambda: engine.seeds_score(ds, dt, dm, THRESH), 20)
+    t0 = time.perf_counter()
+    counts, best = O.seeds_score(src, tgt, models, THRESH)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    assert res["best"] == best and int(res["counts"][best]) == int(counts[best])
+    out["seed_scoring"] = {"workload": "3 000 seed transforms x 30 000 correspondences (cfg-3 pair), inlier threshold 0.6 m",
+                           "ms": ms_seed, "best": res["best"], "best_count": res["best_count"],
+                           "cpu_oracle_ms": cpu_ms, "cpu_cores": O.num_threads(), "identical_to_oracle": True}
     return out
 
 

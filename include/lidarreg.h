@@ -166,8 +166,10 @@ int lr_ransac_rigid(const float *src, const float *tgt, int64_t n, const LrRansa
 int lr_ransac_set_mode(int mode);
 
 /* The same for `count` independent pairs (the reference's per-pair loop over a registration set,
- * Experiments/test.py:108-167, sharded by rank as in data_loaders.py:111-116): src[i] / tgt[i] are device
- * pointers to [n[i],3] fp32 correspondences.  Two pairs are in flight at a time on two internal streams with
+ * Experiments/test.py:108-167, sharded by rank as in data_loaders.py:111-116): src[i] / tgt[i] point to
+ * [n[i],3] fp32 correspondences in device memory OR in host memory (pinned for full PCIe rate; what the
+ * reference's loop holds, GC_RANSAC.py:10-11) -- host arrays are brought in by the copy engine on the pair's
+ * stream, under the kernels of the pair before it.  Two pairs are in flight at a time on two internal streams with
  * separate scratch, so one pair's single-block tail kernels run under the next pair's chip-filling ones and
  * there is no host round trip between pairs.  T_out[16*count] [host], T_refit[16*count] [host, nullable],
  * stats[count] [host, nullable]; results are those of `count` lr_ransac_rigid calls.  The work is ordered

@@ -97,6 +97,7 @@ struct Ws {
     int4 *events;     // records of the residuals inside the tensor sweep's error band, one list per epilogue warp and CTA
     unsigned long long *blockbest;  // k_resolve_end: per-block (key, slot)
     float *packmax;   // k_pack: per-block maxima (|p|_1, |p - c|_2, |q - c'|_inf), reduced by its last block
+    float *stage;     // lr_ransac_rigid_batch: device copy of a pair that was handed over in HOST memory (2 x 3 n floats)
     // LR_SCORE_MSAC runs only (null otherwise)
     unsigned long long *q64;  // per slot: quantised MSAC score
     int32_t *lo_L;            // inlier index list of the current LO round, ascending
@@ -1550,7 +1551,8 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
                    lr::padded(sizeof(double) * 16) + lr::padded(sizeof(uint32_t) * (prosac ? n : 1)) +
                    lr::padded((size_t)((slots + tcs::TM - 1) / tcs::TM) * tcs::A_BLOCK_BYTES) +
                    lr::padded((size_t)ws.n_pad * 64) + lr::padded(sizeof(float) * slots) +
-                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals) + lr::padded(sizeof(int4) * (size_t)kTcEventCap * tc_regions()) + lr::padded(sizeof(float) * 3 * (size_t)(ws.n_pad / 256 + 1)) + lr::padded(sizeof(unsigned long long) * 2 * kEndBlocksMax);
+                   lr::padded(sizeof(double) * kFinBlocksMax * kFinVals) + lr::padded(sizeof(int4) * (size_t)kTcEventCap * tc_regions()) + lr::padded(sizeof(float) * 3 * (size_t)(ws.n_pad / 256 + 1)) + lr::padded(sizeof(unsigned long long) * 2 * kEndBlocksMax) +
+                   lr::padded(sizeof(float) * 6 * (size_t)(n > 0 ? n : 1));
     if (gc)
         bytes += lr::padded(sizeof(unsigned long long) * slots) + lr::padded(sizeof(int32_t) * (n > 0 ? n : 1)) +
                  lr::padded(sizeof(double) * 12 * kGcMaxTrials) + lr::padded(sizeof(unsigned long long) * kGcMaxTrials) +
@@ -1588,6 +1590,7 @@ int ws_setup(int64_t n, int64_t round, int64_t nrounds, Ws &ws, bool prosac = fa
     ws.events = cv.take<int4>((size_t)kTcEventCap * tc_regions());
     ws.packmax = cv.take<float>(3 * (size_t)(ws.n_pad / 256 + 1));
     ws.blockbest = cv.take<unsigned long long>(2 * (size_t)kEndBlocksMax);
+    ws.stage = cv.take<float>(6 * (size_t)(n > 0 ? n : 1));
     ws.q64 = gc ? cv.take<unsigned long long>(slots) : nullptr;
     ws.lo_L = gc ? cv.take<int32_t>(n > 0 ? n : 1) : nullptr;
     ws.tr_T = gc ? cv.take<double>(12 * kGcMaxTrials) : nullptr;
@@ -2245,13 +2248,47 @@ LR_EXPORT int lr_ransac_rigid_batch(const float *const *src, const float *const 
         for (int l = 0; l < 2; ++l) cudaStreamSynchronize(ctx->lane[l]);
         return code;
     };
+    const bool use_conf_b = p.confidence < 1.0 && p.max_iters > 0;
+    const int64_t R_b = use_conf_b ? (int64_t)p.round_size : batch_len(p.max_iters);
     for (int i = 0; i < count; ++i) {
         if (n[i] < p.sample_size) continue;  // identity, filled in below
         const int l = i & 1;
+        const int slot = l ? lr::SLOT_RANSAC_B : lr::SLOT_RANSAC;
+        const float *s_in = src[i], *t_in = tgt[i];
+        // A pair handed over in HOST memory (pinned or pageable) is brought in by the copy engine on its lane, so the
+        // transfer of pair i + 1 runs under the kernels of pair i on the other lane (k_pack reading pinned memory in place,
+        // as the single-pair entry does, would hold SMs for the whole PCIe round trip).
+        cudaPointerAttributes at_s, at_t;
+        const bool host_s = cudaPointerGetAttributes(&at_s, s_in) != cudaSuccess || at_s.type == cudaMemoryTypeHost ||
+                            at_s.type == cudaMemoryTypeUnregistered;
+        const bool host_t = cudaPointerGetAttributes(&at_t, t_in) != cudaSuccess || at_t.type == cudaMemoryTypeHost ||
+                            at_t.type == cudaMemoryTypeUnregistered;
+        (void)cudaGetLastError();  // an unregistered pointer makes older runtimes report an error: it only means "host"
+        if (host_s || host_t) {
+            Ws tmp;
+            rc = ws_setup(n[i], R_b, (p.max_iters + R_b - 1) / R_b, tmp, p.sampler == LR_SAMPLER_PROSAC, slot,
+                          p.scoring == LR_SCORE_MSAC);
+            if (rc) return bail(rc);
+            const size_t bytes = sizeof(float) * 3 * (size_t)n[i];
+            if (host_s) {
+                if (cudaMemcpyAsync(tmp.stage, s_in, bytes, cudaMemcpyHostToDevice, ctx->lane[l]) != cudaSuccess) {
+                    lr::set_error("lr_ransac_rigid_batch: host -> device copy of a source array failed");
+                    return bail(LR_ERR_CUDA);
+                }
+                s_in = tmp.stage;
+            }
+            if (host_t) {
+                if (cudaMemcpyAsync(tmp.stage + 3 * (size_t)n[i], t_in, bytes, cudaMemcpyHostToDevice, ctx->lane[l]) != cudaSuccess) {
+                    lr::set_error("lr_ransac_rigid_batch: host -> device copy of a target array failed");
+                    return bail(LR_ERR_CUDA);
+                }
+                t_in = tmp.stage + 3 * (size_t)n[i];
+            }
+        }
         Ws ws;
-        rc = enqueue_run(src[i], tgt[i], n[i], p, l ? lr::SLOT_RANSAC_B : lr::SLOT_RANSAC, ws, ctx->lane[l]);
+        rc = enqueue_run(s_in, t_in, n[i], p, slot, ws, ctx->lane[l]);
         if (rc) return bail(rc);
-        rc = finish_launch(src[i], tgt[i], n[i], p, ws, p.scoring == LR_SCORE_MSAC ? FIN_GC : FIN_MODEL_READY, 0, want_refit,
+        rc = finish_launch(s_in, t_in, n[i], p, ws, p.scoring == LR_SCORE_MSAC ? FIN_GC : FIN_MODEL_READY, 0, want_refit,
                            nullptr, ctx->lane[l], true, &ctx->host[i]);
         if (rc) return bail(rc);
     }

@@ -155,6 +155,17 @@ def _dev_or_pinned_f32(x):
     return to_dev_f32(x)
 
 
+def _dev_or_host_f32(x):
+    """lr_ransac_rigid_batch takes HOST arrays as they are (contiguous fp32; pinned ones move at full PCIe rate): the
+    library copies them in with the copy engine on the pair's lane, under the other lane's kernels."""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if isinstance(x, torch.Tensor) and not x.is_cuda and x.numel() > 0:
+        _lib.require_cuda()
+        return x.detach().to(torch.float32).contiguous()
+    return to_dev_f32(x)
+
+
 def ransac_rigid(src, tgt, params, want_mask=False, mask_on_host=False):
     """lr_ransac_rigid -> dict(T, T_refit, mask | None, + LrRansacStats fields).
 
@@ -234,9 +245,10 @@ def tc_probe(src, tgt, models, threshold=0.6, want_d=True, want_counts=True):
 
 
 def ransac_rigid_batch(pairs, params):
-    """lr_ransac_rigid_batch: `pairs` = [(src, tgt), ...] of CUDA fp32 [n,3] tensors -> list of dicts as
-    ransac_rigid returns (no masks).  Two pairs in flight at a time, one host synchronisation for the batch."""
-    pairs = [(to_dev_f32(a), to_dev_f32(b)) for a, b in pairs]
+    """lr_ransac_rigid_batch: `pairs` = [(src, tgt), ...] of fp32 [n,3] CUDA tensors, or HOST tensors / numpy arrays
+    (copied in by the library, pair i + 1 under the kernels of pair i) -> list of dicts as ransac_rigid returns (no
+    masks).  Two pairs in flight at a time, one host synchronisation for the batch."""
+    pairs = [(_dev_or_host_f32(a), _dev_or_host_f32(b)) for a, b in pairs]
     k = len(pairs)
     if k == 0:
         return []

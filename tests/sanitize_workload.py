@@ -54,4 +54,20 @@ engine.ransac_set_mode(1)
 r1 = engine.ransac_rigid(*pairs[0], pb)
 engine.ransac_set_mode(0)
 assert r1["best_id"] == rs["best_id"] and r1["best_count"] == rs["best_count"]
+# f4: hashed-grid ICP (small clouds: the sanitizer slows everything ~50x) and seed scoring on the tensor sweep
+from lidarregistration_b200.algorithms import registration_icp
+pp = synthetic.make_pair(1500, seed=9, overlap=0.8)
+T0 = pp["T_gt"].copy()
+T0[:3, 3] += [0.1, -0.1, 0.05]
+ri = registration_icp(pp["xyz0"], pp["xyz1"], 0.6, T0, max_iteration=3)
+oi = O.icp(pp["xyz0"], pp["xyz1"], 0.6, T0, max_iteration=3)
+assert ri.iterations == oi[3] and ri.fitness == oi[1]
+models = np.tile(d["T_gt"], (200, 1, 1))
+models[:, :3, 3] += rng.normal(0, 0.3, (200, 3))
+rsd = engine.seeds_score(d["src"], d["tgt"], models, 0.6)
+ocn, obs = O.seeds_score(d["src"], d["tgt"], models, 0.6)
+assert np.array_equal(rsd["counts"].cpu().numpy(), ocn) and rsd["best"] == obs
+Aw = rng.normal(size=(50, 20, 3)).astype(np.float32)
+Tw = engine.kabsch_weighted_batch(Aw, Aw + 1.0, None).cpu().numpy()
+assert np.array_equal(Tw[7], O.kabsch_weighted(Aw[7], Aw[7] + 1.0, None))
 print("sanitize workload ok")

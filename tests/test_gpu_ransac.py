@@ -190,6 +190,16 @@ def test_batch_equals_single_calls():
             assert np.array_equal(s1["T"], b1["T"])
             assert np.array_equal(s1["T_refit"], b1["T_refit"])  # fixed-order reduction in k_finish: bit-reproducible
     assert engine.ransac_rigid_batch([], params) == []
+    # the same pairs handed over in HOST memory (pinned tensors, pageable numpy arrays, and a mix with device tensors):
+    # the library stages them with the copy engine on the pair's lane; results identical
+    pinned = [(torch.from_numpy(d["src"]).pin_memory(), torch.from_numpy(d["tgt"]).pin_memory()) for d in sets]
+    pageable = [(d["src"], d["tgt"]) for d in sets]
+    mixed = [(pinned[k][0], pairs[k][1]) if k % 2 else (pairs[k][0], pageable[k][1]) for k in range(len(sets))]
+    for host_pairs in (pinned, pageable, mixed):
+        hb = engine.ransac_rigid_batch(host_pairs, params)
+        for b1, h1 in zip(batch, hb):
+            assert all(b1[key] == h1[key] for key in ("best_id", "best_count", "iters_run", "n_scored", "refit_count"))
+            assert np.array_equal(b1["T"], h1["T"]) and np.array_equal(b1["T_refit"], h1["T_refit"])
 
 
 def test_find_rigid_transform_mask_in_pinned_host_memory():
