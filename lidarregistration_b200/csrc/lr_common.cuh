@@ -56,8 +56,33 @@ struct Lock {
 
 // optional device-time accounting (lr_prof.cu); tokens are -1 when disabled
 enum ProfKind { PROF_SCORE = 0, PROF_GEN = 1, PROF_NN = 2, PROF_RECOUNT = 3, PROF_PACK = 4, PROF_END = 5, PROF_FIN = 6 };
+bool prof_on();
 int prof_begin(int kind, cudaStream_t st);
 void prof_end(int token, cudaStream_t st);
+
+// Programmatic dependent launch for the kernel chain of a run (pack -> gen -> Kabsch -> sweep -> round end -> finish):
+// the next kernel's CTAs are scheduled while the previous kernel drains and block in pdl_wait() until it has completed
+// and its writes are visible, so the ~2-3 us of launch latency per boundary leave the critical path of a single-pair call
+// (and of every rank of a hypothesis-sharded one).  EVERY kernel launched through launch_pdl() starts with pdl_wait();
+// launched the ordinary way the two instructions are no-ops.  lr_debug_pdl(0) / profiling runs launch the ordinary way.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (g_pdl && !prof_on()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // carve 256-byte aligned pieces out of one arena block
 struct Carver {

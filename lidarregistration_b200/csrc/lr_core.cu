@@ -6,6 +6,7 @@
 
 namespace lr {
 
+int g_pdl = 1;
 static thread_local char g_err[512] = "";
 static std::recursive_mutex g_mu;
 static const int kMaxDev = 64;
@@ -111,6 +112,13 @@ LR_EXPORT int lr_device_info(int *sms, int *major, int *minor)
     if (sms) *sms = a;
     if (major) *major = b;
     if (minor) *minor = c;
+    return LR_OK;
+}
+
+// A/B switch of the programmatic dependent launch (lr_common.cuh): 0 = ordinary stream-ordered launches
+LR_EXPORT int lr_debug_pdl(int on)
+{
+    lr::g_pdl = on ? 1 : 0;
     return LR_OK;
 }
 

@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(256)
 k_icp_eval(const float *__restrict__ src, int64_t n, const float *__restrict__ tgt, Grid g, double r2, IcpCtl *c,
            double *__restrict__ partial, int e, double rel_fitness, double rel_rmse)
 {
+    lr::pdl_wait();  // (launched with programmatic stream serialisation: iteration e + 1 is resident when e finishes)
+    lr::pdl_launch();
     if (c->done) return;
     __shared__ int s_last;
     __shared__ double s_part[8][kFinVals];

@@ -105,7 +105,8 @@ LR_EXPORT int lr_icp_refine(const float *src, int64_t n, const float *tgt, int64
     if (blocks > cap) blocks = cap;
     // evaluation 0 scores T_init, evaluation e >= 1 is Open3D's iteration e; a converged run turns the rest into no-ops
     for (int e = 0; e <= max_iteration; ++e)
-        k_icp_eval<<<blocks, 256, 0, st>>>(src, n, tgt, w.g, max_dist * max_dist, w.ctl, w.partial, e, rel_fitness, rel_rmse);
+        LR_CUDA_TRY(lr::launch_pdl(k_icp_eval, dim3(blocks), dim3(256), 0, st, src, n, tgt, w.g, max_dist * max_dist, w.ctl,
+                                   w.partial, e, rel_fitness, rel_rmse));
     LR_CUDA_TRY(cudaGetLastError());
     IcpCtl h;
     LR_CUDA_TRY(cudaMemcpyAsync(&h, w.ctl, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -463,6 +463,8 @@ k_pack(const float *__restrict__ src, const float *__restrict__ tgt, int64_t n, 
        float4 *__restrict__ P12, float4 *__restrict__ P8, uint4 *__restrict__ Bimg, Ctl *ctl, float *__restrict__ packmax,
        int want12)
 {
+    lr::pdl_wait();  // (the previous run's k_finish may still be copying this control block out)
+    lr::pdl_launch();
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl_reset_fields(ctl);
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     float p1 = 0.f, pt2 = 0.f, qt = 0.f;
@@ -589,6 +591,8 @@ k_gen(const float4 *__restrict__ P8, int64_t n, uint64_t seed, int sampler,
       int use_elc, double elc_ratio, int64_t id_lo, int64_t id_hi, const int32_t *__restrict__ fed,
       const uint32_t *__restrict__ growth, Ctl *ctl, uint32_t *__restrict__ slot_id, int32_t *__restrict__ samp)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     if (ctl->done) return;
     int64_t id = id_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     bool ok = id < id_hi;
@@ -640,6 +644,8 @@ k_kabsch(const float4 *__restrict__ P8, double thr2, Ctl *ctl,
          const int32_t *__restrict__ samp, float4 *__restrict__ m32, double *__restrict__ m64,
          int *__restrict__ cnt, uint4 *__restrict__ Aimg, float *__restrict__ band)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
     double cen[3], cenq[3];
@@ -1074,6 +1080,8 @@ __global__ void __launch_bounds__(256)
 k_resolve_end(Ctl *ctl, const uint32_t *__restrict__ slot_id, const int *__restrict__ cnt, const double *__restrict__ m64,
               unsigned long long *__restrict__ blockbest, EndArgs a)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
     unsigned long long key = 0ULL;
@@ -1343,7 +1351,8 @@ k_finish(const float *__restrict__ a, const float *__restrict__ b, const int64_t
          const int64_t *__restrict__ ib, int64_t n, double thr2, Ctl *ctl, uint8_t *__restrict__ mask,
          double *__restrict__ partial, int want_refit, Ctl *host_out)
 {
-    __shared__ double sh[8];
+    lr::pdl_wait();
+    lr::pdl_launch();
     __shared__ int s_last;
     double T[12];
 #pragma unroll
@@ -1682,7 +1691,8 @@ int launch_pack(const float *src, const float *tgt, int64_t n, const Ws &ws, cud
 {
     const int tok = lr::prof_begin(lr::PROF_PACK, st);
     int blocks = (int)((ws.n_pad + 255) / 256);
-    k_pack<<<blocks, 256, 0, st>>>(src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.Bimg, ws.ctl, ws.packmax, want12 ? 1 : 0);
+    LR_CUDA_TRY(lr::launch_pdl(k_pack, dim3(blocks), dim3(256), 0, st, src, tgt, n, ws.n_pad, ws.P12, ws.P8, ws.Bimg, ws.ctl,
+                               ws.packmax, want12 ? 1 : 0));
     lr::prof_end(tok, st);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
@@ -1708,14 +1718,19 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
         const bool use_tc = p.scoring == LR_SCORE_COUNT && g_score_mode == 0;
         uint4 *aimg = use_tc ? ws.Aimg : nullptr;
         int tok = lr::prof_begin(lr::PROF_GEN, st);
+        const float4 *P8c = ws.P8;
+        const int32_t *sampc = ws.samp;
+        const uint32_t *growthc = ws.growth;
         if (p.sample_size == 3) {
-            k_gen<3><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
-                                                      ws.growth, ws.ctl, ws.slot_id, ws.samp);
-            k_kabsch<3><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt, aimg, ws.band);
+            LR_CUDA_TRY(lr::launch_pdl(k_gen<3>, dim3(gblocks), dim3(kGenThreads), 0, st, P8c, n, (uint64_t)p.seed, (int)p.sampler,
+                                       (int)p.use_elc, p.elc_ratio, lo, hi, fed, growthc, ws.ctl, ws.slot_id, ws.samp));
+            LR_CUDA_TRY(lr::launch_pdl(k_kabsch<3>, dim3(kblocks), dim3(kGenThreads), 0, st, P8c, thr2, ws.ctl, sampc, ws.m32,
+                                       ws.m64, ws.cnt, aimg, ws.band));
         } else {
-            k_gen<4><<<gblocks, kGenThreads, 0, st>>>(ws.P8, n, p.seed, p.sampler, p.use_elc, p.elc_ratio, lo, hi, fed,
-                                                      ws.growth, ws.ctl, ws.slot_id, ws.samp);
-            k_kabsch<4><<<kblocks, kGenThreads, 0, st>>>(ws.P8, thr2, ws.ctl, ws.samp, ws.m32, ws.m64, ws.cnt, aimg, ws.band);
+            LR_CUDA_TRY(lr::launch_pdl(k_gen<4>, dim3(gblocks), dim3(kGenThreads), 0, st, P8c, n, (uint64_t)p.seed, (int)p.sampler,
+                                       (int)p.use_elc, p.elc_ratio, lo, hi, fed, growthc, ws.ctl, ws.slot_id, ws.samp));
+            LR_CUDA_TRY(lr::launch_pdl(k_kabsch<4>, dim3(kblocks), dim3(kGenThreads), 0, st, P8c, thr2, ws.ctl, sampc, ws.m32,
+                                       ws.m64, ws.cnt, aimg, ws.band));
         }
         lr::prof_end(tok, st);
         if (p.scoring == LR_SCORE_MSAC) return gc_launch_score(src, tgt, n, p, ws, lo, len, scores_out, counts_out, st);
@@ -1723,9 +1738,10 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
         if (use_tc) {
             // persistent CTAs, one per SM (TMEM: 4 x 96 accumulator columns; 57 KB of operand staging)
             LR_CUDA_TRY(tc_smem_attr());
-            tcs::k_score_tc<false><<<sms, tcs::NTHREADS, tcs::kSmemBytes, st>>>(ws.Aimg, ws.Bimg, ws.P8, n, ws.n_pad, ws.ctl,
-                                                                                 ws.m64, ws.band, ws.cnt, thr2, nullptr,
-                                                                                 ws.events, kTcEventCap);
+            LR_CUDA_TRY(lr::launch_pdl(tcs::k_score_tc<false>, dim3(sms), dim3(tcs::NTHREADS), tcs::kSmemBytes, st,
+                                       (const uint4 *)ws.Aimg, (const uint4 *)ws.Bimg, P8c, n, ws.n_pad, ws.ctl,
+                                       (const double *)ws.m64, (const float *)ws.band, ws.cnt, thr2, (float *)nullptr, ws.events,
+                                       kTcEventCap));
         } else if (g_score_mode == 2) {
             // fp32 sweep: 16 resident one-warp CTAs per SM (128 registers per thread fill the register file; 12 KB of
             // staging each): no CTA-level barrier couples warps whose early-out rates differ
@@ -1740,8 +1756,9 @@ int launch_round(const float *src, const float *tgt, int64_t n, const LrRansacPa
     if (rblocks < 1) rblocks = 1;
     if (end) {
         const int tok = lr::prof_begin(lr::PROF_END, st);
-        k_resolve_end<<<rblocks < kEndBlocksMax ? rblocks : kEndBlocksMax, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, ws.m64,
-                                                                                         ws.blockbest, *end);
+        LR_CUDA_TRY(lr::launch_pdl(k_resolve_end, dim3(rblocks < kEndBlocksMax ? rblocks : kEndBlocksMax), dim3(256), 0, st,
+                                   ws.ctl, (const uint32_t *)ws.slot_id, (const int *)ws.cnt, (const double *)ws.m64,
+                                   ws.blockbest, *end));
         lr::prof_end(tok, st);
     } else {
         k_resolve<<<rblocks, 256, 0, st>>>(ws.ctl, ws.slot_id, ws.cnt, counts_out, lo);
@@ -1795,8 +1812,8 @@ int finish_launch(const float *src, const float *tgt, int64_t n, const LrRansacP
             k_model_from_key<4><<<1, 32, 0, st>>>(src, tgt, n, p.seed, p.sampler, ws.growth, key, 0, ws.ctl);
     }
     const int tok = lr::prof_begin(lr::PROF_FIN, st);
-    k_finish<<<finish_blocks(n), 256, 0, st>>>(fa, fb, nullptr, nullptr, n, thr2, ws.ctl, mask, ws.partial, want_refit ? 1 : 0,
-                                               host_out);
+    LR_CUDA_TRY(lr::launch_pdl(k_finish, dim3(finish_blocks(n)), dim3(256), 0, st, fa, fb, (const int64_t *)nullptr,
+                               (const int64_t *)nullptr, n, thr2, ws.ctl, mask, ws.partial, want_refit ? 1 : 0, host_out));
     lr::prof_end(tok, st);
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;

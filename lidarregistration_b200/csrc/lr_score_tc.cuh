@@ -402,6 +402,8 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
            int64_t n_pad, Ctl *ctl, const double *__restrict__ m64, const float *__restrict__ band, int *__restrict__ cnt,
            double thr2, float *__restrict__ dump, int4 *__restrict__ events, unsigned ev_cap)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     if (ctl->done) return;
     const int nsurv = ctl->n_surv;
     if (nsurv <= 0) return;
