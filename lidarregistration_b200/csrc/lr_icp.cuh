@@ -119,6 +119,48 @@ __device__ __forceinline__ long long grid_nearest(const Grid &g, const double (&
     return bj;
 }
 
+// the same search by LANES consecutive lanes of a warp (the 27 cells dealt round-robin, then a lexicographic (d^2, index)
+// minimum across the lanes): the chain of dependent key -> start / count -> point loads is what bounds the search, and this
+// cuts it LANES-fold.  Every lane of the group returns the result; the minimum does not depend on the order it is taken in.
+template <int LANES>
+__device__ __forceinline__ long long grid_nearest_coop(const Grid &g, const double (&mv)[3], double r2, double &best_d2)
+{
+    const int sub = (threadIdx.x & 31) % LANES;
+    const int cx = grid_coord(mv[0], g.inv_cell), cy = grid_coord(mv[1], g.inv_cell), cz = grid_coord(mv[2], g.inv_cell);
+    double best = r2;
+    long long bj = -1;
+    for (int c = sub; c < 27; c += LANES) {
+        const int dz = c / 9 - 1, dy = (c / 3) % 3 - 1, dx = c % 3 - 1;
+        const unsigned long long key = grid_key(cx + dx, cy + dy, cz + dz);
+        unsigned int h = (unsigned int)mix64(key) & g.mask;
+        unsigned long long k;
+        while ((k = __ldg(&g.keys[h])) != kGridEmpty && k != key) h = (h + 1u) & g.mask;
+        if (k != key) continue;
+        const unsigned int a = __ldg(&g.start[h]), b = a + __ldg(&g.cnt[h]);
+        for (unsigned int e = a; e < b; ++e) {
+            const float4 q = __ldg(&g.pts[e]);
+            const double d0 = mv[0] - (double)q.x, d1 = mv[1] - (double)q.y, d2 = mv[2] - (double)q.z;
+            const double d = (d0 * d0 + d1 * d1) + d2 * d2;
+            const long long j = (long long)__float_as_uint(q.w);
+            if (d < best || (d == best && bj >= 0 && j < bj)) {
+                best = d;
+                bj = j;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (oj >= 0 && (od < best || (od == best && (bj < 0 || oj < bj)))) {
+            best = od;
+            bj = oj;
+        }
+    }
+    best_d2 = best;
+    return bj;
+}
+
 __device__ __forceinline__ void icp_move(const double *T, const float *__restrict__ p, double (&mv)[3])
 {
     const double px = (double)p[0], py = (double)p[1], pz = (double)p[2];
@@ -144,6 +186,7 @@ k_nn3d_query(const float *__restrict__ src, int64_t n, Grid g, const double *__r
 }
 
 // ---------------------------------------------------------------- one ICP iteration per launch
+constexpr int kIcpLanes = 8;  // lanes that share the 27-cell search of one source point
 struct IcpCtl {
     double T[12];      // transform the next launch evaluates
     double Tres[12];   // transform of the last evaluation (the result)
@@ -188,11 +231,17 @@ k_icp_eval(const float *__restrict__ src, int64_t n, const float *__restrict__ t
     double v[kFinVals];
 #pragma unroll
     for (int k = 0; k < kFinVals; ++k) v[k] = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double mv[3], bd;
-        icp_move(T, src + 3 * i, mv);
-        const long long j = grid_nearest(g, mv, r2, bd);
-        if (j < 0) continue;
+    // kIcpLanes lanes per source point; the group's first lane carries the point's terms of the sums.  (The trip count is
+    // warp-uniform: the shuffles inside the search need every lane.)
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, gstride = (int64_t)gridDim.x * blockDim.x;
+    const bool lead = (threadIdx.x % kIcpLanes) == 0;
+    const int64_t n_ceil = (n + (32 / kIcpLanes) - 1) / (32 / kIcpLanes) * (32 / kIcpLanes);
+    for (int64_t i = gtid / kIcpLanes; i < n_ceil; i += gstride / kIcpLanes) {
+        double mv[3] = {0, 0, 0}, bd = 0.0;
+        long long j = -1;
+        if (i < n) icp_move(T, src + 3 * i, mv);
+        j = grid_nearest_coop<kIcpLanes>(g, mv, i < n ? r2 : -1.0, bd);
+        if (j < 0 || !lead || i >= n) continue;
         double p[3], q[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {

@@ -100,7 +100,7 @@ LR_EXPORT int lr_icp_refine(const float *src, int64_t n, const float *tgt, int64
     if (rc) return rc;
     LR_CUDA_TRY(cudaMemcpyAsync(w.T12, T12, sizeof(T12), cudaMemcpyHostToDevice, st));
     k_icp_begin<<<1, 32, 0, st>>>(w.ctl, w.T12);
-    int blocks = (int)((n + 255) / 256);
+    int blocks = (int)((n * kIcpLanes + 255) / 256);
     const int cap = lr::sm_count() * 4 < kFinBlocksMax ? lr::sm_count() * 4 : kFinBlocksMax;
     if (blocks > cap) blocks = cap;
     // evaluation 0 scores T_init, evaluation e >= 1 is Open3D's iteration e; a converged run turns the rest into no-ops

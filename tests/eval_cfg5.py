@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from lidarregistration_b200 import metrics, parallel, synthetic  # noqa: E402
-from lidarregistration_b200.algorithms import FR  # noqa: E402
+from lidarregistration_b200.algorithms import FR, registration_icp  # noqa: E402
 from eval_pairs import oracle_fr  # noqa: E402
 
 
@@ -61,8 +61,15 @@ def main():
         torch.cuda.synchronize()
         gpu_wall += time.time() - t0
         T = out[0]
+        # the step right after FR() in the reference's loop (Experiments/test.py:183-188): ICP at 0.6 m from the coarse pose
+        t1 = time.time()
+        icp = registration_icp(out[2], out[3], 0.6, T)
+        icp_s = time.time() - t1
+        Ti = icp.transformation
         rows.append([p, metrics.rotation_error_deg(T, d["T_gt"]), metrics.translation_error_cm(T, d["T_gt"]), out[1],
-                     out[4], out[6]] + list(T[:3, :].reshape(-1)))
+                     out[4], out[6]] + list(T[:3, :].reshape(-1)) +
+                    [metrics.rotation_error_deg(Ti, d["T_gt"]), metrics.translation_error_cm(Ti, d["T_gt"]), icp_s,
+                     float(icp.iterations)])
     gpu_phase = time.time() - t_start
     # the oracle on the subsample (pairs p with p % every == 0), spread over the ranks' host cores
     from oracle import lr_oracle as O
@@ -79,7 +86,7 @@ def main():
         orows.append([p, metrics.rotation_error_deg(To, d["T_gt"]), metrics.translation_error_cm(To, d["T_gt"])] +
                      list(To[:3, :].reshape(-1)))
     cpu_phase = time.time() - t0
-    rows = parallel.gather_rows(np.asarray(rows, dtype=np.float64).reshape(-1, 18))
+    rows = parallel.gather_rows(np.asarray(rows, dtype=np.float64).reshape(-1, 22))
     orows = parallel.gather_rows(np.asarray(orows, dtype=np.float64).reshape(-1, 15))
     tw = torch.tensor([gpu_wall, gpu_phase, cpu_phase], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -102,6 +109,12 @@ def main():
             pairs_per_s_model_time=float(world / rows[:, 3].mean()),
             pairs_per_s_wall_FR_calls=float(a.pairs / float(tw[0])), wall_s_incl_synthetic_data=float(tw[1]),
             mean_filtered_pairs=float(rows[:, 5].mean()),
+            after_icp=dict(recall=float(((rows[:, 18] < 5.0) & (rows[:, 19] < 60.0)).mean()),
+                           RRE_deg=float(rows[(rows[:, 18] < 5.0) & (rows[:, 19] < 60.0), 18].mean()),
+                           RTE_cm=float(rows[(rows[:, 18] < 5.0) & (rows[:, 19] < 60.0), 19].mean()),
+                           icp_time_mean_s=float(rows[:, 20].mean()), icp_time_p99_s=float(np.quantile(rows[:, 20], 0.99)),
+                           icp_iterations_mean=float(rows[:, 21].mean()),
+                           note="registration_icp(pcd0, pcd1, 0.6, T) = lr_icp_refine (Experiments/test.py:183-188)"),
             subsample=dict(n=len(orows),
                            gpu=dict(recall=float(okg.mean()), RRE_deg=float(gs[both, 1].mean()), RTE_cm=float(gs[both, 2].mean())),
                            cpu_oracle=dict(recall=float(oko.mean()), RRE_deg=float(orows[both, 1].mean()),
