@@ -10,4 +10,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 300 python tools/tcs_trace.py 64 1 > gpurun_out/trace_tn64_elc.txt 2>&1; timeout 300 python tools/tcs_trace.py 64 0 > gpurun_out/trace_tn64_noelc.txt 2>&1; grep "^# " gpurun_out/trace_tn64_elc.txt | tail -4
 timeout 600 compute-sanitizer --tool memcheck python tests/sanitize_workload.py > gpurun_out/h_san_mem.log 2>&1; tail -2 gpurun_out/h_san_mem.log
 timeout 600 compute-sanitizer --tool racecheck python tests/sanitize_workload.py > gpurun_out/h_san_race.log 2>&1; tail -2 gpurun_out/h_san_race.log
-for w in 1 8; do timeout 120 python tools/pair_breakdown.py 1 $w > gpurun_out/h_breakdown_w$w.json 2>&1; done; cat gpurun_out/h_breakdown_w8.json
+for w in 1 2 4 8; do timeout 120 python tools/pair_breakdown.py 1 $w > gpurun_out/h_breakdown_w$w.json 2>&1; done; cat gpurun_out/h_breakdown_w8.json; timeout 120 python tools/pdl_ab.py > gpurun_out/h_pdl_ab.json 2>&1
