@@ -52,6 +52,17 @@ constexpr int TM = 128;                 // hypotheses per row block (UMMA M)
 #define LR_TCS_TN 64   // 64: two 192-column TMEM buffers, two MMA warps, every epilogue warp reads 16 columns of every tile
                        // (6.85 ms for 1 M x 30 000 against 7.15 with 32 and 7.9 with 16: fewer, larger MMAs per stage)
 #endif
+// LR_TCS_WIDE (with TN 32): twelve epilogue warps = three groups of four (one per TMEM lane quadrant); a group owns a
+// whole 32-column tile (96 accumulator registers per thread, 128 registers after setmaxnreg), so a TMEM buffer is waited
+// for and handed back by four warps instead of eight or sixteen, the fixed work per barrier round trip covers twice the
+// columns, and the three warps of a sub-partition belong to three different buffers' cycles (nothing re-locks them).
+#ifndef LR_TCS_WIDE
+#define LR_TCS_WIDE 0
+#endif
+#if LR_TCS_WIDE
+#undef LR_TCS_TN
+#define LR_TCS_TN 32
+#endif
 constexpr int TN = LR_TCS_TN;           // correspondences per MMA tile (UMMA N): 16, 32 or 64
 constexpr int BROWS = 128;              // correspondences per shared-memory stage (== kChunk)
 constexpr int TILES_PER_STAGE = BROWS / TN;   // == number of TMEM buffers: sub-tile j of every stage lives in buffer j
@@ -62,14 +73,25 @@ constexpr int A_PART_BYTES = TM / 8 * 256;     // one residual component: 16 gro
 constexpr int A_BLOCK_BYTES = 3 * A_PART_BYTES;  // 12 KB per 128 hypotheses
 constexpr int NBUF = TILES_PER_STAGE;
 constexpr int TMEM_BUF_COLS = 3 * TN;   // the three residual components of a tile (NBUF x 3 x TN = 384 columns in all)
+#if LR_TCS_WIDE
+constexpr int NEPI = 12;                // epilogue warps: 3 tile groups x 4 TMEM lane quadrants, a warp takes all 32 columns
+constexpr int NSLICE = 1;
+constexpr int NGROUP = 3;               // group g takes the tiles t = g (mod 3) of the CTA's tile sequence (4 per stage)
+constexpr int kRegsEpilogue = 112, kRegsOther = 48;  // 12 x 32 x epilogue + 8 x 32 x other < the 640 x 96 registers of the launch (with slack)
+#else
 constexpr int NEPI = 16;                // epilogue warps: 4 TMEM lane quadrants x NGROUP tile groups x NSLICE column slices
 constexpr int NSLICE = TN / 16;         // a warp takes 16 columns of a tile (48 accumulator registers)
 constexpr int NGROUP = 4 / NSLICE;      // group g takes the tiles j = g (mod NGROUP) of every stage: while one group
                                         // computes, another is free to pick the next tile up the moment it is ready
+#endif
 static_assert(TN == 16 || TN == 32 || TN == 64, "tile width");
 constexpr int NMMA = TILES_PER_STAGE;    // MMA-issuing warps: warp WARP_MMA + j owns sub-tile j / TMEM buffer j of every stage
 constexpr int WARP_PRODUCER = NEPI, WARP_MMA = NEPI + 1;
+#if LR_TCS_WIDE
+constexpr int NTHREADS = 32 * ((NEPI + 1 + NMMA + 3) / 4 * 4);  // whole warpgroups (setmaxnreg moves registers between them)
+#else
 constexpr int NTHREADS = 32 * (NEPI + 1 + NMMA);
+#endif
 constexpr uint32_t IDESC = (1u << 4) /*D = f32*/ | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr float kRangeLimit = 15000.f;  // |p~|, |q~| above this: the fp16 pieces could overflow -> fp64 fallback
 constexpr double kAccKappa = 4.0;       // tensor-core accumulation error <= kappa * 2^-24 * sum |terms|
@@ -150,6 +172,37 @@ __device__ __forceinline__ void tmem_ld_wait3(uint32_t (&a)[16], uint32_t (&b)[1
                    "+r"(c[8]), "+r"(c[9]), "+r"(c[10]), "+r"(c[11]), "+r"(c[12]), "+r"(c[13]), "+r"(c[14]), "+r"(c[15])
                  :
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// (tcgen05.wait::ld, then one ordering statement per register array: volatile asm statements keep their order)
+__device__ __forceinline__ void tmem_touch32(uint32_t (&r)[32])
+{
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait3x32(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t (&c)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_touch32(a);
+    tmem_touch32(b);
+    tmem_touch32(c);
 }
 __device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8])
 {
@@ -307,7 +360,10 @@ __device__ long long g_tcs_trace[NEPI + 1 + NMMA][kTraceLen][TILES_PER_STAGE][4]
 #endif
 
 struct __align__(8) Smem {
-    uint64_t a_full[2], a_empty[2], b_full[B_STAGES], b_empty[B_STAGES], t_full[NBUF], t_empty[NBUF];
+    // LR_TCS_WIDE: a group meets TMEM buffer j only every third stage, and a parity wait cannot tell phase s from phase
+    // s - 2 -- so "tile (s, j) is ready" has one barrier per (j, s mod 3), each with one consumer group that sees every
+    // one of its phases
+    uint64_t a_full[2], a_empty[2], b_full[B_STAGES], b_empty[B_STAGES], t_full[NBUF * (LR_TCS_WIDE ? 3 : 1)], t_empty[NBUF];
     uint32_t tmem_base;
 };
 
@@ -448,9 +504,10 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                 mbar_init(&sm->b_full[k], 1);
                 mbar_init(&sm->b_empty[k], NMMA);
             }
+            for (int k = NBUF; k < NBUF * (LR_TCS_WIDE ? 3 : 1); ++k) mbar_init(&sm->t_full[k], 1);
             for (int k = 0; k < NBUF; ++k) {
                 mbar_init(&sm->t_full[k], 1);
-                mbar_init(&sm->t_empty[k], 4 * NSLICE);  // the warps (quadrant x slice) that read this tile
+                mbar_init(&sm->t_empty[k], LR_TCS_WIDE ? 4 : 4 * NSLICE);  // the warps (quadrant x slice) that read a tile
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -465,7 +522,17 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
     tc_fence_after();
     const uint32_t tmem_base = sm->tmem_base;
 
+#if LR_TCS_WIDE
+    // (each role executes its setmaxnreg inside its own branch: the register allocator budgets a region by the instruction
+    // that dominates it)
+#define TCS_REGS_MORE() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpilogue))
+#define TCS_REGS_LESS() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther))
+#else
+#define TCS_REGS_MORE()
+#define TCS_REGS_LESS()
+#endif
     if (warp == WARP_PRODUCER) {
+        TCS_REGS_LESS();
         // ===== producer: bulk copies of the hypothesis block and the correspondence stages =====
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
@@ -488,7 +555,10 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                 pos += sg.c_hi - sg.c_lo;
             }
         }
+    } else if (warp >= WARP_MMA + NMMA) {
+        TCS_REGS_LESS();  // (LR_TCS_WIDE: warps that only complete the last warpgroup)
     } else if (warp >= WARP_MMA) {
+        TCS_REGS_LESS();
         // ===== MMA issuers: warp WARP_MMA + j issues sub-tile j of every stage into TMEM buffer j.  Warp-uniform loops,
         // elect.sync picks the lane; unrolled over the four stages of the B ring, so stage, barrier addresses, parities
         // and descriptors are static.  One issuing warp was the sweep's bottleneck (tools/tcs_trace.py,
@@ -500,7 +570,12 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
         if (rg.pos < rg.end) {
             const uint32_t a_full = smem_u32(&sm->a_full[0]), a_empty = smem_u32(&sm->a_empty[0]);
             const uint32_t b_full = smem_u32(&sm->b_full[0]), b_empty = smem_u32(&sm->b_empty[0]);
+#if LR_TCS_WIDE
+            const uint32_t t_full0 = smem_u32(&sm->t_full[3 * j]), t_empty = smem_u32(&sm->t_empty[j]);
+            uint32_t r3 = 0u;  // stages issued so far, modulo 3
+#else
             const uint32_t t_full = smem_u32(&sm->t_full[j]), t_empty = smem_u32(&sm->t_empty[j]);
+#endif
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB) + j * (TN / 8) * B_GROUP_BYTES;
             const uint32_t d_tmem = tmem_base + j * TMEM_BUF_COLS;
             // B: K-adjacent cores core0 -> core1_a are 128 (1 + a) bytes apart, 8-correspondence groups 512 bytes apart
@@ -529,7 +604,12 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
                     mbar_wait_mma(t_empty, (uint32_t)(s & 1) ^ 1u);
                     TCS_TRACE(st_no, j, 1);
                     tc_fence_after();
+#if LR_TCS_WIDE
+                    tc_issue_tile(d_tmem, ad0, ad1, ad2, x0, x1, x2, t_full0 + r3 * 8u);
+                    r3 = r3 == 2u ? 0u : r3 + 1u;
+#else
                     tc_issue_tile(d_tmem, ad0, ad1, ad2, x0, x1, x2, t_full);
+#endif
                     tc_commit_elect(b_empty + s * 8u);  // the stage's bytes are reusable once the MMAs of all tiles have read them
                     TCS_TRACE(st_no, j, 2);
 #ifdef LR_TCS_TRACE
@@ -557,6 +637,149 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
         }
     } else {
         // ===== epilogue: TMEM -> registers -> counts =====
+        TCS_REGS_MORE();
+#if LR_TCS_WIDE
+        {
+            const int q = warp & 3;    // TMEM lane quadrant this warp may read
+            const int grp = warp >> 2; // this group's tiles: t = grp, grp + 3, ... of the CTA's sequence (4 tiles per stage)
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_full = smem_u32(&sm->t_full[0]), t_empty = smem_u32(&sm->t_empty[0]);
+            const float nthr2 = -(float)thr2;
+            const u64 nthr2p = pk2(__float_as_uint(nthr2), __float_as_uint(nthr2));
+            unsigned long long *n_rechecked = reinterpret_cast<unsigned long long *>(&ctl->n_rechecked);
+            const int region = blockIdx.x * NEPI + warp;
+            int4 *ev_mine = events + (size_t)region * ev_cap;
+            unsigned ev_n = 0, evals_tail = 0;
+            const long long ntiles = (rg.end - rg.pos) * TILES_PER_STAGE;
+            // position of the current tile: stage s of the CTA's range (its parity is the barrier phase: every buffer is
+            // used once per stage), sub-tile j, hypothesis block hb, correspondence stage c
+            long long s = 0;
+            uint32_t sr = 0u, sk = 0u;  // s mod 3 and the parity of s / 3: barrier (j, sr) is in its (s / 3)-th phase
+            int j = grp;  // grp < 4: the first tile of the group lies in stage 0
+            int hb = (int)(rg.pos / nchunks), c = (int)(rg.pos - (long long)hb * nchunks);
+            int slot = hb * TM + q * 32 + lane;
+            bool valid = slot < nsurv;
+            float delta = valid ? band[slot] : -1.f;  // rows past the survivor count hold stale models
+            int count = 0, count_b = 0;
+            unsigned evals = 0;
+            for (long long t = grp; t < ntiles; t += NGROUP) {
+                TCS_TRACE((uint32_t)s, j, 0);
+                mbar_wait(t_full + (uint32_t)(3 * j + (int)sr) * 8u, sk);
+                TCS_TRACE((uint32_t)s, j, 1);
+                tc_fence_after();
+                uint32_t d0[32], d1[32], d2[32];
+                tmem_ld32_issue(taddr + j * TMEM_BUF_COLS, d0);
+                tmem_ld32_issue(taddr + j * TMEM_BUF_COLS + TN, d1);
+                tmem_ld32_issue(taddr + j * TMEM_BUF_COLS + 2 * TN, d2);
+                tmem_ld_wait3x32(d0, d1, d2);
+                // the tile is in this group's registers: hand the TMEM buffer back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + j * 8u);
+                TCS_TRACE((uint32_t)s, j, 2);
+                const int64_t col0 = (int64_t)c * BROWS + j * TN;
+                if (DUMP) {
+                    if (valid) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            float *o = dump + ((size_t)slot * n_pad + (col0 + k)) * 3;
+                            o[0] = __uint_as_float(d0[k]);
+                            o[1] = __uint_as_float(d1[k]);
+                            o[2] = __uint_as_float(d2[k]);
+                        }
+                    }
+                } else {
+                    u64 u[16];
+                    float mn = INFINITY;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const u64 e0 = pk2(d0[2 * k], d0[2 * k + 1]), e1 = pk2(d1[2 * k], d1[2 * k + 1]),
+                                  e2 = pk2(d2[2 * k], d2[2 * k + 1]);
+                        u[k] = fma2(e2, e2, fma2(e1, e1, fma2(e0, e0, nthr2p)));
+                        float ua, ub;
+                        upk2(u[k], ua, ub);
+                        count += (int)(__float_as_uint(ua) >> 31);      // two chains: the LEA.HI adds of a tile do not
+                        count_b += (int)(__float_as_uint(ub) >> 31);    // form one long dependency
+                        mn = min3abs(mn, ua, ub);
+                    }
+                    if (__any_sync(0xffffffffu, mn < delta)) {
+                        // rare: some residual of these 32 columns is within the error band of some hypothesis: the warp
+                        // records which (bit k: |u_k| < delta) and what the tensor-core sign said; decided in fp64 after
+                        // the warp's last tile (see the unwidened loop below for the why)
+                        unsigned bm = 0u, sg_bits = 0u;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            float ua, ub;
+                            upk2(u[k >> 1], ua, ub);
+                            const float uk = (k & 1) ? ub : ua;
+                            bm |= (fabsf(uk) < delta ? 1u : 0u) << k;
+                            sg_bits |= (__float_as_uint(uk) >> 31) << k;
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, bm != 0u);
+                        if (bm != 0u) {
+                            const unsigned e = ev_n + __popc(m & ((1u << lane) - 1u));
+                            if (e < ev_cap) ev_mine[e] = make_int4(slot, (int)col0, (int)bm, (int)sg_bits);
+                            else {  // list full: decide on the spot (same result, only slower)
+                                for (unsigned b = bm; b; b &= b - 1u) {
+                                    const int k = __ffs(b) - 1;
+                                    count += tc_exact_inlier(P8, col0 + k, m64 + (size_t)slot * 12, thr2) - (int)((sg_bits >> k) & 1u);
+                                    ++evals;
+                                }
+                            }
+                        }
+                        ev_n += __popc(m);
+                    }
+                }
+                TCS_TRACE((uint32_t)s, j, 3);
+                // advance three tiles: at most one stage further
+                j += NGROUP;
+                if (j >= TILES_PER_STAGE) {
+                    j -= TILES_PER_STAGE;
+                    ++s;
+                    if (++sr == 3u) {
+                        sr = 0u;
+                        sk ^= 1u;
+                    }
+                    if (++c == nchunks) {  // the next tile belongs to the next hypothesis block: flush this one's counts
+                        if (!DUMP && valid) {
+                            count += count_b;
+                            if (count) atomicAdd(&cnt[slot], count);
+                            if (evals) atomicAdd(n_rechecked, (unsigned long long)evals);
+                        }
+                        count = count_b = 0;
+                        evals = 0;
+                        c = 0;
+                        ++hb;
+                        slot = hb * TM + q * 32 + lane;
+                        valid = slot < nsurv;
+                        delta = valid ? band[slot] : -1.f;
+                    }
+                }
+            }
+            if (!DUMP && valid) {
+                count += count_b;
+                if (count) atomicAdd(&cnt[slot], count);
+                if (evals) atomicAdd(n_rechecked, (unsigned long long)evals);
+            }
+            if (!DUMP && ev_n) {
+                __syncwarp();
+                const unsigned ne = ev_n < ev_cap ? ev_n : ev_cap;
+                for (unsigned e = lane; e < ne; e += 32) {
+                    const int4 v = __ldcg(ev_mine + e);
+                    int d = 0;
+                    for (unsigned b = (unsigned)v.z; b; b &= b - 1u) {
+                        const int k = __ffs(b) - 1;
+                        d += tc_exact_inlier(P8, (int64_t)v.y + k, m64 + (size_t)v.x * 12, thr2) - (int)(((unsigned)v.w >> k) & 1u);
+                        ++evals_tail;
+                    }
+                    if (d) atomicAdd(&cnt[v.x], d);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) evals_tail += __shfl_xor_sync(0xffffffffu, evals_tail, o);
+                if (lane == 0 && evals_tail) atomicAdd(n_rechecked, (unsigned long long)evals_tail);
+            }
+        }
+#else
         // (Tried and dropped: 8-column units whose registers ping-pong so that the next tcgen05.ld is in flight while
         // the current unit is counted, with an early non-blocking probe of the next t_full phase -- 0.57 ms instead of
         // 0.36 ms at cfg 3: the longer serial code per slice cost more than the hidden latencies saved.)
@@ -686,6 +909,7 @@ k_score_tc(const uint4 *__restrict__ Aimg, const uint4 *__restrict__ Bimg, const
             for (int o = 16; o > 0; o >>= 1) evals_tail += __shfl_xor_sync(0xffffffffu, evals_tail, o);
             if (lane == 0 && evals_tail) atomicAdd(n_rechecked, (unsigned long long)evals_tail);
         }
+#endif
     }
 
     tc_fence_before();

@@ -40,7 +40,7 @@ res = {}
 for n in names:
     so = os.path.join(ROOT, "lidarregistration_b200/csrc/variants/lib_%s.so" % n)
     r = subprocess.run([sys.executable, "-c", CHILD], cwd=ROOT, env=dict(os.environ, LIDARREG_SO=so), capture_output=True, text=True,
-                       timeout=90)
+                       timeout=45)
     try:
         res[n] = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception:
