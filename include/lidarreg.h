@@ -300,6 +300,16 @@ int lr_seeds_score(const float *src, const float *tgt, int64_t n, const double *
                    int32_t *counts, uint8_t *labels, int64_t *best, int64_t *best_count, double *T_best,
                    double *T_refit, void *stream);
 
+/* ---- measurement switches (tools/, never needed by a caller) ------------------------------------------ */
+
+/* lr_ransac_rigid then generates and scores only rank's contiguous slice of every round, with no exchange: what ONE
+ * rank of a hypothesis-sharded run executes, measurable on a single GPU (tools/pair_breakdown.py).  (0, 1) = default. */
+int lr_debug_slice(int rank, int world);
+
+/* 0: launch the kernels of a run the ordinary, fully stream-ordered way instead of with programmatic dependent launch
+ * (tools/pdl_ab.py).  Results are identical either way. */
+int lr_debug_pdl(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ SYMBOLS = [
     "lr_prof_enable", "lr_prof_read", "lr_peak_fp32", "lr_match_set_mode", "lr_transform_pad8", "lr_icp_step", "lr_ransac_set_mode",
     "lr_comm_init", "lr_comm_connect", "lr_comm_info", "lr_comm_destroy", "lr_ransac_rigid_sharded", "lr_ransac_tc_probe",
     "lr_gpf_filter", "lr_icp_refine", "lr_nn3d_radius", "lr_kabsch_weighted_batch", "lr_seeds_score",
+    "lr_debug_slice", "lr_debug_pdl",
 ]
 
 
