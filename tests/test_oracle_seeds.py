@@ -80,6 +80,67 @@ def test_nn3d_radius_against_numpy():
     assert (idx[:50] == -1).all()
 
 
+def test_nn3d_radius_against_scipy_kdtree():
+    """an independent KD-tree (scipy's cKDTree, the role nanoflann plays inside Open3D's registration_icp) returns the
+    same neighbour inside the radius for every query of a LiDAR-shaped pair"""
+    from scipy.spatial import cKDTree
+    from lidarregistration_b200 import synthetic
+    p = synthetic.make_pair(6000, seed=123, overlap=0.7)
+    T = p["T_gt"].copy()
+    T[:3, 3] += [0.1, -0.05, 0.02]
+    idx, d2 = O.nn3d_radius(p["xyz0"], p["xyz1"], T, 0.6)
+    moved = p["xyz0"].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    dist, j = cKDTree(p["xyz1"].astype(np.float64)).query(moved, k=1, distance_upper_bound=0.6)
+    found = np.isfinite(dist)
+    # (scipy's bound is inclusive, the oracle's strict; no query sits exactly on the radius here)
+    assert np.array_equal(found, idx >= 0)
+    same = idx[found] == j[found]
+    # a different index is only acceptable for an exact tie in distance
+    assert np.allclose(np.sqrt(d2[found][~same]), dist[found][~same], rtol=0, atol=1e-12)
+    assert same.mean() > 0.999
+    assert np.allclose(np.sqrt(d2[found]), dist[found], atol=1e-9)
+
+
+def test_icp_against_independent_kdtree_svd_icp():
+    """the whole refinement against a second, independent statement of Open3D's loop: scipy cKDTree for the
+    correspondences, numpy SVD (R = V diag(1, 1, det) U^T) for the point-to-point update, the same relative
+    fitness / rmse stopping rule"""
+    from scipy.spatial import cKDTree
+    from lidarregistration_b200 import synthetic
+    p = synthetic.make_pair(5000, seed=321, overlap=0.8)
+    src, tgt = p["xyz0"].astype(np.float64), p["xyz1"].astype(np.float64)
+    T0 = p["T_gt"].copy()
+    T0[:3, 3] += [0.2, -0.15, 0.05]
+    tree = cKDTree(tgt)
+
+    def evaluate(T):
+        moved = src @ T[:3, :3].T + T[:3, 3]
+        dist, j = tree.query(moved, k=1, distance_upper_bound=0.6)
+        keep = np.isfinite(dist)
+        a, b = src[keep], tgt[j[keep]]
+        ca, cb = a.mean(0), b.mean(0)
+        U, _, Vt = np.linalg.svd((a - ca).T @ (b - cb))
+        D = np.diag([1.0, 1.0, np.linalg.det(Vt.T @ U.T)])
+        R = Vt.T @ D @ U.T
+        Tn = np.eye(4)
+        Tn[:3, :3], Tn[:3, 3] = R, cb - R @ ca
+        return Tn, keep.sum() / len(src), float(np.sqrt((dist[keep] ** 2).mean()))
+
+    T = T0
+    Tn, fit, rmse = evaluate(T)
+    it = 0
+    for it in range(1, 31):
+        T = Tn
+        Tn, f2, r2 = evaluate(T)
+        done = abs(fit - f2) < 1e-6 and abs(rmse - r2) < 1e-6
+        fit, rmse = f2, r2
+        if done:
+            break
+    To, fo, ro, ito = O.icp(p["xyz0"], p["xyz1"], 0.6, T0)
+    assert ito == it and abs(fo - fit) < 1e-12 and abs(ro - rmse) < 1e-9
+    assert np.abs(To - T).max() < 1e-8
+
+
 def test_icp_oracle_converges():
     from lidarregistration_b200 import synthetic
     p = synthetic.make_pair(4000, 4000, seed=77, overlap=0.7)
