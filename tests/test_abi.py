@@ -116,3 +116,29 @@ def test_mode_switches_validate_their_argument():
     assert L.lr_match_set_mode(0) == 0
     assert L.lr_match_set_mode(99) != 0 and len(L.lr_last_error()) > 0
     assert L.lr_match_set_mode(0) == 0
+
+
+def test_f4_entries_validate_their_arguments_before_touching_the_device():
+    """lr_icp_refine / lr_nn3d_radius / lr_seeds_score / lr_kabsch_weighted_batch and the measurement switches: bad
+    arguments come back as LR_ERR_ARG with a message (checked before any CUDA call, so this runs without a GPU)"""
+    import ctypes
+    from lidarregistration_b200 import _lib
+    L = _lib.lib()
+    T = (ctypes.c_double * 16)()
+    i64, dbl = ctypes.c_int64, ctypes.c_double
+    buf = ctypes.c_void_p(0x1000)  # never dereferenced: the calls below fail their argument checks first
+    assert L.lr_icp_refine(buf, i64(10), buf, i64(10), dbl(0.0), None, 30, dbl(1e-6), dbl(1e-6), T, None, None, None, None) == 1
+    assert b"max_dist" in L.lr_last_error()
+    assert L.lr_icp_refine(buf, i64(10), buf, i64(10), dbl(0.6), None, -1, dbl(1e-6), dbl(1e-6), T, None, None, None, None) == 1
+    assert L.lr_icp_refine(buf, i64(10), buf, i64(10), dbl(0.6), None, 30, dbl(1e-6), dbl(1e-6), None, None, None, None, None) == 1
+    assert b"T_out" in L.lr_last_error()
+    assert L.lr_nn3d_radius(buf, i64(10), buf, i64(10), None, dbl(-1.0), buf, None, None) == 1 and b"radius" in L.lr_last_error()
+    assert L.lr_nn3d_radius(buf, i64(-3), buf, i64(10), None, dbl(0.6), buf, None, None) == 1
+    assert L.lr_seeds_score(buf, buf, i64(0), buf, i64(5), dbl(0.6), None, None, None, None, T, None, None) == 1
+    assert L.lr_seeds_score(buf, buf, i64(100), buf, i64((1 << 20) + 1), dbl(0.6), None, None, None, None, T, None, None) == 1
+    assert L.lr_seeds_score(buf, buf, i64(100), buf, i64(5), dbl(0.0), None, None, None, None, T, None, None) == 1
+    assert L.lr_seeds_score(buf, buf, i64(100), None, i64(5), dbl(0.6), None, None, None, None, T, None, None) == 1
+    assert L.lr_kabsch_weighted_batch(buf, buf, None, i64(-1), 4, buf, None) == 1
+    assert L.lr_kabsch_weighted_batch(buf, buf, None, i64(0), 4, None, None) == 0   # nothing to do
+    assert L.lr_debug_slice(0, 1) == 0 and L.lr_debug_slice(3, 2) == 1 and L.lr_debug_slice(0, 0) == 1
+    assert L.lr_debug_pdl(0) == 0 and L.lr_debug_pdl(1) == 0
