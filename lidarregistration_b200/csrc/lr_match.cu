@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(kCompactBlock)
 k_mutual_count(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev, int64_t N, int64_t M,
                int *__restrict__ block_cnt)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     __shared__ int warp_tot[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int64_t j;
@@ -301,6 +303,8 @@ k_mutual_count(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev
 __global__ void __launch_bounds__(1024)
 k_block_scan(int *__restrict__ block_cnt, int nblocks, int64_t *__restrict__ K)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -334,6 +338,8 @@ __global__ void __launch_bounds__(kCompactBlock)
 k_mutual_scatter(const int64_t *__restrict__ idx1, const int64_t *__restrict__ rev, int64_t N, int64_t M,
                  const int *__restrict__ block_off, int64_t *__restrict__ out_i, int64_t *__restrict__ out_j)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     __shared__ int warp_tot[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i = blockIdx.x * (int64_t)kCompactBlock + threadIdx.x;
@@ -515,9 +521,9 @@ LR_EXPORT int lr_match_mutual(const float *f0, int64_t N, const float *f1, int64
         rc = nn_sweep(f1, M, f0, N, D, rev, nullptr, scratch + rev_bytes, st);
     }
     if (rc) return rc;
-    k_mutual_count<<<nblocks, kCompactBlock, 0, st>>>(idx1, rev, N, M, block_cnt);
-    k_block_scan<<<1, 1024, 0, st>>>(block_cnt, nblocks, K);
-    k_mutual_scatter<<<nblocks, kCompactBlock, 0, st>>>(idx1, rev, N, M, block_cnt, out_i, out_j);
+    LR_CUDA_TRY(lr::launch_pdl(k_mutual_count, dim3(nblocks), dim3(kCompactBlock), 0, st, idx1, rev, N, M, block_cnt));
+    LR_CUDA_TRY(lr::launch_pdl(k_block_scan, dim3(1), dim3(1024), 0, st, block_cnt, nblocks, K));
+    LR_CUDA_TRY(lr::launch_pdl(k_mutual_scatter, dim3(nblocks), dim3(kCompactBlock), 0, st, idx1, rev, N, M, block_cnt, out_i, out_j));
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }

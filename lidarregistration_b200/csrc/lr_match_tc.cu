@@ -231,6 +231,8 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32])
 // ---------------------------------------------------------------- operand preparation
 __global__ void k_params_reset(Params *p)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         p->maxn0_bits = 0u;
         p->maxn1_bits = 0u;
@@ -267,6 +269,8 @@ __device__ __forceinline__ float sqnorm32_canonical(const float *__restrict__ f)
 __global__ void k_sqnorms_both(const float *__restrict__ F0, int64_t N, float *__restrict__ out0, const float *__restrict__ F1,
                                int64_t M, float *__restrict__ out1, int nb0, Params *p)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     const bool second = (int)blockIdx.x >= nb0;
     const float *F = second ? F1 : F0;
     const int64_t n = second ? M : N;
@@ -342,6 +346,8 @@ __global__ void k_prep16(const float *__restrict__ F0, const float *__restrict__
                          uint4 *__restrict__ out0, const float *__restrict__ F1, const float *__restrict__ nsq1, int64_t N1,
                          int64_t n_pad1, uint4 *__restrict__ out1, int nb0, Params *p)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     const bool second = (int)blockIdx.x >= nb0;
     const float *F = second ? F1 : F0, *nsq = second ? nsq1 : nsq0;
     const int64_t N = second ? N1 : N0, n_pad = second ? n_pad1 : n_pad0;
@@ -606,6 +612,10 @@ k_nn_tc(const uint4 *__restrict__ Aop, const uint4 *__restrict__ Bop, int64_t N,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm->tmem_base;
+    // programmatic dependent launch: barrier init, TMEM allocation and the shared-memory reset above ran while the
+    // kernel before this one (operand preparation / the other direction's merge) was draining; its results are read from here on
+    lr::pdl_wait();
+    lr::pdl_launch();
 
     if (warp == WARP_PRODUCER) {
         // ===== producer: bulk-TMA copies of operand tiles =====
@@ -928,6 +938,8 @@ k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float
          const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, Params *p, int *__restrict__ ovf_rows,
          int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;  // warp-uniform
@@ -1040,6 +1052,8 @@ k_row_exact(const float *__restrict__ F0, const float *__restrict__ F1, const fl
             const float *__restrict__ n1, int64_t M, const Params *__restrict__ p, const int *__restrict__ ovf_rows,
             Top2 *__restrict__ partial, int64_t partial_cap)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     __shared__ Top2 sh[256];
     __shared__ float a[32];
     const int novf = p->ovf_count;
@@ -1084,6 +1098,8 @@ __global__ void __launch_bounds__(1024)
 k_row_merge(Params *__restrict__ p, const int *__restrict__ ovf_rows, const Top2 *__restrict__ partial,
             int64_t partial_cap, int64_t *__restrict__ idx1, int64_t *__restrict__ idx2)
 {
+    lr::pdl_wait();
+    lr::pdl_launch();
     const int novf = p->ovf_count;
     const int nseg = ovf_segments(novf, partial_cap);
     for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < novf; o += gridDim.x * blockDim.x) {
@@ -1140,11 +1156,12 @@ int prepare(const float *f0, int64_t N, const float *f1, int64_t M, char *scratc
     P.ovf_rows = cv.take<int>(mx);
     P.partial = cv.take<char>(sizeof(Top2) * partial_cap(mx));
     P.partial_cap = partial_cap(mx);
-    k_params_reset<<<1, 32, 0, st>>>(P.params);
+    LR_CUDA_TRY(lr::launch_pdl(k_params_reset, dim3(1), dim3(32), 0, st, P.params));
     const int nbs0 = (int)((N + 255) / 256), nbs1 = (int)((M + 255) / 256);
-    k_sqnorms_both<<<nbs0 + nbs1, 256, 0, st>>>(f0, N, P.n0, f1, M, P.n1, nbs0, P.params);
+    LR_CUDA_TRY(lr::launch_pdl(k_sqnorms_both, dim3(nbs0 + nbs1), dim3(256), 0, st, f0, N, P.n0, f1, M, P.n1, nbs0, P.params));
     const int nbp0 = (int)((P.pad0 * 8 + 255) / 256), nbp1 = (int)((P.pad1 * 8 + 255) / 256);
-    k_prep16<<<nbp0 + nbp1, 256, 0, st>>>(f0, P.n0, N, P.pad0, P.op0, f1, P.n1, M, P.pad1, P.op1, nbp0, P.params);
+    LR_CUDA_TRY(lr::launch_pdl(k_prep16, dim3(nbp0 + nbp1), dim3(256), 0, st, f0, P.n0, N, P.pad0, P.op0, f1, P.n1, M, P.pad1, P.op1, nbp0,
+                               P.params));
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
@@ -1202,8 +1219,8 @@ int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, 
     const int tok = lr::prof_begin(lr::PROF_NN, st);
     auto launch = [&](auto kern) -> int {
         LR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NTHREADS, smem, st>>>(opa, opb, Na, Nb, n_rowblocks, n_coltiles, sc, P.params, swap ? 1 : 0, seed_cfg, P.cand,
-                                           P.cand_cnt);
+        LR_CUDA_TRY(lr::launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, st, opa, opb, Na, Nb, n_rowblocks, n_coltiles, sc,
+                                   P.params, swap ? 1 : 0, seed_cfg, P.cand, P.cand_cnt));
         return LR_OK;
     };
     int lrc;
@@ -1214,12 +1231,12 @@ int sweep(const Prepared &P, bool swap, bool acc16, const float *f0, int64_t N, 
 #ifdef LR_TC_TIMING
     g_last = P; g_last_regions = nsplit * NGROUPS; g_last_rows = Na;
 #endif
-    k_rerank<<<(unsigned)((Na + 7) / 8), 256, 0, st>>>(fa, fb, na, nb, Na, Nb, nsplit * NGROUPS, acc16, swap ? 1 : 0, P.cand, P.cand_cnt,
-                                                       P.params, P.ovf_rows, idx1, idx2);
-    k_row_exact<<<sms * 2, 256, 0, st>>>(fa, fb, na, nb, Nb, P.params, P.ovf_rows, reinterpret_cast<Top2 *>(P.partial),
-                                         P.partial_cap);
-    k_row_merge<<<1, 1024, 0, st>>>(P.params, P.ovf_rows, reinterpret_cast<const Top2 *>(P.partial), P.partial_cap, idx1,
-                                   idx2);
+    LR_CUDA_TRY(lr::launch_pdl(k_rerank, dim3((unsigned)((Na + 7) / 8)), dim3(256), 0, st, fa, fb, na, nb, Na, Nb, nsplit * NGROUPS,
+                               acc16, swap ? 1 : 0, P.cand, P.cand_cnt, P.params, P.ovf_rows, idx1, idx2));
+    LR_CUDA_TRY(lr::launch_pdl(k_row_exact, dim3(sms * 2), dim3(256), 0, st, fa, fb, na, nb, Nb, P.params, P.ovf_rows,
+                               reinterpret_cast<Top2 *>(P.partial), P.partial_cap));
+    LR_CUDA_TRY(lr::launch_pdl(k_row_merge, dim3(1), dim3(1024), 0, st, P.params, P.ovf_rows,
+                               reinterpret_cast<const Top2 *>(P.partial), P.partial_cap, idx1, idx2));
     LR_CUDA_TRY(cudaGetLastError());
     return LR_OK;
 }
