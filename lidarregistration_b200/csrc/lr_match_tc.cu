@@ -932,7 +932,12 @@ __device__ __forceinline__ void warp_lexmin(float &s, int &j)
 // cut: only events within beta of it can hold a (second) nearest neighbour -- on cfg 2 about 1.2 of the
 // ~3.4 events a row records.  Their 32 columns (lane = column) are evaluated with the canonical fp32
 // expression; per-lane lexicographic top-2, merged by shuffles.
-__global__ void __launch_bounds__(256)
+// (four resident blocks per SM = 64 registers: the kernel is a chain of dependent loads per row -- counts, events, target
+// rows -- and 32 instead of 24 warps per SM in flight cut find_nn by 5.7 %; five blocks = 48 registers spill and lose it again)
+#ifndef LR_RERANK_MINB
+#define LR_RERANK_MINB 4
+#endif
+__global__ void __launch_bounds__(256, LR_RERANK_MINB)
 k_rerank(const float *__restrict__ F0, const float *__restrict__ F1, const float *__restrict__ n0,
          const float *__restrict__ n1, int64_t N, int64_t M, int nregions, bool acc16, int role,
          const int2 *__restrict__ cand, const int *__restrict__ cand_cnt, Params *p, int *__restrict__ ovf_rows,
