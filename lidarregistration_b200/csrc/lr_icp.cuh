@@ -209,7 +209,10 @@ __global__ void k_icp_begin(IcpCtl *c, const double *T12)
 
 // evaluation e of the refinement (e = 0: the initial transform): correspondences of c->T, their count / squared error,
 // Kabsch over them (fixed-order two-stage reduction as k_finish), Open3D's stopping rule in the last block
-__global__ void __launch_bounds__(256)
+#ifndef LR_ICP_MINB
+#define LR_ICP_MINB 3   // 80 registers, three blocks per SM: the search is a chain of dependent loads (0.756 -> 0.702 ms per 25k-point pair)
+#endif
+__global__ void __launch_bounds__(256, LR_ICP_MINB)
 k_icp_eval(const float *__restrict__ src, int64_t n, const float *__restrict__ tgt, Grid g, double r2, IcpCtl *c,
            double *__restrict__ partial, int e, double rel_fitness, double rel_rmse)
 {
